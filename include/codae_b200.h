@@ -1,0 +1,188 @@
+/*
+ * codae_b200.h -- C ABI of libcodae_b200.so: the B200 (sm_100a) implementation of CODAE's
+ * data-parallel hot path (denoising-autoencoder training step + complementarity inference).
+ *
+ * The reference (victordeleau/MUI-DeepAutoEncoder) is pure Python on stock PyTorch: it has no FFI.
+ * Its "plugin boundary" for this path is the set of library calls its Python makes on device
+ * tensors.  Each entry point below names the reference call site (paths relative to the reference
+ * root) whose device work it replaces.  INTEGRATION.md shows the ctypes stub a maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer borrowed from the caller (PyTorch allocations); the
+ *     library never frees or keeps them.  `stream` is a cudaStream_t passed as void*.
+ *   - all matrices are row-major; `ld*` is the row pitch in ELEMENTS.  Tensor-core paths need
+ *     pitches that are multiples of 16 bytes (the caller pads; see *_EINVAL).
+ *   - every call is asynchronous on `stream`, allocates nothing and never synchronises the host,
+ *     so a whole training step can be captured into a CUDA graph.
+ *   - return value: 0 or a negative CODAE_E* code; text via codae_last_error().  Nothing aborts,
+ *     nothing throws, and there is no CPU or non-sm_100 fallback (CODAE_EARCH instead).
+ *   - reductions use fixed trees: results are bitwise reproducible run to run for fixed shapes.
+ */
+#ifndef CODAE_B200_H
+#define CODAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CODAE_VERSION 100 /* 0.1.0 */
+
+typedef struct codae_ctx codae_ctx;
+
+enum codae_status { CODAE_OK = 0, CODAE_EINVAL = -1, CODAE_EARCH = -2, CODAE_ECUDA = -3, CODAE_ENOMEM = -4 };
+enum codae_dtype { CODAE_F32 = 0, CODAE_BF16 = 1 };
+enum codae_act { CODAE_ACT_NONE = 0, CODAE_ACT_RELU = 1 };
+enum codae_metric { CODAE_METRIC_SQERR = 0, CODAE_METRIC_COSINE = 1 };
+enum codae_vartype { CODAE_VAR_REGRESSION = 0, CODAE_VAR_CLASSIFICATION = 1 };
+/* GEMM engines (a shape/dtype specialisation chosen by the library, reported for tests/bench) */
+enum codae_engine { CODAE_ENGINE_SIMT_F32 = 0, CODAE_ENGINE_TCGEN05_BF16 = 1 };
+
+/* ---- context ------------------------------------------------------------------------------ */
+int codae_version(void);
+/* Binds to `device`; fails with CODAE_EARCH unless it is compute capability 10.x. */
+int codae_ctx_create(int device, codae_ctx** out);
+int codae_ctx_destroy(codae_ctx* ctx);
+const char* codae_last_error(const codae_ctx* ctx); /* ctx may be NULL: last process-wide error */
+int codae_ctx_sm_count(const codae_ctx* ctx);
+/* Which engine codae_linear_* will use for (dtype, M, N, K). */
+int codae_linear_engine(const codae_ctx* ctx, int dtype, int M, int N, int K);
+
+/* ---- K1: corruption ------------------------------------------------------------------------ */
+/* Replaces the un-seeded `random.sample` draw of Corrupter.mask_to_use
+ * (codae/tool/data_tool.py:222-226) by a Philox4x32-10 stream: out[i, :] (int16 [n_obs, nb_run]) is a
+ * permutation of range(nb_run) that depends only on (seed, first_obs + i).  nb_run <= 1024. */
+int codae_mask_table_philox(codae_ctx* ctx, uint64_t seed, int64_t first_obs, int64_t n_obs, int nb_run,
+                            int16_t* out, void* stream);
+
+/* Fused batch gather + slot-mask corruption.  Replaces collate_embedding's torch.stack
+ * (codae/tool/data_tool.py:96-103), Corrupter.get_masks (data_tool.py:239-262) and model.corrupt
+ * (codae/model/embedding_denoising_autoencoder.py:226-239).
+ *   data      [n_rows, ld_data] f32   resident dataset (ConcatenatedEmbeddingDataset.data)
+ *   batch_idx [B] int64 or NULL       observation ids (NULL: observations 0..B-1)
+ *   mask_table[n_rows, nb_run] int16  mask id of (observation, run)
+ *   mask_bits [nb_run] u64            bit v set <=> variable v is zeroed by that mask (V <= 64)
+ *   col_var   [io] u8                 variable index of every column
+ *   out_cx    [B, ld_cx] f32|bf16     x * mask (a multiply: -0.0 / NaN propagate like the reference)
+ *   out_x     [B, ld_x] f32 or NULL   gathered clean rows
+ *   out_mask_id [B] int32 or NULL     mask id applied to every row                              */
+int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t ld_data, const int64_t* batch_idx, int B,
+                      const int16_t* mask_table, int nb_run, int run, const uint64_t* mask_bits,
+                      const uint8_t* col_var, int io, void* out_cx, int cx_dtype, int64_t ld_cx, float* out_x,
+                      int64_t ld_x, int32_t* out_mask_id, void* stream);
+
+/* Dense masks for the legacy API: Corrupter.get_masks (data_tool.py:239-262).
+ *   out_masks [k_max, B, io] f32 (row i of plane k-1 holds the mask iff its subset has k variables)
+ *   out_fmask [B, io] f32 = sum over k.  nb_missing [nb_run] u8.                                */
+int codae_dense_masks(codae_ctx* ctx, const int64_t* batch_idx, int B, const int16_t* mask_table, int nb_run,
+                      int run, const uint64_t* mask_bits, const uint8_t* nb_missing, const uint8_t* col_var, int io,
+                      int k_max, float* out_masks, float* out_fmask, void* stream);
+
+/* out = x * mask, elementwise over n floats: model.corrupt for caller-supplied dense masks
+ * (embedding_denoising_autoencoder.py:239, mixed_variable_denoising_autoencoder.py:262). */
+int codae_mul_mask(codae_ctx* ctx, const float* x, const float* mask, float* out, int64_t n, void* stream);
+
+/* ---- K1-loss: reconstruction loss, its gradient and the monitors ------------------------------ */
+/* MSELoss("mean")(x, y) forward + backward and the host-side monitor sums, in one pass.
+ * Replaces script/train_dae_on_embedding.py:206 (loss), :210 (first backward node) and
+ * :217-223 (full / partial error sums, there computed on the host after two D2H copies).
+ *   x        clean rows: x[i, :] = data[batch_idx ? batch_idx[i] : i, :]   (f32, pitch ld_x)
+ *   y        [B, ld_y] f32|bf16 reconstructions
+ *   mask_id  [B] int32 (from codae_corrupt_fwd); mask_bits/col_var as above
+ *   dy       [B, ld_dy] f32|bf16 or NULL:  grad_scale * (y - x)   (grad_scale = 2 / (B_global * io))
+ *   acc      double[4]:  acc[0] += sum (x-y)^2 ; acc[1] += sum (1-m)(x-y)^2 ; acc[2] += B ;
+ *                        acc[3]  = this call's sum (x-y)^2  (loss = acc[3] / (B*io))
+ *   workspace >= codae_loss_workspace_bytes()                                                     */
+size_t codae_loss_workspace_bytes(const codae_ctx* ctx);
+int codae_mse_loss_fwd_bwd(codae_ctx* ctx, const float* x, int64_t ld_x, const int64_t* batch_idx, const void* y,
+                           int y_dtype, int64_t ld_y, const int32_t* mask_id, const uint64_t* mask_bits,
+                           const uint8_t* col_var, int B, int io, float grad_scale, void* dy, int dy_dtype,
+                           int64_t ld_dy, double* acc, void* workspace, size_t ws_bytes, void* stream);
+
+/* CombinedCriterion(reduction="mean") forward + backward (codae/tool/metering.py:155-180;
+ * script/train_dae_on_abalone.py:215,219).  Per-variable RMSE over the batch / softmax-NLL, weighted.
+ *   var_pos/var_size/var_type [V] int32 ; weight [V] f32 ; x,y [B, ld] f32 ; dy [B, ld] f32
+ *   loss_out: float[1 + V] = {loss, l_0 .. l_{V-1}}.  Single-CTA kernel: meant for tabular widths. */
+int codae_mixed_loss_fwd_bwd(codae_ctx* ctx, const float* x, const float* y, int B, int io, int64_t ld, int V,
+                             const int32_t* var_pos, const int32_t* var_size, const int32_t* var_type,
+                             const float* weight, float* dy, float* loss_out, void* stream);
+
+/* Monitor pass of the abalone loop (train_dae_on_abalone.py:227-236): Normalizer.undo on columns
+ * [norm_first, io) (data_tool.py:80-90), CombinedCriterion(reduction="none") (metering.py:131-152),
+ * get_per_k / get_partial (metering.py:187-204), accumulated on the device.
+ *   out_loss [B, V] f32 (required; the as_numpy matrix, also the kernel's staging buffer)
+ *   acc double[2 + 2*k_max*V]: {ftl, ptl, ftl_per_k[k_max][V], ptl_per_k[k_max][V]}  (+=)            */
+int codae_mixed_monitor(codae_ctx* ctx, const float* x, const float* y, int B, int io, int64_t ld, int V,
+                        const int32_t* var_pos, const int32_t* var_size, const int32_t* var_type,
+                        const float* norm_scale, const float* norm_min, int norm_first, const int32_t* mask_id,
+                        const uint64_t* mask_bits, const uint8_t* nb_missing, int k_max, float* out_loss, double* acc,
+                        void* stream);
+
+/* ---- K2: encoder / decoder contractions ------------------------------------------------------- */
+/* dtype = CODAE_F32 : operands and outputs f32 (exact-fp32 engine).
+ * dtype = CODAE_BF16: X, W, dY bf16 operands, fp32 accumulation on tcgen05 tensor cores; the output type
+ *                     is `out_dtype`.  M = batch rows, N = out features, K = in features.
+ * Y[M,N] = act(X[M,K] . W[N,K]^T + bias[N])      nn.Linear forward + ReLU(inplace)
+ *                                                (embedding_denoising_autoencoder.py:63-129,166,183)   */
+int codae_linear_fwd(codae_ctx* ctx, const void* X, int64_t ldx, const void* W, int64_t ldw, const float* bias,
+                     void* Y, int64_t ldy, int M, int N, int K, int act, int dtype, int out_dtype, void* stream);
+/* dX[M,K] = (dY[M,N] . W[N,K]) * (A_prev > 0 ? 1 : 0)   autograd's mm + threshold_backward for loss.backward()
+ * (train_dae_on_embedding.py:210).  A_prev [M,K] = this layer's input (post-ReLU output of the previous
+ * layer), same dtype as the operands, or NULL when the previous layer has no ReLU.                       */
+int codae_linear_dgrad(codae_ctx* ctx, const void* dY, int64_t lddy, const void* W, int64_t ldw, const void* A_prev,
+                       int64_t lda, void* dX, int64_t lddx, int M, int N, int K, int dtype, int out_dtype,
+                       void* stream);
+/* dW[N,K] = dY[M,N]^T . X[M,K]  (f32 out, pitch lddw) and db[N] = column sums of dY (f32).
+ * The weight/bias gradient of nn.Linear in loss.backward().                                           */
+int codae_linear_wgrad(codae_ctx* ctx, const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW,
+                       int64_t lddw, float* db, int M, int N, int K, int dtype, void* stream);
+/* f32 -> bf16 copy of n elements (weight shadow / activation cast). */
+int codae_cast_bf16(codae_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
+
+/* ---- K4: clip_grad_norm_ + Adam over flat buffers ----------------------------------------------- */
+/* out_sqnorm (f32[1]) = sum g^2 over the flat gradient buffer: clip_grad_norm_(params, 1)
+ * (train_dae_on_embedding.py:212-213).  workspace >= codae_sqnorm_workspace_bytes().          */
+size_t codae_sqnorm_workspace_bytes(const codae_ctx* ctx);
+int codae_grad_sqnorm(codae_ctx* ctx, const float* g, int64_t n, float* out_sqnorm, void* workspace,
+                      size_t ws_bytes, void* stream);
+/* torch.optim.Adam(lr, weight_decay).step() with the clip scale folded in (train_dae_on_embedding.py:
+ * 160-163,215).  g_eff = g * grad_scale * min(1, max_norm / (sqrt(sqnorm)*grad_scale + 1e-6));
+ * g_eff += wd*p ; m = lerp(m, g_eff, 1-b1) ; v = b2*v + (1-b2) g_eff^2 ;
+ * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+ *   max_norm < 0 or sqnorm == NULL: no clipping.  p_bf16 (or NULL): bf16 shadow of p, rewritten.
+ *   Hyper-parameters are doubles: the bias corrections are derived in double like torch's Python code,
+ *   then rounded to f32 once.  `step` is 1-based; step_dev (device int32, or NULL) overrides it so that a
+ *   captured CUDA graph can advance the step count without new scalar arguments.                       */
+int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
+                    double lr, double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
+                    const float* sqnorm, double grad_scale, const int32_t* step_dev, void* stream);
+/* *counter += delta on the device (the Adam step counter of a CUDA-graph-captured training step). */
+int codae_counter_add(codae_ctx* ctx, int32_t* counter, int delta, void* stream);
+
+/* ---- K3: complementarity inference -------------------------------------------------------------- */
+/* Scores every row of a catalog shard against Q query vectors and keeps the best k per query.
+ * Generalises RankingLoss.get (codae/tool/metering.py:46-79) into the stage-IV entry point the README
+ * names (README.md:14-16,30-32; script absent from the reference).
+ *   catalog [n_rows, ld] f32|bf16 ; query [Q, E] f32 ; score_j = sum_d (q_d - cat_jd * inv_scale)^2
+ *   (SQERR, lower is better) or cosine similarity (higher is better; metering.py:67-69).
+ *   out_score [Q, k] f32, out_idx [Q, k] int64 = row_offset + local row; sorted best first,
+ *   ties -> lower index.  Unused slots (n_rows < k): idx = -1.  1 <= k <= 128, E <= 4096, E % 4 == 0.  */
+size_t codae_score_topk_workspace_bytes(const codae_ctx* ctx, int Q, int k);
+int codae_score_topk(codae_ctx* ctx, const void* catalog, int cat_dtype, int64_t n_rows, int64_t ld, int E,
+                     int64_t row_offset, const float* query, int Q, float inv_scale, int metric, int k,
+                     float* out_score, int64_t* out_idx, void* workspace, size_t ws_bytes, void* stream);
+/* Deterministic merge of G per-shard lists [G, Q, k] (e.g. after an all-gather) into [Q, k]. */
+int codae_topk_merge(codae_ctx* ctx, const float* scores, const int64_t* idx, int G, int Q, int k, int metric,
+                     float* out_score, int64_t* out_idx, void* stream);
+/* out_rank[q] = #{ j in subset : score(true_idx[q]) strictly better than score(j) } -- the rank inside
+ * RankingLoss.get (metering.py:72-75).  subset_idx int64 [n_subset] or NULL (all rows).  Q <= 1024.   */
+int codae_score_rank(codae_ctx* ctx, const void* catalog, int cat_dtype, int64_t n_rows, int64_t ld, int E,
+                     const float* query, int Q, float inv_scale, int metric, const int64_t* true_idx,
+                     const int64_t* subset_idx, int64_t n_subset, int64_t* out_rank, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CODAE_B200_H */

@@ -1,0 +1,263 @@
+"""ctypes binding of libcodae_b200.so (the C ABI declared in include/codae_b200.h).
+
+PyTorch is only the plumbing here: it owns device memory and streams; every hot-path operation goes
+through the C ABI with raw device pointers.  There is no CPU or eager-PyTorch fallback: importing
+this module without the built library, or calling an op without a B200, raises.
+"""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_lib", "libcodae_b200.so")
+
+OK, EINVAL, EARCH, ECUDA, ENOMEM = 0, -1, -2, -3, -4
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU = 0, 1
+METRIC_SQERR, METRIC_COSINE = 0, 1
+VAR_REGRESSION, VAR_CLASSIFICATION = 0, 1
+ENGINE_SIMT_F32, ENGINE_TCGEN05_BF16 = 0, 1
+
+_c = ctypes
+_vp, _i, _i64, _u64, _f, _d, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64, _c.c_float, _c.c_double, _c.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/codae_b200.h (tests/test_abi.py checks)
+SIGNATURES = {
+    "codae_version": (_i, []),
+    "codae_ctx_create": (_i, [_i, _c.POINTER(_vp)]),
+    "codae_ctx_destroy": (_i, [_vp]),
+    "codae_last_error": (_c.c_char_p, [_vp]),
+    "codae_ctx_sm_count": (_i, [_vp]),
+    "codae_linear_engine": (_i, [_vp, _i, _i, _i, _i]),
+    "codae_mask_table_philox": (_i, [_vp, _u64, _i64, _i64, _i, _vp, _vp]),
+    "codae_corrupt_fwd": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i64, _vp, _i64, _vp, _vp]),
+    "codae_dense_masks": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "codae_mul_mask": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "codae_loss_workspace_bytes": (_sz, [_vp]),
+    "codae_mse_loss_fwd_bwd": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i64, _vp, _vp, _vp, _i, _i, _f, _vp, _i, _i64, _vp, _vp, _sz, _vp]),
+    "codae_mixed_loss_fwd_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "codae_mixed_monitor": (_i, [_vp, _vp, _vp, _i, _i, _i64, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "codae_linear_fwd": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
+    "codae_linear_dgrad": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "codae_linear_wgrad": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
+    "codae_cast_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "codae_sqnorm_workspace_bytes": (_sz, [_vp]),
+    "codae_grad_sqnorm": (_i, [_vp, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "codae_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _d, _vp, _vp]),
+    "codae_counter_add": (_i, [_vp, _vp, _i, _vp]),
+    "codae_score_topk_workspace_bytes": (_sz, [_vp, _i, _i]),
+    "codae_score_topk": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "codae_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "codae_score_rank": (_i, [_vp, _vp, _i, _i64, _i64, _i, _vp, _i, _f, _i, _vp, _vp, _i64, _vp, _vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+_ctxs = {}
+
+
+def lib():
+    """The loaded shared library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        "libcodae_b200.so is not built (%s). Run `python __graft_entry__.py` or "
+                        "`make -C mui-deepautoencoder_b200/csrc`. There is no CPU fallback." % LIB_PATH)
+                l = ctypes.CDLL(LIB_PATH)
+                for name, (res, args) in SIGNATURES.items():
+                    fn = getattr(l, name)
+                    fn.restype = res
+                    fn.argtypes = args
+                _lib = l
+    return _lib
+
+
+def ctx(device=None):
+    """codae_ctx* for a CUDA device (one per process and device)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("codae: no CUDA device; the B200 path has no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    if dev is None:
+        dev = torch.cuda.current_device()
+    c = _ctxs.get(dev)
+    if c is None:
+        with _lock:
+            c = _ctxs.get(dev)
+            if c is None:
+                out = _vp()
+                rc = lib().codae_ctx_create(dev, ctypes.byref(out))
+                if rc != OK:
+                    raise RuntimeError("codae_ctx_create failed (%d): %s" % (rc, (lib().codae_last_error(None) or b"").decode()))
+                c = out
+                _ctxs[dev] = c
+    return c
+
+
+def check(rc, c):
+    if rc != OK:
+        raise RuntimeError("libcodae_b200 error %d: %s" % (rc, (lib().codae_last_error(c) or b"").decode()))
+
+
+def p(t):
+    """Raw device pointer of a tensor (or NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("codae: unsupported dtype %s" % t.dtype)
+
+
+def _dev_check(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("codae: tensor is not on a CUDA device; the B200 path has no CPU fallback")
+
+
+# ---- thin typed wrappers (tensor in, kernel launch on the current stream) ---------------------------
+
+def mask_table_philox(seed, first_obs, n_obs, nb_run, device):
+    out = torch.empty((n_obs, nb_run), dtype=torch.int16, device=device)
+    c = ctx(device)
+    check(lib().codae_mask_table_philox(c, seed & 0xFFFFFFFFFFFFFFFF, first_obs, n_obs, nb_run, p(out), stream()), c)
+    return out
+
+
+def corrupt_fwd(data, batch_idx, B, mask_table, run, mask_bits, col_var, io, out_cx, out_x=None, out_mask_id=None):
+    _dev_check(data, batch_idx, mask_table, out_cx)
+    c = ctx(data.device)
+    check(lib().codae_corrupt_fwd(c, p(data), data.stride(0), p(batch_idx), B, p(mask_table), mask_table.shape[1], run,
+                                  p(mask_bits), p(col_var), io, p(out_cx), dt(out_cx), out_cx.stride(0), p(out_x),
+                                  0 if out_x is None else out_x.stride(0), p(out_mask_id), stream()), c)
+
+
+def dense_masks(batch_idx, B, mask_table, run, mask_bits, nb_missing, col_var, io, k_max, out_masks, out_fmask):
+    _dev_check(mask_table, out_masks)
+    c = ctx(mask_table.device)
+    check(lib().codae_dense_masks(c, p(batch_idx), B, p(mask_table), mask_table.shape[1], run, p(mask_bits), p(nb_missing),
+                                  p(col_var), io, k_max, p(out_masks), p(out_fmask), stream()), c)
+
+
+def mul_mask(x, mask, out):
+    _dev_check(x, mask, out)
+    c = ctx(x.device)
+    check(lib().codae_mul_mask(c, p(x), p(mask), p(out), x.numel(), stream()), c)
+
+
+def loss_workspace(device):
+    c = ctx(device)
+    return torch.zeros(int(lib().codae_loss_workspace_bytes(c)), dtype=torch.uint8, device=device)
+
+
+def mse_loss_fwd_bwd(x, batch_idx, y, mask_id, mask_bits, col_var, B, io, grad_scale, dy, acc, ws):
+    _dev_check(x, y, acc, ws)
+    c = ctx(x.device)
+    check(lib().codae_mse_loss_fwd_bwd(c, p(x), x.stride(0), p(batch_idx), p(y), dt(y), y.stride(0), p(mask_id), p(mask_bits),
+                                       p(col_var), B, io, grad_scale, p(dy), F32 if dy is None else dt(dy),
+                                       0 if dy is None else dy.stride(0), p(acc), p(ws), ws.numel(), stream()), c)
+
+
+def mixed_loss_fwd_bwd(x, y, var_pos, var_size, var_type, weight, dy, loss_out):
+    _dev_check(x, y, dy)
+    c = ctx(x.device)
+    assert x.stride(0) == y.stride(0) == dy.stride(0)
+    check(lib().codae_mixed_loss_fwd_bwd(c, p(x), p(y), x.shape[0], x.shape[1], x.stride(0), var_pos.numel(), p(var_pos),
+                                         p(var_size), p(var_type), p(weight), p(dy), p(loss_out), stream()), c)
+
+
+def mixed_monitor(x, y, var_pos, var_size, var_type, norm_scale, norm_min, norm_first, mask_id, mask_bits, nb_missing,
+                  k_max, out_loss, acc):
+    _dev_check(x, y, out_loss, acc)
+    c = ctx(x.device)
+    assert x.stride(0) == y.stride(0)
+    check(lib().codae_mixed_monitor(c, p(x), p(y), x.shape[0], x.shape[1], x.stride(0), var_pos.numel(), p(var_pos),
+                                    p(var_size), p(var_type), p(norm_scale), p(norm_min), norm_first, p(mask_id),
+                                    p(mask_bits), p(nb_missing), k_max, p(out_loss), p(acc), stream()), c)
+
+
+def linear_fwd(X, W, bias, Y, M, N, K, act, dtype):
+    c = ctx(X.device)
+    check(lib().codae_linear_fwd(c, p(X), X.stride(0), p(W), W.stride(0), p(bias), p(Y), Y.stride(0), M, N, K, act, dtype,
+                                 dt(Y), stream()), c)
+
+
+def linear_dgrad(dY, W, A_prev, dX, M, N, K, dtype):
+    c = ctx(dY.device)
+    check(lib().codae_linear_dgrad(c, p(dY), dY.stride(0), p(W), W.stride(0), p(A_prev),
+                                   0 if A_prev is None else A_prev.stride(0), p(dX), dX.stride(0), M, N, K, dtype, dt(dX),
+                                   stream()), c)
+
+
+def linear_wgrad(dY, X, dW, db, M, N, K, dtype):
+    c = ctx(dY.device)
+    check(lib().codae_linear_wgrad(c, p(dY), dY.stride(0), p(X), X.stride(0), p(dW), dW.stride(0), p(db), M, N, K, dtype,
+                                   stream()), c)
+
+
+def cast_bf16(src, dst):
+    c = ctx(src.device)
+    check(lib().codae_cast_bf16(c, p(src), p(dst), src.numel(), stream()), c)
+
+
+def sqnorm_workspace(device):
+    c = ctx(device)
+    return torch.zeros(int(lib().codae_sqnorm_workspace_bytes(c)), dtype=torch.uint8, device=device)
+
+
+def grad_sqnorm(g, out, ws):
+    c = ctx(g.device)
+    check(lib().codae_grad_sqnorm(c, p(g), g.numel(), p(out), p(ws), ws.numel(), stream()), c)
+
+
+def adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm, grad_scale, step_dev=None):
+    c = ctx(pf.device)
+    check(lib().codae_adam_step(c, p(pf), p(g), p(m), p(v), p(p_bf16), pf.numel(), lr, beta1, beta2, eps, wd, step, max_norm,
+                                p(sqnorm), grad_scale, p(step_dev), stream()), c)
+
+
+def counter_add(counter, delta):
+    c = ctx(counter.device)
+    check(lib().codae_counter_add(c, p(counter), delta, stream()), c)
+
+
+def score_topk_workspace(device, Q, k):
+    c = ctx(device)
+    return torch.empty(int(lib().codae_score_topk_workspace_bytes(c, Q, k)), dtype=torch.uint8, device=device)
+
+
+def score_topk(catalog, E, row_offset, query, inv_scale, metric, k, out_score, out_idx, ws):
+    _dev_check(catalog, query, out_score, out_idx, ws)
+    c = ctx(catalog.device)
+    check(lib().codae_score_topk(c, p(catalog), dt(catalog), catalog.shape[0], catalog.stride(0), E, row_offset, p(query),
+                                 query.shape[0], inv_scale, metric, k, p(out_score), p(out_idx), p(ws), ws.numel(),
+                                 stream()), c)
+
+
+def topk_merge(scores, idx, metric, out_score, out_idx):
+    c = ctx(scores.device)
+    G, Q, k = scores.shape
+    check(lib().codae_topk_merge(c, p(scores), p(idx), G, Q, k, metric, p(out_score), p(out_idx), stream()), c)
+
+
+def score_rank(catalog, E, query, inv_scale, metric, true_idx, subset_idx, out_rank):
+    _dev_check(catalog, query, true_idx, out_rank)
+    c = ctx(catalog.device)
+    check(lib().codae_score_rank(c, p(catalog), dt(catalog), catalog.shape[0], catalog.stride(0), E, p(query),
+                                 query.shape[0], inv_scale, metric, p(true_idx), p(subset_idx),
+                                 0 if subset_idx is None else subset_idx.numel(), p(out_rank), stream()), c)
+
+
+def linear_engine(device, dtype, M, N, K):
+    return lib().codae_linear_engine(ctx(device), dtype, M, N, K)

@@ -1,0 +1,221 @@
+"""Flat-buffer MLP shared by the two denoising autoencoders.
+
+The nn.Linear / nn.ReLU modules only carry the structure (same `state_dict` keys and `print(model)` as
+the reference); on a CUDA device every Parameter is re-pointed into ONE flat fp32 buffer (row pitches padded
+to 8 elements so TMA can tile them) and all arithmetic goes through libcodae_b200's C ABI.
+"""
+import torch
+
+from codae import _C
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class _MLPFunction(torch.autograd.Function):
+    """Legacy-API bridge: `model(x)` + `loss.backward()` route through the CUDA kernels
+    (reference call sites: embedding_denoising_autoencoder.py:166,183; train_dae_on_embedding.py:210)."""
+
+    @staticmethod
+    def forward(ctx, x, mlp, first, last, *params):
+        acts = mlp.forward_layers(x, first, last)
+        ctx.mlp, ctx.first, ctx.last, ctx.acts = mlp, first, last, acts
+        out_w = mlp.dims[last - 1][1]
+        return acts[-1][:, :out_w].float() if acts[-1].dtype != torch.float32 else acts[-1][:, :out_w]
+
+    @staticmethod
+    def backward(ctx, dy):
+        mlp = ctx.mlp
+        gflat = torch.zeros_like(mlp.flat)
+        dx = mlp.backward_layers(ctx.acts, dy, ctx.first, ctx.last, gflat, need_dx=ctx.needs_input_grad[0])
+        grads = []
+        for l in range(ctx.first, ctx.last):
+            grads.append(mlp.weight_view(gflat, l))
+            grads.append(mlp.bias_view(gflat, l))
+        return (dx, None, None, None) + tuple(grads)
+
+
+class FlatMLP(torch.nn.Module):
+
+    def _finish_init(self, dims, relu, nb_encoder):
+        """dims: [(in, out)], relu: [bool] per Linear; encoder = first nb_encoder Linears."""
+        self.dims = list(dims)
+        self.relu = list(relu)
+        self.nb_encoder = nb_encoder
+        self.flat = None          # fp32 [P_padded] on the CUDA device
+        self.flat_bf16 = None     # bf16 shadow (tensor-core engine)
+        self.compute_dtype = "fp32"
+        self._layout = None
+
+    # ---- structure ---------------------------------------------------------------------------
+    def linears(self):
+        return [m for m in list(self.input_layer) + list(self.output_layer) if isinstance(m, torch.nn.Linear)]
+
+    def layout(self):
+        """[(w_off, ldw, b_off)] per layer and the padded total; every segment starts 16-byte aligned in
+        both the fp32 buffer and its bf16 shadow."""
+        if self._layout is None:
+            off, out = 0, []
+            for (i, o) in self.dims:
+                ldw = _round_up(i, 8)
+                w_off = off
+                off += _round_up(o * ldw, 8)
+                b_off = off
+                off += _round_up(o, 8)
+                out.append((w_off, ldw, b_off))
+            self._layout = (out, off)
+        return self._layout
+
+    def weight_view(self, flat, l):
+        (w_off, ldw, _), (i, o) = self.layout()[0][l], self.dims[l]
+        return flat[w_off:w_off + o * ldw].view(o, ldw)[:, :i]
+
+    def bias_view(self, flat, l):
+        (_, _, b_off), (_, o) = self.layout()[0][l], self.dims[l]
+        return flat[b_off:b_off + o]
+
+    def nb_parameters(self):
+        return sum(i * o + o for i, o in self.dims)
+
+    # ---- device placement ------------------------------------------------------------------------
+    def to(self, *args, **kwargs):
+        """Like the reference's override (embedding_denoising_autoencoder.py:214-223), then flatten."""
+        self = super().to(*args, **kwargs)
+        self.input_layer = self.input_layer.to(*args, **kwargs)
+        self.output_layer = self.output_layer.to(*args, **kwargs)
+        dev = next(self.parameters()).device
+        if dev.type == "cuda":
+            self._flatten(dev)
+        return self
+
+    def _flatten(self, dev):
+        lay, total = self.layout()
+        flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        for l, lin in enumerate(self.linears()):
+            self.weight_view(flat, l).copy_(lin.weight.data)
+            self.bias_view(flat, l).copy_(lin.bias.data)
+            lin.weight.data = self.weight_view(flat, l)
+            lin.bias.data = self.bias_view(flat, l)
+        self.flat = flat
+        self.flat_bf16 = None
+
+    def set_compute_dtype(self, name):
+        """"fp32": exact-fp32 FFMA engine (reference precision).  "bf16": tcgen05 tensor cores with fp32
+        accumulation and fp32 master weights; falls back to nothing -- layers the tensor-core engine cannot
+        tile (tabular widths) make the whole model stay on the fp32 engine, decided here, up front."""
+        if name not in ("fp32", "bf16"):
+            raise Exception("Unknown compute dtype.")
+        self.compute_dtype = name
+        return self
+
+    def engine_dtype(self):
+        if self.compute_dtype == "bf16" and self.flat is not None:
+            ok = all(_C.linear_engine(self.flat.device, _C.BF16, 128, o, i) == _C.ENGINE_TCGEN05_BF16 for i, o in self.dims)
+            if ok:
+                return _C.BF16
+        return _C.F32
+
+    def refresh_shadow(self):
+        if self.flat_bf16 is None:
+            self.flat_bf16 = torch.empty(self.flat.numel(), dtype=torch.bfloat16, device=self.flat.device)
+        _C.cast_bf16(self.flat, self.flat_bf16)
+
+    def _require_cuda(self):
+        if self.flat is None:
+            raise RuntimeError("codae: the model must be moved to a CUDA device (model.to(device)); "
+                               "the B200 path has no CPU fallback")
+
+    # ---- compute -----------------------------------------------------------------------------------
+    def forward_layers(self, x, first, last, acts=None):
+        """Runs Linear[first:last] (+ReLU).  Returns the activation list [input, out_first, ...]; buffers are
+        [B, round_up(width, 8)] with zero padding.  The last Linear of the chain writes fp32."""
+        self._require_cuda()
+        eng = self.engine_dtype()
+        B = x.shape[0]
+        dev = self.flat.device
+        adt = torch.bfloat16 if eng == _C.BF16 else torch.float32
+        wflat = self.flat
+        if eng == _C.BF16:
+            self.refresh_shadow()
+            wflat = self.flat_bf16
+        in_w = self.dims[first][0]
+        a0 = torch.zeros((B, _round_up(in_w, 8)), dtype=adt, device=dev)
+        a0[:, :in_w] = x
+        out = [a0]
+        for l in range(first, last):
+            i, o = self.dims[l]
+            is_last = l == last - 1
+            y = torch.zeros((B, _round_up(o, 8)), dtype=torch.float32 if is_last else adt, device=dev)
+            _C.linear_fwd(out[-1], self.weight_view(wflat, l), self.bias_view(self.flat, l), y, B, o, i,
+                          _C.ACT_RELU if self.relu[l] else _C.ACT_NONE, eng)
+            out.append(y)
+        return out
+
+    def backward_layers(self, acts, dy, first, last, gflat, need_dx=False):
+        """dW/db of Linear[first:last] into `gflat` (flat layout) and optionally dL/dx."""
+        eng = self.engine_dtype()
+        dev = self.flat.device
+        adt = torch.bfloat16 if eng == _C.BF16 else torch.float32
+        wflat = self.flat_bf16 if eng == _C.BF16 else self.flat
+        B = dy.shape[0]
+        o_last = self.dims[last - 1][1]
+        g = torch.zeros((B, _round_up(o_last, 8)), dtype=adt, device=dev)
+        g[:, :o_last] = dy
+        # the last Linear of a chain may itself be followed by ReLU (encode() alone never is; decode() neither)
+        dx = None
+        for l in range(last - 1, first - 1, -1):
+            i, o = self.dims[l]
+            a_in = acts[l - first]
+            if a_in.dtype != adt:
+                a_in = a_in.to(adt)
+            _C.linear_wgrad(g, a_in, self.weight_view(gflat, l), self.bias_view(gflat, l), B, o, i, eng)
+            if l > first or need_dx:
+                gp = torch.zeros((B, _round_up(i, 8)), dtype=adt, device=dev)
+                prev_relu = l > 0 and self.relu[l - 1] and l > first
+                _C.linear_dgrad(g, self.weight_view(wflat, l), a_in if prev_relu else None, gp, B, o, i, eng)
+                g = gp
+                if l == first:
+                    dx = gp[:, :i].float()
+        return dx
+
+    def _run(self, x, first, last):
+        self._require_cuda()
+        if not x.is_cuda:
+            raise RuntimeError("codae: input is not on a CUDA device; the B200 path has no CPU fallback")
+        params = []
+        for lin in self.linears()[first:last]:
+            params += [lin.weight, lin.bias]
+        return _MLPFunction.apply(x, self, first, last, *params)
+
+    def forward(self, x):
+        """y = decode(encode(x))  (embedding_denoising_autoencoder.py:137-151)."""
+        return self._run(x, 0, len(self.dims))
+
+    def encode(self, x):
+        """(embedding_denoising_autoencoder.py:155-168)"""
+        return self._run(x, 0, self.nb_encoder)
+
+    def decode(self, z):
+        """(embedding_denoising_autoencoder.py:171-185)"""
+        return self._run(z, self.nb_encoder, len(self.dims))
+
+    def corrupt_dense(self, input_data, mask):
+        """input_data.clone() * mask as one kernel (embedding_denoising_autoencoder.py:239)."""
+        if not input_data.is_cuda:
+            raise RuntimeError("codae: input is not on a CUDA device; the B200 path has no CPU fallback")
+        x = input_data.contiguous()
+        m = mask.to(torch.float32).expand_as(x).contiguous()
+        out = torch.empty_like(x)
+        _C.mul_mask(x, m, out)
+        return out
+
+    def init_weight_general_rule(self, m):
+        """xavier_uniform_ on every Linear (embedding_denoising_autoencoder.py:188-197)."""
+        if m.__class__.__name__.find('Linear') != -1:
+            torch.nn.init.xavier_uniform_(m.weight)
+
+    def init_bias_zero(self, m):
+        """zero bias (embedding_denoising_autoencoder.py:200-211)."""
+        if m.__class__.__name__.find('Linear') != -1:
+            m.bias.data.fill_(0)

@@ -1,0 +1,215 @@
+"""FusedStep -- the training-loop body of the reference scripts as a fixed sequence of libcodae_b200 kernels.
+
+Replaces, per step (script/train_dae_on_embedding.py:198-223; script/train_dae_on_abalone.py:206-236):
+  get_masks + corrupt      -> codae_corrupt_fwd      (row gather + slot mask, mask never materialised)
+  model(c_input)           -> L x codae_linear_fwd   (bias + ReLU fused)
+  criterion + first bwd    -> codae_mse_loss_fwd_bwd (loss, dL/dy and the full/partial monitor sums, one pass)
+                              or codae_mixed_loss_fwd_bwd + codae_mixed_monitor (abalone)
+  loss.backward()          -> L x codae_linear_wgrad (+ bias column sums), (L-1) x codae_linear_dgrad
+  [data parallel]          -> one NCCL all-reduce of the flat gradient buffer
+  clip_grad_norm_ + Adam   -> codae_grad_sqnorm + codae_adam_step over the flat buffers
+No host synchronisation happens inside a step; monitors stay on the device until read_monitors().
+The whole sequence can be captured once per batch size into a CUDA graph (use_graph=True).
+"""
+import torch
+
+from codae import _C
+from codae.tool.metering import arch_tables
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class FusedStep:
+
+    def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
+                 max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None):
+        """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
+        tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
+        {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
+        world_size > 1: gradients are summed across `process_group` (each rank computes dL/dy with the GLOBAL
+        batch size, so the sum is the global-batch gradient the single-process reference would see)."""
+        if model.flat is None:
+            raise RuntimeError("codae: FusedStep needs model.to(cuda_device) first; there is no CPU fallback")
+        if not data.is_cuda:
+            raise RuntimeError("codae: FusedStep needs dataset.to(cuda_device) first; there is no CPU fallback")
+        self.model, self.corrupter, self.data = model, corrupter, data
+        self.lr, self.wd, self.clip, self.betas, self.eps, self.max_norm = lr, weight_decay, clip, betas, eps, max_norm
+        self.world_size, self.pg = world_size, process_group
+        self.use_graph = use_graph
+        self.mixed = mixed
+        dev = model.flat.device
+        self.dev = dev
+        self.io = model.dims[0][0]
+        self.eng = model.engine_dtype()
+        self.adt = torch.bfloat16 if self.eng == _C.BF16 else torch.float32
+        n = model.flat.numel()
+        self.gflat = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
+        if self.eng == _C.BF16:
+            model.refresh_shadow()
+        self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.norm_ws = _C.sqnorm_workspace(dev)
+        self.loss_ws = _C.loss_workspace(dev)
+        self.acc = torch.zeros(4, dtype=torch.float64, device=dev)   # {sum full, sum partial, rows, last step's sum}
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.step_count = 0
+        self.kernel_launches = 0
+        if mixed is not None:
+            V = len(mixed["arch"])
+            self.var_tables = arch_tables(mixed["arch"], dev)
+            self.weight = torch.tensor(list(mixed["weight"]), dtype=torch.float32, device=dev)
+            self.norm_scale = None if mixed.get("norm_scale") is None else mixed["norm_scale"].to(dev, torch.float32).contiguous()
+            self.norm_min = None if mixed.get("norm_min") is None else mixed["norm_min"].to(dev, torch.float32).contiguous()
+            self.norm_first = int(mixed.get("norm_first", self.io))
+            self.mixed_loss = torch.zeros(1 + V, dtype=torch.float32, device=dev)
+            self.mixed_acc = torch.zeros(2 + 2 * corrupter.k_max * V, dtype=torch.float64, device=dev)
+        for l, lin in enumerate(model.linears()):   # .grad views into the flat gradient buffer
+            lin.weight.grad = model.weight_view(self.gflat, l)
+            lin.bias.grad = model.bias_view(self.gflat, l)
+        self._bufs = {}
+        self._graphs = {}
+        self._calls = {}
+
+    # ---- buffers ------------------------------------------------------------------------------------
+    def _buffers(self, B):
+        b = self._bufs.get(B)
+        if b is None:
+            dev, adt, dims = self.dev, self.adt, self.model.dims
+            wmax = max(_round_up(max(i, o), 8) for i, o in dims)
+            # tabular (mixed) mode keeps one pitch for every buffer: the mixed-loss kernel takes a single ld
+            width = (lambda w: wmax) if self.mixed is not None else (lambda w: _round_up(w, 8))
+            acts = [torch.zeros((B, width(dims[0][0])), dtype=adt, device=dev)]
+            for l, (i, o) in enumerate(dims):
+                last = l == len(dims) - 1
+                acts.append(torch.zeros((B, width(o)), dtype=torch.float32 if last else adt, device=dev))
+            b = dict(acts=acts,
+                     g0=torch.zeros((B, wmax), dtype=adt, device=dev), g1=torch.zeros((B, wmax), dtype=adt, device=dev),
+                     mask_id=torch.zeros(B, dtype=torch.int32, device=dev),
+                     idx=torch.zeros(B, dtype=torch.int64, device=dev),
+                     x=torch.zeros((B, wmax), dtype=torch.float32, device=dev) if self.mixed is not None else None,
+                     mon=torch.zeros((B, len(self.mixed["arch"])), dtype=torch.float32, device=dev) if self.mixed is not None else None)
+            self._bufs[B] = b
+        return b
+
+    # ---- the kernel sequence ----------------------------------------------------------------------------
+    def _enqueue(self, B, b, run, global_batch, data, idx, table, train=True):
+        model, dims, eng = self.model, self.model.dims, self.eng
+        L = len(dims)
+        _, bits, col_var, nmiss = self.corrupter.device_tables()
+        acts = b["acts"]
+        n = 0
+        _C.corrupt_fwd(data, idx, B, table, run, bits, col_var, self.io, acts[0], b["x"], b["mask_id"]); n += 1
+        wflat = model.flat_bf16 if eng == _C.BF16 else model.flat
+        for l, (i, o) in enumerate(dims):
+            _C.linear_fwd(acts[l], model.weight_view(wflat, l), model.bias_view(model.flat, l), acts[l + 1], B, o, i,
+                          _C.ACT_RELU if model.relu[l] else _C.ACT_NONE, eng); n += 1
+        y = acts[L]
+        o_last = dims[L - 1][1]
+        g = b["g0"][:, :_round_up(o_last, 8)]
+        if self.mixed is None:
+            _C.mse_loss_fwd_bwd(data, idx, y, b["mask_id"], bits, col_var, B, self.io, 2.0 / (global_batch * self.io),
+                                g if train else None, self.acc, self.loss_ws); n += 1
+        else:
+            pos, size, typ = self.var_tables
+            gm = g if g.dtype == torch.float32 else torch.empty_like(y)
+            _C.mixed_loss_fwd_bwd(b["x"], y, pos, size, typ, self.weight, gm, self.mixed_loss); n += 1
+            _C.mixed_monitor(b["x"], y, pos, size, typ, self.norm_scale, self.norm_min, self.norm_first, b["mask_id"], bits,
+                             nmiss, self.corrupter.k_max, b["mon"], self.mixed_acc); n += 1
+        if not train:
+            return n
+        cur, nxt = "g0", "g1"
+        for l in range(L - 1, -1, -1):
+            i, o = dims[l]
+            gl = b[cur][:, :_round_up(o, 8)]
+            _C.linear_wgrad(gl, acts[l], model.weight_view(self.gflat, l), model.bias_view(self.gflat, l), B, o, i, eng); n += 2
+            if l > 0:
+                gp = b[nxt][:, :_round_up(i, 8)]
+                _C.linear_dgrad(gl, model.weight_view(wflat, l), acts[l] if model.relu[l - 1] else None, gp, B, o, i, eng); n += 1
+                cur, nxt = nxt, cur
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+        if self.clip:
+            _C.grad_sqnorm(self.gflat, self.sqnorm, self.norm_ws); n += 1
+        _C.counter_add(self.step_dev, 1); n += 1
+        _C.adam_step(model.flat, self.gflat, self.m, self.v, model.flat_bf16 if eng == _C.BF16 else None, self.lr,
+                     self.betas[0], self.betas[1], self.eps, self.wd, 0, self.max_norm if self.clip else -1.0,
+                     self.sqnorm if self.clip else None, 1.0, self.step_dev); n += 1
+        return n
+
+    # ---- public API ------------------------------------------------------------------------------------------
+    def step(self, batch_idx, run=0, global_batch=None, staged=None):
+        """One training step on observations `batch_idx` (int64 CUDA tensor [B]).
+        staged=(rows [B, io] f32, table_rows [B, nb_run] i16): host-staged batch (end-to-end path): the kernels
+        then read the staged rows instead of gathering from the resident dataset."""
+        B = int(batch_idx.numel()) if staged is None else int(staged[0].shape[0])
+        gb = B * self.world_size if global_batch is None else global_batch
+        b = self._buffers(B)
+        table = self.corrupter.device_tables()[0]
+        if staged is not None:
+            data, idx, table = staged[0], None, staged[1]
+        else:
+            data, idx = self.data, b["idx"]
+            idx.copy_(batch_idx, non_blocking=True)
+        self.step_count += 1
+        key = (B, run, gb, staged is not None)
+        if not self.use_graph:
+            self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table)
+            return
+        calls = self._calls.get(key, 0)
+        self._calls[key] = calls + 1
+        if calls == 0:            # first step of this shape runs eagerly (lazy attribute setup, warm caches)
+            self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table)
+            return
+        gr = self._graphs.get(key)
+        if gr is None:
+            torch.cuda.synchronize()
+            gr = torch.cuda.CUDAGraph()
+            self._static = getattr(self, "_static", {})
+            self._static[key] = (data, idx, table)
+            with torch.cuda.graph(gr):
+                self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table)
+            self._graphs[key] = gr
+        else:
+            sd, si, st = self._static[key]
+            if staged is not None and (sd.data_ptr() != data.data_ptr() or st.data_ptr() != table.data_ptr()):
+                raise RuntimeError("codae: a captured step must be replayed on the same staging buffers")
+        gr.replay()
+
+    def evaluate(self, batch_idx, run=0):
+        """Validation pass: corruption + forward + monitor sums only (train_dae_on_embedding.py:241-259),
+        without building any autograd state.  Returns the reconstruction [B, io] (device, fp32)."""
+        B = int(batch_idx.numel())
+        b = self._buffers(B)
+        b["idx"].copy_(batch_idx, non_blocking=True)
+        self._enqueue(B, b, run, B, self.data, b["idx"], self.corrupter.device_tables()[0], train=False)
+        return b["acts"][-1][:, :self.io]
+
+    def last_mask_ids(self, B):
+        return self._bufs[B]["mask_id"]
+
+    def reset_monitors(self):
+        self.acc.zero_()
+        if self.mixed is not None:
+            self.mixed_acc.zero_()
+
+    def read_monitors(self):
+        """One D2H copy: {'full', 'partial', 'rows', 'last_loss'} (embedding) -- the quantities the reference
+        accumulates on the host every step (train_dae_on_embedding.py:217-228)."""
+        a = self.acc.cpu().tolist()
+        out = dict(full=a[0], partial=a[1], rows=a[2], last_sum=a[3])
+        if self.mixed is not None:
+            V, K = len(self.mixed["arch"]), self.corrupter.k_max
+            m = self.mixed_acc.cpu()
+            out.update(ftl=float(m[0]), ptl=float(m[1]), ftl_per_k=m[2:2 + K * V].view(K, V).numpy().copy(),
+                       ptl_per_k=m[2 + K * V:].view(K, V).numpy().copy(), loss=self.mixed_loss.cpu().tolist())
+        return out
+
+    def last_loss(self, B):
+        """Loss of the most recent step (synchronises)."""
+        if self.mixed is not None:
+            return float(self.mixed_loss[0].item())
+        return float(self.acc[3].item()) / (B * self.io)

@@ -1,0 +1,93 @@
+// Shared device/host helpers for libcodae_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <mutex>
+
+#include "../../include/codae_b200.h"
+
+struct CUtensorMap_st;
+
+struct codae_ctx {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+    char err[512];
+    void* encode_tiled;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
+    std::mutex mu;
+};
+
+extern char g_codae_last_error[512];
+
+int codae_fail(codae_ctx* ctx, int code, const char* fmt, ...);
+int codae_check_launch(codae_ctx* ctx, const char* what);
+
+#define CODAE_REQUIRE(ctx, cond, ...)                                     \
+    do {                                                                  \
+        if (!(cond)) return codae_fail((ctx), CODAE_EINVAL, __VA_ARGS__); \
+    } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_stream_u4(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_u2(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void stg_stream_u2(void* p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum with a fixed tree (warp shuffles, then warp 0 over the per-warp partials).
+// Result valid in thread 0.  `scratch` holds >= 32 elements of T.
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    T r = T(0);
+    if (warp == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        r = lane < nw ? scratch[lane] : T(0);
+        r = warp_sum(r);
+    }
+    __syncthreads();
+    return r;
+}

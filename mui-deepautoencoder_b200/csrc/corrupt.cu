@@ -1,0 +1,207 @@
+// K1 -- corruption: Philox mask-id table, fused row gather + slot-mask corruption, dense masks.
+// HBM-bound elementwise work: 128-bit streaming loads/stores, one mask id per row looked up from the
+// (observation, run) table; the dense mask is computed from (mask_bits, col_var) and never stored.
+#include "common.cuh"
+
+namespace {
+
+// ---- Philox4x32-10 (Salmon et al., SC'11); the host restatement is oracle/philox.py ---------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+constexpr int kMaxRun = 1024;
+
+// One thread per observation: Fisher-Yates over range(nb_run) held in the output row itself.
+__global__ void mask_table_philox_kernel(uint64_t seed, int64_t first_obs, int64_t n_obs, int nb_run,
+                                         int16_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_obs) return;
+    int16_t* row = out + i * nb_run;
+    for (int t = 0; t < nb_run; ++t) row[t] = (int16_t)t;
+    const uint64_t obs = (uint64_t)(first_obs + i);
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    uint32_t blk[4];
+    for (int t = 0; t + 1 < nb_run; ++t) {
+        if ((t & 3) == 0) philox4x32_10((uint32_t)obs, (uint32_t)(obs >> 32), (uint32_t)(t >> 2), 0x434F4441u, k0, k1, blk);
+        const uint32_t draw = blk[t & 3];
+        const int j = t + (int)(((uint64_t)draw * (uint64_t)(nb_run - t)) >> 32);
+        const int16_t a = row[t];
+        row[t] = row[j];
+        row[j] = a;
+    }
+}
+
+__device__ __forceinline__ float keep_of(uint64_t bits, uint32_t var) { return ((bits >> var) & 1ull) ? 0.0f : 1.0f; }
+
+// Vector path: io % 4 == 0, all pitches % 4 == 0, 16-byte aligned bases.
+template <bool kBf16Out>
+__global__ void __launch_bounds__(256) corrupt_fwd_vec_kernel(const float* __restrict__ data, int64_t ld_data,
+                                                              const int64_t* __restrict__ batch_idx, int B,
+                                                              const int16_t* __restrict__ mask_table, int nb_run, int run,
+                                                              const uint64_t* __restrict__ mask_bits,
+                                                              const uint8_t* __restrict__ col_var, int io4,
+                                                              void* __restrict__ out_cx, int64_t ld_cx,
+                                                              float* __restrict__ out_x, int64_t ld_x,
+                                                              int32_t* __restrict__ out_mask_id) {
+    const int64_t total = (int64_t)B * io4;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(e / io4);
+        const int c4 = (int)(e - (int64_t)row * io4);
+        const int64_t obs = batch_idx ? batch_idx[row] : (int64_t)row;
+        const int mid = mask_table[obs * nb_run + run];
+        const uint64_t bits = mask_bits[mid];
+        const uchar4 var = *reinterpret_cast<const uchar4*>(col_var + 4 * c4);
+        const float4 x = ldg_stream_f4(data + obs * ld_data + 4 * (int64_t)c4);
+        float4 cx;
+        cx.x = x.x * keep_of(bits, var.x);
+        cx.y = x.y * keep_of(bits, var.y);
+        cx.z = x.z * keep_of(bits, var.z);
+        cx.w = x.w * keep_of(bits, var.w);
+        if (kBf16Out) {
+            uint2 p;
+            p.x = pack_bf16x2(cx.x, cx.y);
+            p.y = pack_bf16x2(cx.z, cx.w);
+            stg_stream_u2(reinterpret_cast<__nv_bfloat16*>(out_cx) + (int64_t)row * ld_cx + 4 * c4, p);
+        } else {
+            stg_stream_f4(reinterpret_cast<float*>(out_cx) + (int64_t)row * ld_cx + 4 * c4, cx);
+        }
+        if (out_x) stg_stream_f4(out_x + (int64_t)row * ld_x + 4 * c4, x);
+        if (out_mask_id && c4 == 0) out_mask_id[row] = mid;
+    }
+}
+
+// Scalar path for tabular widths (io = 11 for abalone) and unaligned pitches.
+template <bool kBf16Out>
+__global__ void __launch_bounds__(256) corrupt_fwd_scalar_kernel(const float* __restrict__ data, int64_t ld_data,
+                                                                 const int64_t* __restrict__ batch_idx, int B,
+                                                                 const int16_t* __restrict__ mask_table, int nb_run,
+                                                                 int run, const uint64_t* __restrict__ mask_bits,
+                                                                 const uint8_t* __restrict__ col_var, int io,
+                                                                 void* __restrict__ out_cx, int64_t ld_cx,
+                                                                 float* __restrict__ out_x, int64_t ld_x,
+                                                                 int32_t* __restrict__ out_mask_id) {
+    const int64_t total = (int64_t)B * io;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(e / io);
+        const int c = (int)(e - (int64_t)row * io);
+        const int64_t obs = batch_idx ? batch_idx[row] : (int64_t)row;
+        const int mid = mask_table[obs * nb_run + run];
+        const float x = data[obs * ld_data + c];
+        const float cx = x * keep_of(mask_bits[mid], col_var[c]);
+        if (kBf16Out) reinterpret_cast<__nv_bfloat16*>(out_cx)[(int64_t)row * ld_cx + c] = __float2bfloat16_rn(cx);
+        else reinterpret_cast<float*>(out_cx)[(int64_t)row * ld_cx + c] = cx;
+        if (out_x) out_x[(int64_t)row * ld_x + c] = x;
+        if (out_mask_id && c == 0) out_mask_id[row] = mid;
+    }
+}
+
+__global__ void __launch_bounds__(256) dense_masks_kernel(const int64_t* __restrict__ batch_idx, int B,
+                                                          const int16_t* __restrict__ mask_table, int nb_run, int run,
+                                                          const uint64_t* __restrict__ mask_bits,
+                                                          const uint8_t* __restrict__ nb_missing,
+                                                          const uint8_t* __restrict__ col_var, int io, int k_max,
+                                                          float* __restrict__ out_masks, float* __restrict__ out_fmask) {
+    const int64_t total = (int64_t)B * io;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(e / io);
+        const int c = (int)(e - (int64_t)row * io);
+        const int64_t obs = batch_idx ? batch_idx[row] : (int64_t)row;
+        const int mid = mask_table[obs * nb_run + run];
+        const float keep = keep_of(mask_bits[mid], col_var[c]);
+        const int kk = nb_missing[mid] - 1;
+        for (int k = 0; k < k_max; ++k) out_masks[((int64_t)k * B + row) * io + c] = (k == kk) ? keep : 0.0f;
+        out_fmask[e] = keep;
+    }
+}
+
+__global__ void __launch_bounds__(256) mul_mask_kernel(const float* __restrict__ x, const float* __restrict__ m,
+                                                       float* __restrict__ out, int64_t n) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x)
+        out[e] = x[e] * m[e];
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+inline int grid_for(const codae_ctx* ctx, int64_t work_items, int threads, int per_thread) {
+    int64_t blocks = (work_items + (int64_t)threads * per_thread - 1) / ((int64_t)threads * per_thread);
+    const int64_t cap = (int64_t)ctx->sm_count * 8;  // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" {
+
+int codae_mask_table_philox(codae_ctx* ctx, uint64_t seed, int64_t first_obs, int64_t n_obs, int nb_run, int16_t* out,
+                            void* stream) {
+    CODAE_REQUIRE(ctx, ctx && out, "codae_mask_table_philox: NULL argument");
+    CODAE_REQUIRE(ctx, nb_run >= 1 && nb_run <= kMaxRun, "codae_mask_table_philox: nb_run %d outside [1, %d]", nb_run,
+                  kMaxRun);
+    CODAE_REQUIRE(ctx, n_obs >= 0 && first_obs >= 0, "codae_mask_table_philox: negative size");
+    if (n_obs == 0) return CODAE_OK;
+    const int threads = 128;
+    mask_table_philox_kernel<<<(unsigned)((n_obs + threads - 1) / threads), threads, 0, as_stream(stream)>>>(
+        seed, first_obs, n_obs, nb_run, out);
+    return codae_check_launch(ctx, "mask_table_philox_kernel");
+}
+
+int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t ld_data, const int64_t* batch_idx, int B,
+                      const int16_t* mask_table, int nb_run, int run, const uint64_t* mask_bits, const uint8_t* col_var,
+                      int io, void* out_cx, int cx_dtype, int64_t ld_cx, float* out_x, int64_t ld_x,
+                      int32_t* out_mask_id, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && data && mask_table && mask_bits && col_var && out_cx, "codae_corrupt_fwd: NULL argument");
+    CODAE_REQUIRE(ctx, B >= 0 && io >= 1, "codae_corrupt_fwd: bad shape B=%d io=%d", B, io);
+    CODAE_REQUIRE(ctx, run >= 0 && run < nb_run, "codae_corrupt_fwd: run %d outside [0, %d)", run, nb_run);
+    CODAE_REQUIRE(ctx, ld_data >= io && ld_cx >= io && (!out_x || ld_x >= io), "codae_corrupt_fwd: pitch < io");
+    CODAE_REQUIRE(ctx, cx_dtype == CODAE_F32 || cx_dtype == CODAE_BF16, "codae_corrupt_fwd: bad cx_dtype %d", cx_dtype);
+    if (B == 0) return CODAE_OK;
+    const bool bf = cx_dtype == CODAE_BF16;
+    const bool vec = (io % 4 == 0) && (ld_data % 4 == 0) && (ld_cx % 4 == 0) && (!out_x || ld_x % 4 == 0) &&
+                     aligned16(data) && aligned16(out_cx) && (!out_x || aligned16(out_x)) &&
+                     ((reinterpret_cast<uintptr_t>(col_var) & 3) == 0);
+    cudaStream_t s = as_stream(stream);
+    if (vec) {
+        const int g = grid_for(ctx, (int64_t)B * (io / 4), 256, 4);
+        if (bf) corrupt_fwd_vec_kernel<true><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        else corrupt_fwd_vec_kernel<false><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+    } else {
+        const int g = grid_for(ctx, (int64_t)B * io, 256, 4);
+        if (bf) corrupt_fwd_scalar_kernel<true><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        else corrupt_fwd_scalar_kernel<false><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+    }
+    return codae_check_launch(ctx, "corrupt_fwd_kernel");
+}
+
+int codae_dense_masks(codae_ctx* ctx, const int64_t* batch_idx, int B, const int16_t* mask_table, int nb_run, int run,
+                      const uint64_t* mask_bits, const uint8_t* nb_missing, const uint8_t* col_var, int io, int k_max,
+                      float* out_masks, float* out_fmask, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && mask_table && mask_bits && nb_missing && col_var && out_masks && out_fmask,
+                  "codae_dense_masks: NULL argument");
+    CODAE_REQUIRE(ctx, B >= 0 && io >= 1 && k_max >= 1, "codae_dense_masks: bad shape");
+    CODAE_REQUIRE(ctx, run >= 0 && run < nb_run, "codae_dense_masks: run %d outside [0, %d)", run, nb_run);
+    if (B == 0) return CODAE_OK;
+    dense_masks_kernel<<<grid_for(ctx, (int64_t)B * io, 256, 2), 256, 0, as_stream(stream)>>>(
+        batch_idx, B, mask_table, nb_run, run, mask_bits, nb_missing, col_var, io, k_max, out_masks, out_fmask);
+    return codae_check_launch(ctx, "dense_masks_kernel");
+}
+
+int codae_mul_mask(codae_ctx* ctx, const float* x, const float* mask, float* out, int64_t n, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && x && mask && out && n >= 0, "codae_mul_mask: bad argument");
+    if (n == 0) return CODAE_OK;
+    mul_mask_kernel<<<grid_for(ctx, n, 256, 4), 256, 0, as_stream(stream)>>>(x, mask, out, n);
+    return codae_check_launch(ctx, "mul_mask_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,78 @@
+// Context, error reporting and engine selection of libcodae_b200.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+char g_codae_last_error[512] = "";
+
+int codae_fail(codae_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        strncpy(ctx->err, buf, sizeof(ctx->err) - 1);
+    }
+    strncpy(g_codae_last_error, buf, sizeof(g_codae_last_error) - 1);
+    return code;
+}
+
+int codae_check_launch(codae_ctx* ctx, const char* what) {
+    cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return codae_fail(ctx, CODAE_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+    return CODAE_OK;
+}
+
+extern "C" {
+
+int codae_version(void) { return CODAE_VERSION; }
+
+int codae_ctx_create(int device, codae_ctx** out) {
+    if (!out) return codae_fail(nullptr, CODAE_EINVAL, "codae_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return codae_fail(nullptr, CODAE_EARCH, "codae_ctx_create: no CUDA device (%s); this library has no CPU path",
+                          e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return codae_fail(nullptr, CODAE_EINVAL, "codae_ctx_create: bad device %d", device);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return codae_fail(nullptr, CODAE_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return codae_fail(nullptr, CODAE_EARCH,
+                          "codae_ctx_create: device %d is sm_%d%d; libcodae_b200 is built for sm_100a only", device,
+                          prop.major, prop.minor);
+    codae_ctx* c = new codae_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->err[0] = 0;
+    c->encode_tiled = nullptr;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) c->encode_tiled = fn;
+    else cudaGetLastError();
+    *out = c;
+    return CODAE_OK;
+}
+
+int codae_ctx_destroy(codae_ctx* ctx) {
+    delete ctx;
+    return CODAE_OK;
+}
+
+const char* codae_last_error(const codae_ctx* ctx) { return ctx ? ctx->err : g_codae_last_error; }
+
+int codae_ctx_sm_count(const codae_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+}  // extern "C"

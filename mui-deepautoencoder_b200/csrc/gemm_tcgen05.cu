@@ -1,0 +1,362 @@
+// K2 (tensor-core engine) -- bf16 GEMM on 5th-generation tensor cores: tcgen05.mma with the fp32
+// accumulator in TMEM, operands staged in shared memory by TMA (128-byte swizzle), fused epilogues.
+//
+//   C[M,N] = epilogue( sum_k A(m,k) * B(n,k) )        A: M x K, B: N x K (each K-major or MN-major in HBM)
+//
+// One kernel covers nn.Linear's three contractions (see linear.cu):
+//   fwd   Y  = X . W^T      A = X  K-major, B = W  K-major,  epilogue bias + ReLU
+//   dgrad dX = dY . W       A = dY K-major, B = W  MN-major, epilogue ReLU mask of the layer input
+//   wgrad dW = dY^T . X     A = dY MN-major, B = X MN-major, fp32 output into the flat gradient buffer
+//
+// CTA = 6 warps, one 128 x BN output tile: warp 0 = TMA producer (one elected lane), warp 1 = TMEM
+// allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (tcgen05.ld 32 lanes x 32 columns each).
+// Pipeline: kStages smem slots guarded by full/empty mbarriers; tcgen05.commit releases a slot when the
+// MMAs that read it have drained, and signals the epilogue after the last k-block.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "gemm.h"
+
+namespace {
+
+constexpr int BM = 128;          // UMMA_M (cta_group::1)
+constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr uint32_t kATileBytes = BM * BK * 2;  // 16 KB
+
+struct Params {
+    int M, N, K;
+    int a_kmajor, b_kmajor;
+    void* C;
+    long long ldc;
+    int c_bf16;
+    const float* bias;
+    int act;
+    const __nv_bfloat16* mask_src;
+    long long ldm;
+};
+
+template <int BN>
+struct Cfg {
+    static constexpr uint32_t kBTileBytes = BN * BK * 2;
+    static constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
+    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (reported as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 format: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
+//   K-major tile  [rows][64 elems]: 8-row swizzle atoms 1024 B apart (SBO); LBO unused (=1).
+//   MN-major tile [64 k-rows][64 elems] per 64-wide MN chunk: k-groups of 8 rows 1024 B apart (SBO),
+//                 MN chunks 8192 B apart (LBO).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool kmajor) {
+    const uint64_t lbo = kmajor ? 1ull : (8192ull >> 4);
+    const uint64_t sbo = 1024ull >> 4;
+    return (uint64_t)((saddr >> 4) & 0x3fff) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor: c=f32 [4,6)=1, a=bf16 [7,10)=1, b=bf16 [10,13)=1, a_major bit15, b_major bit16,
+// N>>3 [17,23), M>>4 [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int n, bool a_kmajor, bool b_kmajor) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((a_kmajor ? 0u : 1u) << 15) | ((b_kmajor ? 0u : 1u) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                                const __grid_constant__ CUtensorMap tma_b, const Params p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+    uint64_t* empty_bar = full_bar + C::kStages;
+    uint64_t* tmem_full_bar = empty_bar + C::kStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+        for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % C::kStages;
+                const uint32_t ph = (kb / C::kStages) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* a_dst = smem + s * C::kStageBytes;
+                uint8_t* b_dst = a_dst + kATileBytes;
+                mbar_expect_tx(&full_bar[s], C::kStageBytes);
+                const int k0 = kb * BK;
+                if (p.a_kmajor) {
+                    tma_load_2d(&tma_a, &full_bar[s], a_dst, k0, m0);                       // box {64 k, 128 m}
+                } else {
+                    tma_load_2d(&tma_a, &full_bar[s], a_dst, m0, k0);                       // box {64 m, 64 k} x 2
+                    tma_load_2d(&tma_a, &full_bar[s], a_dst + 8192, m0 + 64, k0);
+                }
+                if (p.b_kmajor) {
+                    tma_load_2d(&tma_b, &full_bar[s], b_dst, k0, n0);                       // box {64 k, BN n}
+                } else {
+#pragma unroll
+                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tma_b, &full_bar[s], b_dst + j * 8192, n0 + 64 * j, k0);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BN, p.a_kmajor != 0, p.b_kmajor != 0);
+            const uint32_t a_adv = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);   // bytes per UMMA_K step
+            const uint32_t b_adv = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % C::kStages;
+                const uint32_t ph = (kb / C::kStages) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
+                const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    umma_bf16(tmem_base, make_desc(a_addr + k * a_adv, p.a_kmajor != 0),
+                              make_desc(b_addr + k * b_adv, p.b_kmajor != 0), idesc, (kb | k) != 0);
+                }
+                umma_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
+            }
+            umma_commit(tmem_full_bar);              // accumulator complete
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> HBM =====
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;                      // TMEM lane quarter this warp may read
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < p.M;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            const int col0 = n0 + c * 32;
+            if (!row_ok || col0 >= p.N) continue;
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            const bool full = col0 + 32 <= p.N;
+            if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+            }
+            if (p.act == CODAE_ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (p.mask_src) {
+                const __nv_bfloat16* mrow = p.mask_src + (long long)row * p.ldm + col0;
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 mv = *reinterpret_cast<const uint4*>(mrow + 8 * j);
+                        const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            if (!(bf16_lo(w[t]) > 0.f)) f[8 * j + 2 * t] = 0.f;
+                            if (!(bf16_hi(w[t]) > 0.f)) f[8 * j + 2 * t + 1] = 0.f;
+                        }
+                    }
+                } else {
+                    for (int j = 0; j < 32 && col0 + j < p.N; ++j)
+                        if (!(__bfloat162float(mrow[j]) > 0.f)) f[j] = 0.f;
+                }
+            }
+            if (p.c_bf16) {
+                __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                        o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                        o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                        o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(crow + 8 * j) = o;
+                    }
+                } else {
+                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __float2bfloat16_rn(f[j]);
+                }
+            } else {
+                float* crow = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+                if (full) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(crow + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                } else {
+                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = f[j];
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, BN);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D bf16 tensor map over a row-major [rows, cols] matrix with pitch ld (elements); box {box_cols, box_rows}.
+int make_map(codae_ctx* ctx, CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
+             int box_rows) {
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+        map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return codae_fail(ctx, CODAE_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+    return CODAE_OK;
+}
+
+template <int BN>
+int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
+    using C = Cfg<BN>;
+    CUtensorMap ma, mb;
+    int rc;
+    // A(m,k): K-major storage [M rows, K cols]; MN-major storage [K rows, M cols]
+    if (g.a_kmajor) rc = make_map(ctx, &ma, g.A, g.M, g.K, g.lda, BK, BM);
+    else rc = make_map(ctx, &ma, g.A, g.K, g.M, g.lda, 64, BK);
+    if (rc) return rc;
+    if (g.b_kmajor) rc = make_map(ctx, &mb, g.B, g.N, g.K, g.ldb, BK, BN);
+    else rc = make_map(ctx, &mb, g.B, g.K, g.N, g.ldb, 64, BK);
+    if (rc) return rc;
+    Params p;
+    p.M = g.M; p.N = g.N; p.K = g.K;
+    p.a_kmajor = g.a_kmajor; p.b_kmajor = g.b_kmajor;
+    p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_dtype == CODAE_BF16;
+    p.bias = g.bias; p.act = g.act;
+    p.mask_src = reinterpret_cast<const __nv_bfloat16*>(g.mask_src); p.ldm = g.ldm;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tc05_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
+        if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaFuncSetAttribute(smem=%u): %s", C::kSmemBytes, cudaGetErrorString(e));
+        attr_set = true;
+    }
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+    tc05_gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, p);
+    return codae_check_launch(ctx, "tc05_gemm_kernel");
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+bool codae_tc05_supported(const codae_ctx* ctx, const Tc05Gemm& g) {
+    if (!ctx || !ctx->encode_tiled) return false;
+    if (g.M < 1 || g.N < 1 || g.K < 1) return false;
+    // TMA: 16-byte aligned bases and pitches (bf16 -> multiples of 8 elements)
+    if (!al16(g.A) || !al16(g.B) || !al16(g.C) || (g.lda % 8) || (g.ldb % 8)) return false;
+    if (g.c_dtype == CODAE_BF16 ? (g.ldc % 8) : (g.ldc % 4)) return false;
+    if (g.mask_src && (!al16(g.mask_src) || (g.ldm % 8))) return false;
+    // tiny problems (abalone 11x11) are not worth a 128-row tensor-core tile
+    if (g.N < 32 || g.K < 32) return false;
+    return true;
+}
+
+int codae_tc05_gemm(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
+    if (!codae_tc05_supported(ctx, g)) return codae_fail(ctx, CODAE_EINVAL, "codae_tc05_gemm: unsupported shape/alignment");
+    // tile width: the widest tile that still yields at least one CTA per SM (small batches want many CTAs
+    // streaming the weights), 256-wide for large problems.
+    const long tiles_m = (g.M + BM - 1) / BM;
+    const long t256 = tiles_m * ((g.N + 255) / 256), t128 = tiles_m * ((g.N + 127) / 128);
+    if (t256 >= ctx->sm_count && g.N >= 256) return launch<256>(ctx, g, s);
+    if (t128 >= ctx->sm_count && g.N >= 128) return launch<128>(ctx, g, s);
+    return launch<64>(ctx, g, s);
+}

@@ -1,0 +1,357 @@
+// K3 -- complementarity inference: sweep a catalog shard against query vectors staged in shared
+// memory, reduce each candidate's score with warp shuffles and keep the best k per query in-kernel.
+// HBM-bound: E*sizeof(dtype) bytes per candidate, nothing written per candidate.
+// Ordering is the total order (score, index) -> the selected set and its order do not depend on the
+// sweep schedule, so results are bit-reproducible and shard-invariant.
+#include <float.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kWarps = 8;                 // warps per CTA
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxK = 128;
+constexpr int kSlots = kMaxK / 32;        // list entries per lane
+constexpr int64_t kEmptyIdx = 0x7fffffffffffffffLL;
+
+struct Entry { float s; int64_t i; };
+
+// "a is strictly better than b" under the total order; sqerr: smaller score first, cosine: larger first.
+template <int METRIC>
+__device__ __forceinline__ bool better(float sa, int64_t ia, float sb, int64_t ib) {
+    if (METRIC == CODAE_METRIC_SQERR) return sa < sb || (sa == sb && ia < ib);
+    return sa > sb || (sa == sb && ia < ib);
+}
+template <int METRIC>
+__device__ __forceinline__ float worst_score() { return METRIC == CODAE_METRIC_SQERR ? INFINITY : -INFINITY; }
+
+// Warp-cooperative sorted insertion into a k-entry list held in shared memory (best first).
+// Returns true if the entry made it into the list.  All lanes must call with identical (s, i).
+template <int METRIC>
+__device__ __forceinline__ bool list_insert(float* ls, int64_t* li, int k, float s, int64_t i, int lane) {
+    if (!better<METRIC>(s, i, ls[k - 1], li[k - 1])) return false;
+    // position = number of entries strictly better than the new one
+    int pos = 0;
+    for (int b = 0; b < k; b += 32) {
+        const int e = b + lane;
+        const bool bt = e < k && better<METRIC>(ls[e], li[e], s, i);
+        pos += __popc(__ballot_sync(0xffffffffu, bt));
+    }
+    // shift [pos, k-1) one slot towards the tail, highest chunk first
+    for (int b = ((k - 1) / 32) * 32; b >= 0; b -= 32) {
+        const int e = b + lane;
+        float ts = 0.f; int64_t ti = 0;
+        const bool mv = e > pos && e < k;
+        if (mv) { ts = ls[e - 1]; ti = li[e - 1]; }
+        __syncwarp();
+        if (mv) { ls[e] = ts; li[e] = ti; }
+        __syncwarp();
+    }
+    if (lane == 0) { ls[pos] = s; li[pos] = i; }
+    __syncwarp();
+    return true;
+}
+
+// One candidate row against QC queries (smem), partial sums per lane.
+//   SQERR : acc[q] = sum (q_d - c_d*inv_scale)^2 ; COSINE: acc[q] = sum c_d q_d, cc = sum c_d^2
+template <int METRIC, int QC, bool kBf16>
+__device__ __forceinline__ void row_partial(const void* __restrict__ row, int E, const float* __restrict__ qs, float inv_scale,
+                                            int lane, float acc[QC], float& cc) {
+#pragma unroll
+    for (int q = 0; q < QC; ++q) acc[q] = 0.f;
+    cc = 0.f;
+    if (kBf16) {
+        const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(row);
+#pragma unroll 2
+        for (int c = lane * 8; c < E; c += 256) {
+            const uint4 p = ldg_stream_u4(r + c);
+            const float v[8] = {bf16_lo(p.x), bf16_hi(p.x), bf16_lo(p.y), bf16_hi(p.y),
+                                bf16_lo(p.z), bf16_hi(p.z), bf16_lo(p.w), bf16_hi(p.w)};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (METRIC == CODAE_METRIC_COSINE) cc = fmaf(v[j], v[j], cc);
+#pragma unroll
+                for (int q = 0; q < QC; ++q) {
+                    const float qv = qs[q * E + c + j];
+                    if (METRIC == CODAE_METRIC_SQERR) { const float d = qv - v[j] * inv_scale; acc[q] = fmaf(d, d, acc[q]); }
+                    else acc[q] = fmaf(v[j], qv, acc[q]);
+                }
+            }
+        }
+    } else {
+        const float* r = reinterpret_cast<const float*>(row);
+#pragma unroll 4
+        for (int c = lane * 4; c < E; c += 128) {
+            const float4 p = ldg_stream_f4(r + c);
+            const float v[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (METRIC == CODAE_METRIC_COSINE) cc = fmaf(v[j], v[j], cc);
+#pragma unroll
+                for (int q = 0; q < QC; ++q) {
+                    const float qv = qs[q * E + c + j];
+                    if (METRIC == CODAE_METRIC_SQERR) { const float d = qv - v[j] * inv_scale; acc[q] = fmaf(d, d, acc[q]); }
+                    else acc[q] = fmaf(v[j], qv, acc[q]);
+                }
+            }
+        }
+    }
+}
+
+template <int METRIC>
+__device__ __forceinline__ float finish_score(float acc, float cc, float qq) {
+    if (METRIC == CODAE_METRIC_SQERR) return acc;
+    return acc / fmaxf(sqrtf(cc * qq), 1e-8f);
+}
+
+// Workspace layout: [grid][QC][k] entries per launch (scores then indices).
+template <int METRIC, int QC, bool kBf16>
+__global__ void __launch_bounds__(kThreads) score_topk_kernel(const void* __restrict__ catalog, int64_t n_rows, int64_t ld,
+                                                              int E, int64_t row_offset, const float* __restrict__ query,
+                                                              float inv_scale, int k, float* __restrict__ ws_score,
+                                                              int64_t* __restrict__ ws_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* qs = reinterpret_cast<float*>(smem_raw);                        // [QC][E]
+    float* qq = qs + QC * E;                                               // [QC] |q|^2
+    int64_t* li = reinterpret_cast<int64_t*>(qq + ((QC + 3) & ~3));         // [kWarps][QC][k]
+    float* ls = reinterpret_cast<float*>(li + kWarps * QC * k);            // [kWarps][QC][k]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < QC * E; e += kThreads) qs[e] = query[e];
+    for (int e = threadIdx.x; e < kWarps * QC * k; e += kThreads) { ls[e] = worst_score<METRIC>(); li[e] = kEmptyIdx; }
+    __syncthreads();
+    if (warp < QC) {
+        float s = 0.f;
+        for (int c = lane; c < E; c += 32) s = fmaf(qs[warp * E + c], qs[warp * E + c], s);
+        s = warp_sum(s);
+        if (lane == 0) qq[warp] = s;
+    }
+    __syncthreads();
+    float* my_s = ls + warp * QC * k;
+    int64_t* my_i = li + warp * QC * k;
+    const size_t esz = kBf16 ? 2 : 4;
+    const int64_t wstride = (int64_t)gridDim.x * kWarps;
+    for (int64_t r = (int64_t)blockIdx.x * kWarps + warp; r < n_rows; r += wstride) {
+        float acc[QC], cc;
+        row_partial<METRIC, QC, kBf16>(reinterpret_cast<const unsigned char*>(catalog) + (size_t)r * ld * esz, E, qs,
+                                       inv_scale, lane, acc, cc);
+        if (METRIC == CODAE_METRIC_COSINE) cc = warp_sum(cc);
+#pragma unroll
+        for (int q = 0; q < QC; ++q) {
+            const float s = finish_score<METRIC>(warp_sum(acc[q]), cc, qq[q]);
+            if (s == s) list_insert<METRIC>(my_s + q * k, my_i + q * k, k, s, row_offset + r, lane);  // NaN never ranks
+        }
+    }
+    __syncthreads();
+    // CTA merge: warp w (< QC) folds the lists of query w from all warps; sorted inputs -> stop at first reject
+    for (int q = warp; q < QC; q += kWarps) {
+        float* dst_s = ls + q * k;            // warp 0's list of query q
+        int64_t* dst_i = li + q * k;
+        for (int w = 1; w < kWarps; ++w) {
+            const float* src_s = ls + (w * QC + q) * k;
+            const int64_t* src_i = li + (w * QC + q) * k;
+            for (int e = 0; e < k; ++e) {
+                if (src_i[e] == kEmptyIdx) break;
+                if (!list_insert<METRIC>(dst_s, dst_i, k, src_s[e], src_i[e], lane)) break;
+            }
+        }
+        for (int e = lane; e < k; e += 32) {
+            ws_score[((int64_t)blockIdx.x * QC + q) * k + e] = dst_s[e];
+            ws_idx[((int64_t)blockIdx.x * QC + q) * k + e] = dst_i[e];
+        }
+    }
+}
+
+// Merge `n_lists` sorted k-lists per query (layout [n_lists][Q][k]) into out [Q][k].  One CTA per query;
+// every warp folds a strided subset of the lists, then warp 0 folds the per-warp results.
+template <int METRIC>
+__global__ void __launch_bounds__(kThreads) topk_merge_kernel(const float* __restrict__ in_s, const int64_t* __restrict__ in_i,
+                                                              int n_lists, int Q, int k, float* __restrict__ out_s,
+                                                              int64_t* __restrict__ out_i, int q_out_offset, int q_out_stride) {
+    __shared__ float ls[kWarps][kMaxK];
+    __shared__ int64_t li[kWarps][kMaxK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = blockIdx.x;
+    for (int e = lane; e < k; e += 32) { ls[warp][e] = worst_score<METRIC>(); li[warp][e] = kEmptyIdx; }
+    __syncwarp();
+    for (int l = warp; l < n_lists; l += kWarps) {
+        const float* s = in_s + ((int64_t)l * Q + q) * k;
+        const int64_t* i = in_i + ((int64_t)l * Q + q) * k;
+        for (int e = 0; e < k; ++e) {
+            const int64_t ii = i[e];
+            if (ii == kEmptyIdx || ii < 0) break;
+            if (!list_insert<METRIC>(ls[warp], li[warp], k, s[e], ii, lane)) break;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < kWarps; ++w)
+            for (int e = 0; e < k; ++e) {
+                if (li[w][e] == kEmptyIdx) break;
+                if (!list_insert<METRIC>(ls[0], li[0], k, ls[w][e], li[w][e], lane)) break;
+            }
+        const int qo = q_out_offset + q * q_out_stride;
+        for (int e = lane; e < k; e += 32) {
+            const bool empty = li[0][e] == kEmptyIdx;
+            out_s[(int64_t)qo * k + e] = ls[0][e];
+            out_i[(int64_t)qo * k + e] = empty ? -1 : li[0][e];
+        }
+    }
+}
+
+// Rank mode: s_true[q] = score(query q, row true_idx[q]); out_rank[q] = #{j in subset : s_true[q] better-than s_q[j]}.
+template <int METRIC, bool kBf16>
+__global__ void __launch_bounds__(kThreads) score_rank_kernel(const void* __restrict__ catalog, int64_t n_rows, int64_t ld,
+                                                              int E, const float* __restrict__ query, int Q, float inv_scale,
+                                                              const int64_t* __restrict__ true_idx,
+                                                              const int64_t* __restrict__ subset, int64_t n_subset,
+                                                              unsigned long long* __restrict__ out_rank) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_true = reinterpret_cast<float*>(smem_raw);     // [Q]
+    float* qq = s_true + Q;                                 // [Q]
+    int* cnt = reinterpret_cast<int*>(qq + Q);              // [Q]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t esz = kBf16 ? 2 : 4;
+    for (int q = threadIdx.x; q < Q; q += kThreads) cnt[q] = 0;
+    for (int q = warp; q < Q; q += kWarps) {
+        float s = 0.f;
+        for (int c = lane; c < E; c += 32) { const float v = query[(int64_t)q * E + c]; s = fmaf(v, v, s); }
+        s = warp_sum(s);
+        float acc[1], cc;
+        row_partial<METRIC, 1, kBf16>(reinterpret_cast<const unsigned char*>(catalog) + (size_t)true_idx[q] * ld * esz, E,
+                                      query + (int64_t)q * E, inv_scale, lane, acc, cc);
+        if (METRIC == CODAE_METRIC_COSINE) cc = warp_sum(cc);
+        const float st = finish_score<METRIC>(warp_sum(acc[0]), cc, s);
+        if (lane == 0) { qq[q] = s; s_true[q] = st; }
+    }
+    __syncthreads();
+    const int64_t wstride = (int64_t)gridDim.x * kWarps;
+    for (int64_t t = (int64_t)blockIdx.x * kWarps + warp; t < n_subset; t += wstride) {
+        const int64_t r = subset ? subset[t] : t;
+        const unsigned char* row = reinterpret_cast<const unsigned char*>(catalog) + (size_t)r * ld * esz;
+        for (int q = 0; q < Q; ++q) {
+            float acc[1], cc;
+            row_partial<METRIC, 1, kBf16>(row, E, query + (int64_t)q * E, inv_scale, lane, acc, cc);
+            if (METRIC == CODAE_METRIC_COSINE) cc = warp_sum(cc);
+            const float s = finish_score<METRIC>(warp_sum(acc[0]), cc, qq[q]);
+            const bool b = METRIC == CODAE_METRIC_SQERR ? (s_true[q] < s) : (s_true[q] > s);
+            if (lane == 0 && b) atomicAdd(&cnt[q], 1);
+        }
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < Q; q += kThreads)
+        if (cnt[q]) atomicAdd(&out_rank[q], (unsigned long long)cnt[q]);
+}
+
+inline int sweep_grid(const codae_ctx* ctx, int64_t n_rows) {
+    int64_t g = (n_rows + kWarps - 1) / kWarps;
+    const int64_t cap = (int64_t)ctx->sm_count * 4;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+inline size_t topk_smem(int QC, int E, int k) {
+    return (size_t)QC * E * 4 + (size_t)((QC + 3) & ~3) * 4 + (size_t)kWarps * QC * k * 12;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t codae_score_topk_workspace_bytes(const codae_ctx* ctx, int Q, int k) {
+    if (!ctx || Q < 1 || k < 1) return 0;
+    return (size_t)ctx->sm_count * 4 * 4 /*QC max*/ * (size_t)k * 12 + 256;
+}
+
+int codae_score_topk(codae_ctx* ctx, const void* catalog, int cat_dtype, int64_t n_rows, int64_t ld, int E,
+                     int64_t row_offset, const float* query, int Q, float inv_scale, int metric, int k, float* out_score,
+                     int64_t* out_idx, void* workspace, size_t ws_bytes, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && catalog && query && out_score && out_idx && workspace, "codae_score_topk: NULL argument");
+    CODAE_REQUIRE(ctx, k >= 1 && k <= kMaxK, "codae_score_topk: k %d outside [1, %d]", k, kMaxK);
+    CODAE_REQUIRE(ctx, Q >= 1 && n_rows >= 0, "codae_score_topk: bad Q / n_rows");
+    CODAE_REQUIRE(ctx, metric == CODAE_METRIC_SQERR || metric == CODAE_METRIC_COSINE, "codae_score_topk: bad metric %d", metric);
+    const bool bf = cat_dtype == CODAE_BF16;
+    CODAE_REQUIRE(ctx, cat_dtype == CODAE_F32 || bf, "codae_score_topk: bad cat_dtype %d", cat_dtype);
+    const int vec = bf ? 8 : 4;
+    CODAE_REQUIRE(ctx, E >= vec && E <= 4096 && E % vec == 0 && ld >= E && ld % vec == 0 &&
+                           (reinterpret_cast<uintptr_t>(catalog) & 15) == 0,
+                  "codae_score_topk: E=%d ld=%lld must be multiples of %d (16-byte rows), E <= 4096", E, (long long)ld, vec);
+    if (ws_bytes < codae_score_topk_workspace_bytes(ctx, Q, k))
+        return codae_fail(ctx, CODAE_ENOMEM, "codae_score_topk: workspace %zu < %zu bytes", ws_bytes,
+                          codae_score_topk_workspace_bytes(ctx, Q, k));
+    cudaStream_t s = as_stream(stream);
+    const int grid = sweep_grid(ctx, n_rows);
+    int64_t* ws_idx = reinterpret_cast<int64_t*>(workspace);
+    float* ws_score = reinterpret_cast<float*>(ws_idx + (size_t)grid * 4 * k);
+    for (int q0 = 0; q0 < Q; q0 += 4) {
+        const int qc = (Q - q0 >= 4) ? 4 : 1;
+        const int reps = (Q - q0 >= 4) ? 1 : (Q - q0);  // leftover queries one at a time
+        for (int rpt = 0; rpt < reps; ++rpt) {
+            const float* qptr = query + (int64_t)(q0 + rpt) * E;
+            const size_t smem = topk_smem(qc, E, k);
+#define LAUNCH(MET, QC, BF)                                                                                       \
+    do {                                                                                                          \
+        cudaFuncSetAttribute(score_topk_kernel<MET, QC, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        score_topk_kernel<MET, QC, BF><<<grid, kThreads, smem, s>>>(catalog, n_rows, ld, E, row_offset, qptr, inv_scale, k, \
+                                                                    ws_score, ws_idx);                           \
+    } while (0)
+            if (metric == CODAE_METRIC_SQERR) {
+                if (qc == 4) { if (bf) LAUNCH(CODAE_METRIC_SQERR, 4, true); else LAUNCH(CODAE_METRIC_SQERR, 4, false); }
+                else { if (bf) LAUNCH(CODAE_METRIC_SQERR, 1, true); else LAUNCH(CODAE_METRIC_SQERR, 1, false); }
+            } else {
+                if (qc == 4) { if (bf) LAUNCH(CODAE_METRIC_COSINE, 4, true); else LAUNCH(CODAE_METRIC_COSINE, 4, false); }
+                else { if (bf) LAUNCH(CODAE_METRIC_COSINE, 1, true); else LAUNCH(CODAE_METRIC_COSINE, 1, false); }
+            }
+#undef LAUNCH
+            int rc = codae_check_launch(ctx, "score_topk_kernel");
+            if (rc) return rc;
+            if (metric == CODAE_METRIC_SQERR)
+                topk_merge_kernel<CODAE_METRIC_SQERR><<<qc, kThreads, 0, s>>>(ws_score, ws_idx, grid, qc, k, out_score, out_idx, q0 + rpt, 1);
+            else
+                topk_merge_kernel<CODAE_METRIC_COSINE><<<qc, kThreads, 0, s>>>(ws_score, ws_idx, grid, qc, k, out_score, out_idx, q0 + rpt, 1);
+            rc = codae_check_launch(ctx, "topk_merge_kernel");
+            if (rc) return rc;
+        }
+    }
+    return CODAE_OK;
+}
+
+int codae_topk_merge(codae_ctx* ctx, const float* scores, const int64_t* idx, int G, int Q, int k, int metric,
+                     float* out_score, int64_t* out_idx, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && scores && idx && out_score && out_idx, "codae_topk_merge: NULL argument");
+    CODAE_REQUIRE(ctx, G >= 1 && Q >= 1 && k >= 1 && k <= kMaxK, "codae_topk_merge: bad shape");
+    if (metric == CODAE_METRIC_SQERR)
+        topk_merge_kernel<CODAE_METRIC_SQERR><<<Q, kThreads, 0, as_stream(stream)>>>(scores, idx, G, Q, k, out_score, out_idx, 0, 1);
+    else if (metric == CODAE_METRIC_COSINE)
+        topk_merge_kernel<CODAE_METRIC_COSINE><<<Q, kThreads, 0, as_stream(stream)>>>(scores, idx, G, Q, k, out_score, out_idx, 0, 1);
+    else
+        return codae_fail(ctx, CODAE_EINVAL, "codae_topk_merge: bad metric %d", metric);
+    return codae_check_launch(ctx, "topk_merge_kernel");
+}
+
+int codae_score_rank(codae_ctx* ctx, const void* catalog, int cat_dtype, int64_t n_rows, int64_t ld, int E,
+                     const float* query, int Q, float inv_scale, int metric, const int64_t* true_idx,
+                     const int64_t* subset_idx, int64_t n_subset, int64_t* out_rank, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && catalog && query && true_idx && out_rank, "codae_score_rank: NULL argument");
+    CODAE_REQUIRE(ctx, Q >= 1 && Q <= 1024, "codae_score_rank: Q %d outside [1, 1024]", Q);
+    const bool bf = cat_dtype == CODAE_BF16;
+    const int vec = bf ? 8 : 4;
+    CODAE_REQUIRE(ctx, E >= vec && E <= 4096 && E % vec == 0 && ld >= E && ld % vec == 0 &&
+                           (reinterpret_cast<uintptr_t>(catalog) & 15) == 0 && (reinterpret_cast<uintptr_t>(query) & 15) == 0,
+                  "codae_score_rank: E=%d ld=%lld must be multiples of %d", E, (long long)ld, vec);
+    cudaStream_t s = as_stream(stream);
+    if (!subset_idx) n_subset = n_rows;
+    cudaError_t e = cudaMemsetAsync(out_rank, 0, sizeof(int64_t) * Q, s);
+    if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    const int grid = sweep_grid(ctx, n_subset);
+    const size_t smem = (size_t)Q * 12;
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(out_rank);
+#define LAUNCH(MET, BF) score_rank_kernel<MET, BF><<<grid, kThreads, smem, s>>>(catalog, n_rows, ld, E, query, Q, inv_scale, true_idx, subset_idx, n_subset, out)
+    if (metric == CODAE_METRIC_SQERR) { if (bf) LAUNCH(CODAE_METRIC_SQERR, true); else LAUNCH(CODAE_METRIC_SQERR, false); }
+    else if (metric == CODAE_METRIC_COSINE) { if (bf) LAUNCH(CODAE_METRIC_COSINE, true); else LAUNCH(CODAE_METRIC_COSINE, false); }
+    else return codae_fail(ctx, CODAE_EINVAL, "codae_score_rank: bad metric %d", metric);
+#undef LAUNCH
+    return codae_check_launch(ctx, "score_rank_kernel");
+}
+
+}  // extern "C"

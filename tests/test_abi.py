@@ -1,0 +1,83 @@
+"""CPU: the C-ABI library loads, exports every symbol include/codae_b200.h declares, the ctypes table matches the
+header's arity, and the product fails loudly (never falls back) without a GPU."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "codae_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|size_t|const char\*)\s+(codae_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+        out[m.group(1)] = n
+    return out
+
+
+def test_header_vs_ctypes_table():
+    from codae import _C
+    fns = header_functions()
+    assert len(fns) >= 25
+    assert set(fns) == set(_C.SIGNATURES), set(fns) ^ set(_C.SIGNATURES)
+    for name, n in fns.items():
+        assert len(_C.SIGNATURES[name][1]) == n, name
+
+
+def test_library_exports_every_symbol():
+    from codae import _C
+    lib = _C.lib()
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    assert lib.codae_version() == 100
+    out = subprocess.run(["nm", "-D", "--defined-only", _C.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (codae_\w+)", out))
+    assert set(header_functions()) <= exported
+
+
+def test_sass_is_blackwell_native():
+    """tcgen05.mma / tcgen05.ld / TMA show up as UTCHMMA / LDTM / UTMALDG in the sm_100a SASS."""
+    from codae import _C
+    r = subprocess.run(["cuobjdump", "-sass", _C.LIB_PATH], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in r.stdout
+    for mnem in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnem in r.stdout, mnem
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_gpu_fails_loudly():
+    import ctypes
+    from codae import _C
+    out = ctypes.c_void_p()
+    rc = _C.lib().codae_ctx_create(0, ctypes.byref(out))
+    assert rc == _C.EARCH and not out.value
+    assert b"no CPU path" in _C.lib().codae_last_error(None)
+    with pytest.raises(RuntimeError):
+        _C.ctx()
+    from codae.model import EmbeddingDenoisingAutoencoder
+    m = EmbeddingDenoisingAutoencoder(48, 48, 16, 2, 2, False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(2, 48))
+    from codae.tool import Corrupter
+    c = Corrupter(4, [dict(size=16, position=16 * i) for i in range(3)], 1, torch.device("cpu"))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        c.get_masks((0, 1), 0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "mui-deepautoencoder_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                s = open(os.path.join(d, f)).read()
+                assert "oracle" not in s.replace("# oracle", ""), os.path.join(d, f)
