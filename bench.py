@@ -1,0 +1,447 @@
+"""bench.py -- CODAE hot path on B200: train samples/s (headline) + candidate scores/s, with roofline and CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload embedding|modanet|polyvore] [--dtype fp32|bf16]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU, NCCL)
+  python bench.py --impl reference ...   the reference's CPU implementation of the same step (oracle port), host cores
+
+A "step" is one pass of the training-step hot path over one batch of synthetic embeddings of the config's shape
+(corrupt -> encoder/decoder GEMMs -> loss -> backward GEMMs -> [all-reduce] -> clip -> Adam).  `value` is the
+whole-job samples/s with the dataset resident in HBM (timed with CUDA events, max over ranks); `e2e` is the same
+metric through the public API (codae.tool.FusedStep.step(staged=...)) with the batch rows coming from pinned host
+memory every step and the loss read back every step.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "mui-deepautoencoder_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (yaml, S, E, z, nin, nout, B per GPU, k_max, lr, wd, clip, default dtype, N observations)
+    "embedding": dict(yaml="config/embedding.yaml", S=3, E=512, z=1536, nin=4, nout=4, B=128, k_max=1, lr=1e-5, wd=1e-4,
+                      clip=True, dtype="fp32", N=131072, seed=27493045),
+    "modanet": dict(yaml="config/modanet_merge_top_bottom_shoe.yaml", S=3, E=512, z=1536, nin=3, nout=3, B=32, k_max=1,
+                    lr=1e-4, wd=1e-2, clip=False, dtype="bf16", N=131072, seed=50493213),
+    "polyvore": dict(yaml="config/polyvore_multislot.yaml", S=8, E=512, z=4096, nin=4, nout=4, B=8192, k_max=2, lr=1e-4,
+                     wd=1e-2, clip=True, dtype="bf16", N=262144, seed=50493213),
+}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tensor=d["bf16_tflops"], tensor_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def layer_dims(w):
+    from codae.model import EmbeddingDenoisingAutoencoder  # noqa: F401
+    io = w["S"] * w["E"]
+    inc_in, inc_out = (io - w["z"]) // w["nin"], (io - w["z"]) // w["nout"]
+    dims = [(io, io)]
+    last = None
+    for i in range(1, w["nin"]):
+        a, last = max(io - (i - 1) * inc_in, w["z"]), max(io - i * inc_in, w["z"])
+        dims.append((a, last))
+    dims.append((last, w["z"]))
+    for i in range(w["nout"]):
+        a, last = min(w["z"] + i * inc_out, io), min(w["z"] + (i + 1) * inc_out, io)
+        dims.append((a, last))
+    dims.append((last, io))
+    return dims
+
+
+def synthetic_rows(N, io, seed, device):
+    """Scaled dataset rows of the config's shape: |N(0,1)| * Bernoulli(0.7), divided by (max - min) like
+    ConcatenatedEmbeddingDataset does (reference concatenated_embedding_dataset.py:69-74)."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.randn((N, io), generator=g, device=device).abs_()
+    x *= (torch.rand((N, io), generator=g, device=device) < 0.7)
+    return x / float(x.max() - x.min())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's step on the host cores
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference(w, steps, warmup, seed=0):
+    from oracle import codae_oracle as O
+    torch.manual_seed(seed)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    io, B = w["S"] * w["E"], w["B"]
+    dims = layer_dims(w)
+    relu = [True] * len(dims)
+    relu[w["nin"]] = False
+    relu[-1] = False
+    W = [torch.empty(o, i).uniform_(-1, 1) * (6.0 / (i + o)) ** 0.5 for i, o in dims]
+    b = [torch.zeros(o) for _, o in dims]
+    dae = O.OracleDAE(W, b, relu, w["lr"], w["wd"], w["clip"])
+    n = max(4 * B, 1024)
+    data = synthetic_rows(n, io, seed, "cpu")
+    arch = [dict(size=w["E"], position=p) for p in range(0, io, w["E"])]
+    bm, nmiss, _ = O.binary_masks(arch, w["k_max"])
+    import random
+    random.seed(seed)
+    tbl = O.mask_table_compat(n, bm.shape[0])
+    rng = np.random.RandomState(seed)
+    t0 = None
+    for s in range(warmup + steps):
+        if s == warmup:
+            t0 = time.perf_counter()
+        idx = rng.randint(0, n, size=B).tolist()
+        _, fmask = O.get_masks(bm, nmiss, tbl, idx, 0, w["k_max"])       # the reference's per-sample Python loop
+        dae.step_embedding(data[idx], fmask)
+    dt = time.perf_counter() - t0
+    return dict(value=B * steps / dt, unit="samples/s", cores=cores, kind="port",
+                sample="%d steps of B=%d (%s layer sizes) with the oracle port of the reference step on %d host threads"
+                       % (steps, B, "x".join(str(o) for _, o in dims[:2]) + "...", cores), ms_per_step=1e3 * dt / steps)
+
+
+def cpu_scoring(E, rows=1_000_000):
+    from oracle import codae_oracle as O  # noqa: F401
+    cat = torch.rand(rows, E)
+    q = torch.rand(1, E)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        s = torch.nn.functional.cosine_similarity(cat, q)     # the reference's op (metering.py:67-69)
+        torch.topk(s, 10)
+    return rows * reps / (time.perf_counter() - t0)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", type=str, default="embedding", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", type=str, default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--catalog", type=int, default=10_000_000)
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    dtype = args.dtype or w["dtype"]
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    io = w["S"] * w["E"]
+    dims = layer_dims(w)
+    Wsum = sum(i * o for i, o in dims)
+    P = Wsum + sum(o for _, o in dims)
+    config = {"workload": "%s (%s): %d x Linear, io=%d, B=%d/GPU, k_max=%d" % (args.workload, w["yaml"], len(dims), io, w["B"], w["k_max"]),
+              "params": P, "l2_policy": "no flush: every step streams weights + Adam state (%.0f MB) and random dataset rows, "
+                                        "larger than the 126 MB L2" % (32.0 * P / 1e6),
+              "parallelism": "dp%d" % world}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = min(args.steps, 40 if args.workload != "polyvore" else 2)
+        r = cpu_reference(w, steps, min(args.warmup, 3))
+        print(json.dumps({"impl": "reference", "metric": "train samples/s", "value": r["value"], "unit": "samples/s",
+                          "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": config, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                          "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    from codae import _C
+    from codae.dataset import ConcatenatedEmbeddingDataset
+    from codae.model import EmbeddingDenoisingAutoencoder
+    from codae.tool import Corrupter, FusedStep
+    from codae.tool.inference import ComplementarityScorer, shard_rows
+
+    pk = peaks()
+    B, K, Wm = w["B"], args.steps, args.warmup
+    torch.manual_seed(w["seed"])
+    data = synthetic_rows(w["N"], io, w["seed"], dev)
+    ds = ConcatenatedEmbeddingDataset.__new__(ConcatenatedEmbeddingDataset)
+    ds.data, ds.nb_observation, ds.embedding_size, ds.nb_used_category = data, w["N"], w["E"], w["S"]
+    ds.arch = [dict(name=str(i), size=w["E"], type="regression", position=i * w["E"]) for i in range(w["S"])]
+    model = EmbeddingDenoisingAutoencoder(io, w["z"], w["E"], w["nin"], w["nout"], False)
+    assert model.dims == dims
+    model.set_compute_dtype(dtype)
+    model.to(dev)
+    cor = Corrupter(w["N"], ds.arch, w["k_max"], dev, seed=w["seed"])
+    fs = FusedStep(model, cor, data, lr=w["lr"], weight_decay=w["wd"], clip=w["clip"], world_size=world,
+                   use_graph=not args.no_graph)
+    rng = np.random.RandomState(w["seed"] + rank)
+    nb = Wm + K
+    batches = torch.from_numpy(rng.randint(0, w["N"], size=(nb, B))).to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: `value` ---------------------------------------------------------------------
+    for s in range(Wm):
+        fs.step(batches[s], global_batch=B * world)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(Wm, Wm + K):
+        fs.step(batches[s], global_batch=B * world)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop() if sampler else None
+    launches = K * fs.kernel_launches
+    loss_last = fs.last_loss(B)
+
+    # ---- end-to-end through the public API with host buffers: `e2e` -------------------------------------------------
+    table = cor.device_tables()[0]
+    host_rows = torch.empty((4, B, io), dtype=torch.float32).pin_memory()
+    host_tab = torch.empty((4, B, table.shape[1]), dtype=torch.int16).pin_memory()
+    for j in range(4):
+        host_rows[j].copy_(data[batches[j]].cpu())
+        host_tab[j].copy_(table[batches[j]].cpu())
+    st_rows = torch.empty((B, io), dtype=torch.float32, device=dev)
+    st_tab = torch.empty((B, table.shape[1]), dtype=torch.int16, device=dev)
+    loss_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+    Ke = max(10, K // 2)
+
+    def e2e_step(s):
+        st_rows.copy_(host_rows[s % 4], non_blocking=True)
+        st_tab.copy_(host_tab[s % 4], non_blocking=True)
+        fs.step(None, global_batch=B * world, staged=(st_rows, st_tab))
+        loss_host.copy_(fs.acc, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(loss_host[3]) / (B * io)
+
+    for s in range(5):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(Ke):
+        e2e_step(s)
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * Ke / (float(e2e_ms.item()) / 1e3)
+
+    # ---- per-kernel durations inside a real step (CUDA events on the launch stream) -> roofline ----------------------
+    prof = profile_step(fs, batches[0], B, world) if rank == 0 else None
+
+    # ---- scoring: candidate scores/s over a sharded synthetic catalog ---------------------------------------------------
+    scoring = None
+    if not args.no_scoring:
+        del data, fs
+        torch.cuda.empty_cache()
+        lo, n_local = shard_rows(args.catalog, world, rank)
+        g = torch.Generator(device=dev).manual_seed(w["seed"] + 17)
+        catalog = torch.rand((n_local, w["E"]), generator=g, device=dev)
+        q = torch.rand((1, w["E"]), generator=g, device=dev)
+        sc = ComplementarityScorer(catalog, w["E"], metric="sqerr", k=10, row_offset=lo)
+        for _ in range(3):
+            sc.topk(q)
+        barrier()
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            sc.topk(q)
+        e1.record()
+        barrier()
+        sms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        sweep_ms = float(sms.item()) / reps
+        # kernel alone (local sweep, no merge collective) for the roofline
+        e0.record()
+        for _ in range(reps):
+            sc.topk_local(q)
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / reps
+        bytes_per = n_local * w["E"] * 4
+        scoring = {"metric": "candidate-outfit scores/s", "value": args.catalog / (sweep_ms / 1e3), "unit": "scores/s",
+                   "catalog_rows": args.catalog, "E": w["E"], "dtype": "f32", "k": 10, "ms_per_sweep": sweep_ms, "scaling": "strong",
+                   "roofline": {"bound": "hbm", "achieved": bytes_per / (k_ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                "frac": bytes_per / (k_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None,
+                                "kernel": "score_topk_kernel (+merge)", "peak_source": pk["src"]}}
+        if rank == 0 and not args.no_cpu:
+            scoring["cpu_baseline"] = {"value": cpu_scoring(w["E"]), "unit": "scores/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "3 x cosine_similarity + topk over 1M x %d rows (the reference's op)" % w["E"]}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    out = {"metric": "train samples/s", "value": world * B * K / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": K,
+           "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32" if fs_dtype(dtype, model) == "fp32" else "bf16", "data": "synthetic", "config": config,
+           "loss_last_step": loss_last, "clocks": clocks,
+           "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": B * io * 4 + B * table.shape[1] * 2,
+                   "d2h_bytes_per_step": 32, "steps": Ke, "api": "codae.tool.FusedStep.step(staged=(rows, mask_table_rows))"},
+           "gpu_launches": launches, "cuda_graph": not args.no_graph,
+           "roofline": prof["roofline"] if prof else None, "kernels": prof["kernels"] if prof else None,
+           "step_floor": prof["floor"] if prof else None, "scoring": scoring}
+    if not args.no_cpu:
+        r = cpu_reference(w, 40 if args.workload != "polyvore" else 1, 3 if args.workload != "polyvore" else 1)
+        out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def fs_dtype(dtype, model):
+    from codae import _C
+    return "bf16" if model.engine_dtype() == _C.BF16 else "fp32"
+
+
+def profile_step(fs, idx, B, world):
+    """Times every kernel launch of one eager step with CUDA events on the launching stream (3 repetitions, mean),
+    groups them by kernel, and derives the roofline of the dominant one from its ALGORITHMIC bytes / flops."""
+    from codae import _C
+    pk = peaks()
+    model = fs.model
+    dims = model.dims
+    names = ["corrupt_fwd"] + ["linear_fwd"] * len(dims) + ["mse_loss_fwd_bwd"]
+    for l in range(len(dims) - 1, -1, -1):
+        names += ["linear_wgrad+colsum"] + (["linear_dgrad"] if l > 0 else [])
+    names += (["grad_sqnorm"] if fs.clip else []) + ["counter_add", "adam_step"]
+    # wrap the ctypes entry points with event pairs
+    wrapped = ["corrupt_fwd", "linear_fwd", "mse_loss_fwd_bwd", "linear_wgrad", "linear_dgrad", "grad_sqnorm", "counter_add", "adam_step"]
+    orig = {n: getattr(_C, n) for n in wrapped}
+    events = []
+
+    def wrap(n):
+        def f(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig[n](*a, **k)
+            e.record()
+            events.append((n, s, e))
+            return r
+        return f
+
+    saved_graph = fs.use_graph
+    fs.use_graph = False
+    totals = {}
+    reps = 3
+    try:
+        for n in wrapped:
+            setattr(_C, n, wrap(n))
+        import codae.tool.fused_step as F
+        for _ in range(reps):
+            events.clear()
+            fs.step(idx, global_batch=B * world)
+            torch.cuda.synchronize()
+            for n, s, e in events:
+                totals.setdefault(n, [0.0, 0])
+                totals[n][0] += s.elapsed_time(e)
+                totals[n][1] += 1
+    finally:
+        for n in wrapped:
+            setattr(_C, n, orig[n])
+        fs.use_graph = saved_graph
+    kernels = {n: {"ms_per_step": t / reps, "launches_per_step": c // reps, "us_per_launch": 1e3 * t / c} for n, (t, c) in totals.items()}
+    step_ms = sum(k["ms_per_step"] for k in kernels.values())
+    for k in kernels.values():
+        k["share"] = k["ms_per_step"] / step_ms
+    Wsum = sum(i * o for i, o in dims)
+    P = model.flat.numel()
+    io = dims[0][0]
+    bf = fs.eng == _C.BF16
+    sw = 2 if bf else 4
+    algo = {  # algorithmic bytes or flops per STEP of each kernel group
+        "adam_step": ("hbm", (28 + (2 if bf else 0)) * P),
+        "grad_sqnorm": ("hbm", 4 * P),
+        "corrupt_fwd": ("hbm", B * io * (4 + sw)),
+        "mse_loss_fwd_bwd": ("hbm", B * io * (4 + 4 + sw)),
+        "linear_fwd": ("tensor", 2.0 * B * Wsum),
+        "linear_wgrad": ("tensor", 2.0 * B * Wsum),
+        "linear_dgrad": ("tensor", 2.0 * B * (Wsum - dims[0][0] * dims[0][1])),
+    }
+    gemm_bytes = {"linear_fwd": Wsum * sw, "linear_dgrad": (Wsum - dims[0][0] * dims[0][1]) * sw, "linear_wgrad": Wsum * 4}
+    top = max((n for n in kernels if n in algo), key=lambda n: kernels[n]["ms_per_step"])
+    bound, work = algo[top]
+    sec = kernels[top]["ms_per_step"] / 1e3
+    if bound == "tensor" and B <= 1024:
+        # small batch: the contraction is bound by streaming the weights / writing dW once, not by the tensor pipe
+        bound, work = "hbm", gemm_bytes[top] + 2 * B * sum(i + o for i, o in dims) * sw
+    if bound == "hbm":
+        ach, peak, unit = work / sec / 1e9, pk["hbm"], "GB/s"
+    else:
+        ach, peak, unit = work / sec / 1e12, (pk["tensor_sustained"] if bf else pk["tensor_sustained"] / 2), "TFLOP/s"
+    roof = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None, "kernel": top,
+            "share_of_step": kernels[top]["share"], "peak_source": pk["src"],
+            "algorithmic_per_launch": work / kernels[top]["launches_per_step"]}
+    floor_bytes = 32 * P + 3 * Wsum * sw + B * 20 * io
+    floor = {"hbm_bytes_per_step": floor_bytes, "ms_at_peak": floor_bytes / (pk["hbm"] * 1e9) * 1e3,
+             "sum_of_kernel_ms": step_ms}
+    return {"kernels": kernels, "roofline": roof, "floor": floor}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,107 @@
+"""GPU parity tests of complementarity inference: top-k rankings bit-exact against the fp64 oracle, rank mode against
+the reference's RankingLoss golden values, shard/merge invariance, and size-independent properties at scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+@pytest.mark.parametrize("n,E,Q,k,metric,bf16", [(5000, 512, 1, 10, "sqerr", False), (5000, 512, 1, 10, "cosine", False),
+                                                 (20000, 512, 5, 100, "sqerr", False), (3000, 64, 4, 7, "cosine", False),
+                                                 (7, 512, 1, 10, "sqerr", False), (40000, 512, 2, 10, "sqerr", True),
+                                                 (1, 16, 1, 1, "cosine", False), (9000, 4096, 1, 128, "sqerr", False)])
+def test_topk_matches_oracle(n, E, Q, k, metric, bf16):
+    from oracle import codae_oracle as O
+    from codae.tool.inference import ComplementarityScorer
+    torch.manual_seed(n + E + k)
+    cat = torch.randn(n, E).abs() * (torch.rand(n, E) < 0.7)
+    if bf16:
+        cat = cat.to(torch.bfloat16)
+    q = torch.randn(Q, E).abs() * 0.3
+    if n > 10:
+        cat[n // 2] = cat[3]                      # exact duplicate rows: ties must resolve to the lower index
+        q[0] = cat[3].float() * 0.5 + 0.01
+    sc = ComplementarityScorer(cat.to(DEV).contiguous(), E, metric=metric, k=k, inv_scale=0.5, row_offset=1000)
+    s, i = sc.topk_local(q.to(DEV))
+    s, i = s.cpu(), i.cpu()
+    for qi in range(Q):
+        scores = O.score_candidates(cat.float(), q[qi], metric, inv_scale=0.5)
+        ws, wi = O.topk(scores, k, metric, row_offset=1000)
+        m = min(k, n)
+        assert i[qi, :m].tolist() == wi.tolist(), (qi, i[qi, :m], wi)
+        assert torch.all(i[qi, m:] == -1)
+        assert np.allclose(s[qi, :m].numpy(), ws.numpy(), rtol=2e-5, atol=1e-6)
+
+
+def test_topk_shard_merge_equals_unsharded():
+    from oracle import codae_oracle as O
+    from codae import _C
+    from codae.tool.inference import ComplementarityScorer, shard_rows
+    torch.manual_seed(0)
+    n, E, k, G = 30011, 512, 10, 4
+    cat = torch.randn(n, E).abs().to(DEV)
+    q = torch.randn(3, E).abs().to(DEV)
+    full_s, full_i = ComplementarityScorer(cat, E, "sqerr", k).topk_local(q)
+    full_s, full_i = full_s.clone(), full_i.clone()
+    parts_s, parts_i = [], []
+    for r in range(G):
+        lo, c = shard_rows(n, G, r)
+        s, i = ComplementarityScorer(cat[lo:lo + c], E, "sqerr", k, row_offset=lo).topk_local(q)
+        parts_s.append(s.clone()); parts_i.append(i.clone())
+    ms, mi = torch.empty_like(full_s), torch.empty_like(full_i)
+    _C.topk_merge(torch.stack(parts_s), torch.stack(parts_i), _C.METRIC_SQERR, ms, mi)
+    assert torch.equal(mi, full_i) and torch.equal(ms, full_s)
+    # and the same merge restated on the host
+    for qi in range(3):
+        _, wi = O.topk_merge([p[qi].cpu() for p in parts_s], [p[qi].cpu() for p in parts_i], k)
+        assert wi.tolist() == mi[qi].cpu().tolist()
+
+
+@pytest.mark.parametrize("name", ["emb_small"])
+def test_ranking_loss_matches_reference(name):
+    """RankingLoss.get (metering.py:46-79) on the golden validation batch: same ranks, same loss."""
+    from oracle import codae_oracle as O
+    from codae.dataset import ConcatenatedEmbeddingDataset
+    from codae.tool import RankingLoss
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    e = int(g["e"])
+    ncat = int(g["io"]) // e
+    ds = ConcatenatedEmbeddingDataset.from_tensors([torch.from_numpy(g["cat%d" % c]) for c in range(ncat)])
+    ds.to(DEV)
+    val = [int(v) for v in g["rank_val"]]
+    rl = RankingLoss(ds, val, device=DEV)
+    pred = torch.from_numpy(g["rank_pred"]).to(DEV)
+    fmask = torch.from_numpy(g["rank_fmask"]).to(DEV)
+    idx = tuple(int(i) for i in g["rank_idx"])
+    total, ranks = O.ranking_loss([torch.from_numpy(g["cat%d" % c]) for c in range(ncat)], e, val,
+                                  torch.from_numpy(g["rank_pred"]), torch.from_numpy(g["rank_fmask"]), idx)
+    assert rl.ranks(pred, fmask, idx).cpu().tolist() == ranks
+    assert abs(rl.get(pred, fmask, idx) - float(g["rank_loss"])) < 1e-9
+
+
+def test_scale_properties_planted_winners():
+    """2M x 512 fp32 (4 GB) catalog, too big for the oracle in seconds: plant k near-copies of the query at known
+    rows -> the top-k must be exactly those rows in order of their planted distance; bf16 catalog agrees."""
+    from codae.tool.inference import ComplementarityScorer
+    torch.manual_seed(5)
+    n, E, k = 2_000_000, 512, 10
+    g = torch.Generator(device=DEV).manual_seed(5)
+    cat = torch.rand((n, E), generator=g, device=DEV)
+    q = torch.rand((1, E), generator=g, device=DEV)
+    rows = torch.tensor([1_999_999, 7, 1_000_003, 55_555, 1_234_567, 0, 999_999, 424_242, 1_500_000, 31], device=DEV)
+    for j, r in enumerate(rows.tolist()):
+        cat[r] = q[0] + 1e-3 * (j + 1)           # squared error grows with j
+    s, i = ComplementarityScorer(cat, E, "sqerr", k).topk_local(q)
+    assert i[0].tolist() == rows.tolist()
+    assert torch.all(s[0, 1:] > s[0, :-1])
+    sb, ib = ComplementarityScorer(cat.to(torch.bfloat16), E, "sqerr", k).topk_local(q)
+    assert sorted(ib[0].tolist()) == sorted(rows.tolist())
+    # permutation invariance of the selected set: reversed catalog
+    s2, i2 = ComplementarityScorer(cat.flip(0).contiguous(), E, "sqerr", k).topk_local(q)
+    assert (n - 1 - i2[0]).tolist() == rows.tolist()

@@ -1,0 +1,320 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (codae._C) against oracle/ on the same seeded inputs.
+Bit-exact for masks / ids / indices; 1e-5 relative for fp32 arithmetic; 1e-2 for the bf16 tensor-core engine."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def C():
+    from codae import _C
+    _C.ctx(torch.device("cuda", 0))
+    return _C
+
+
+def arch_of(sizes):
+    arch, pos = [], 0
+    for s in sizes:
+        arch.append(dict(size=int(s), position=pos, type="regression"))
+        pos += int(s)
+    return arch
+
+
+def test_ctx_and_errors(C, dev):
+    c = C.ctx(dev)
+    assert C.lib().codae_ctx_sm_count(c) >= 100
+    with pytest.raises(RuntimeError, match="run"):
+        t = torch.zeros((4, 3), dtype=torch.int16, device=dev)
+        C.corrupt_fwd(torch.zeros(4, 8, device=dev), None, 4, t, 5, torch.zeros(3, dtype=torch.int64, device=dev),
+                      torch.zeros(8, dtype=torch.uint8, device=dev), 8, torch.zeros(4, 8, device=dev))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        C.mul_mask(torch.zeros(4), torch.zeros(4), torch.zeros(4))
+
+
+@pytest.mark.parametrize("nb_run,n", [(3, 1000), (9, 4177), (36, 513), (129, 300), (1, 5)])
+def test_philox_table_bit_exact(C, dev, nb_run, n):
+    from oracle.philox import philox_mask_table
+    for seed, first in [(27493045, 0), (0xDEADBEEFCAFE1234, 1 << 33)]:
+        got = C.mask_table_philox(seed, first, n, nb_run, dev).cpu().numpy()
+        want = philox_mask_table(seed, n, nb_run, first_observation=first)
+        assert got.dtype == np.int16 and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("sizes,k_max,B,bf16", [([16, 16, 16], 1, 8, False), ([512, 512, 512], 1, 128, False),
+                                                ([512] * 8, 2, 64, True), ([3, 1, 1, 1, 1, 1, 1, 1, 1], 3, 50, False),
+                                                ([4, 4, 4], 2, 1, False)])
+def test_corrupt_fwd_and_dense_masks(C, dev, sizes, k_max, B, bf16):
+    from oracle import codae_oracle as O
+    from codae.tool import Corrupter
+    torch.manual_seed(1)
+    arch = arch_of(sizes)
+    io = sum(sizes)
+    N = 3 * B + 7
+    data = torch.randn(N, io)
+    data[0, 0] = -0.0
+    data[1, :2] = torch.tensor([float("inf"), float("nan")])
+    cor = Corrupter(N, arch, k_max, dev, seed=99)
+    table, bits, col_var, nmiss = cor.device_tables()
+    bm, nm, _ = O.binary_masks(arch, k_max)
+    idx = torch.randperm(N)[:B]
+    idx[0] = 0
+    if B > 1:
+        idx[1] = 1
+    for run in sorted({0, cor.nb_run - 1}):
+        masks, fmask = O.get_masks(bm, nm, cor.mask_to_use, idx.tolist(), run, k_max)
+        want = O.corrupt(data[idx], fmask)
+        ld = (io + 7) // 8 * 8
+        cx = torch.zeros((B, ld), dtype=torch.bfloat16 if bf16 else torch.float32, device=dev)
+        x = torch.zeros((B, ld), device=dev)
+        mid = torch.zeros(B, dtype=torch.int32, device=dev)
+        C.corrupt_fwd(data.to(dev), idx.to(dev), B, table, run, bits, col_var, io, cx, x, mid)
+        assert torch.equal(mid.cpu().long(), cor.mask_to_use[idx, run])
+        assert torch.equal(x[:, :io].cpu().view(torch.int32), data[idx].view(torch.int32))  # gather is bit-exact
+        if bf16:
+            ok = ~torch.isnan(want)
+            assert torch.equal(cx[:, :io].cpu().view(torch.int16)[ok], want.to(torch.bfloat16).view(torch.int16)[ok])
+        else:
+            # bit-exact including -0.0 and NaN placement (x*mask semantics, embedding_denoising_autoencoder.py:239)
+            g, w = cx[:, :io].cpu(), want
+            assert torch.equal(torch.isnan(g), torch.isnan(w))
+            assert torch.equal(g.view(torch.int32)[~torch.isnan(w)], w.view(torch.int32)[~torch.isnan(w)])
+        gm, gf = cor.get_masks(idx, run)
+        assert torch.equal(gf.cpu(), fmask)
+        for k in range(k_max):
+            assert torch.equal(gm[k].cpu(), masks[k])
+    # staged path: rows + table rows already gathered, batch_idx = NULL
+    rows = data[idx].contiguous().to(dev)
+    trows = table[idx.to(dev)].contiguous()
+    cx2 = torch.zeros((B, ld), device=dev)
+    C.corrupt_fwd(rows, None, B, trows, 0, bits, col_var, io, cx2, None, None)
+    _, fm0 = O.get_masks(bm, nm, cor.mask_to_use, idx.tolist(), 0, k_max)
+    w0 = O.corrupt(data[idx], fm0)
+    ok = ~torch.isnan(w0)
+    assert torch.equal(cx2[:, :io].cpu()[ok], w0[ok])
+
+
+def test_mul_mask_matches_clone_times_mask(C, dev):
+    x = torch.randn(37, 48)
+    m = (torch.rand(37, 48) > 0.3).float()
+    out = torch.empty(37, 48, device=dev)
+    C.mul_mask(x.to(dev), m.to(dev), out)
+    assert torch.equal(out.cpu().view(torch.int32), (x.clone() * m).view(torch.int32))
+
+
+@pytest.mark.parametrize("sizes,B,ybf,dybf", [([16, 16, 16], 8, False, False), ([512, 512, 512], 128, False, False),
+                                              ([512, 512, 512], 32, False, True), ([512] * 8, 300, True, True),
+                                              ([3, 1, 1, 1, 1, 1, 1, 1, 1], 64, False, False)])
+def test_mse_loss_fwd_bwd(C, dev, sizes, B, ybf, dybf):
+    from oracle import codae_oracle as O
+    from codae.tool import Corrupter
+    torch.manual_seed(2)
+    arch, io = arch_of(sizes), sum(sizes)
+    N = B + 5
+    data = torch.rand(N, io)
+    y = torch.rand(B, io)
+    if ybf:
+        y = y.to(torch.bfloat16).float()
+    cor = Corrupter(N, arch, 1, dev, seed=5)
+    table, bits, col_var, _ = cor.device_tables()
+    idx = torch.randperm(N)[:B]
+    bm, nm, _ = O.binary_masks(arch, 1)
+    _, fmask = O.get_masks(bm, nm, cor.mask_to_use, idx.tolist(), 0, 1)
+    x = data[idx]
+    loss, dy = O.mse_mean_loss_and_grad(x, y)
+    full, part = O.embedding_monitors(x, y, fmask)
+    ld = (io + 7) // 8 * 8
+    yd = torch.zeros((B, ld), dtype=torch.bfloat16 if ybf else torch.float32, device=dev)
+    yd[:, :io] = y.to(dev)
+    dyd = torch.zeros((B, ld), dtype=torch.bfloat16 if dybf else torch.float32, device=dev)
+    mid = cor.mask_to_use[idx, 0].to(torch.int32).to(dev)
+    acc = torch.zeros(4, dtype=torch.float64, device=dev)
+    ws = C.loss_workspace(dev)
+    for rep in range(2):   # twice: the workspace ticket must reset itself, accumulators add up
+        C.mse_loss_fwd_bwd(data.to(dev), idx.to(dev), yd, mid, bits, col_var, B, io, 2.0 / (B * io), dyd, acc, ws)
+    a = acc.cpu().numpy()
+    assert abs(a[3] / (B * io) - float(loss)) <= 1e-6 * float(loss)
+    assert abs(a[0] - 2 * full) <= 1e-5 * 2 * full and abs(a[1] - 2 * part) <= 1e-5 * 2 * part and a[2] == 2 * B
+    tol = 1e-2 if dybf else 1e-6
+    assert rel(dyd[:, :io].float().cpu().numpy(), dy.numpy()) < tol
+    # forward-only (validation) call leaves dy untouched
+    C.mse_loss_fwd_bwd(data.to(dev), idx.to(dev), yd, mid, bits, col_var, B, io, 0.0, None, acc, ws)
+    assert acc.cpu().numpy()[2] == 3 * B
+
+
+@pytest.mark.parametrize("n,clip,wd,shadow", [(1000, True, 1e-4, False), (23_608_320 // 16 + 3, True, 1e-2, True),
+                                              (792, False, 1e-6, False), (5, True, 0.0, False)])
+def test_clip_adam_matches_torch_semantics(C, dev, n, clip, wd, shadow):
+    from oracle import codae_oracle as O
+    torch.manual_seed(3)
+    p0 = torch.randn(n) * 0.05
+    m = torch.zeros(n)
+    v = torch.zeros(n)
+    P, M, V = p0.clone().to(dev), m.clone().to(dev), v.clone().to(dev)
+    pad = (-n) % 8
+    if pad:   # buffers are 16-byte aligned and padded in the product; emulate with a padded allocation
+        P, M, V = [torch.cat([t, torch.zeros(pad, device=dev)])[:n] for t in (P, M, V)]
+    sh = torch.zeros(n, dtype=torch.bfloat16, device=dev) if shadow else None
+    sq = torch.zeros(1, device=dev)
+    ws = C.sqnorm_workspace(dev)
+    po = p0.clone()
+    for step in range(1, 4):
+        g = torch.randn(n) * (10.0 if step == 1 else 0.001)   # step 1 clips, later steps do not
+        G = g.clone().to(dev)
+        if clip:
+            C.grad_sqnorm(G, sq, ws)
+            assert abs(float(sq.item()) - float((g.double() ** 2).sum())) <= 1e-5 * float((g.double() ** 2).sum())
+        C.adam_step(P, G, M, V, sh, 1e-3, 0.9, 0.999, 1e-8, wd, step, 1.0 if clip else -1.0, sq if clip else None, 1.0)
+        gl = [g.clone()]
+        if clip:
+            gl, _ = O.clip_grad_norm(gl, 1.0)
+        O.adam_step([po], gl, [m], [v], step, 1e-3, wd)
+        # compare the update, not just the weights: |dp| ~ lr
+        assert rel((P.cpu() - p0).numpy(), (po - p0).numpy()) < 2e-5, step
+        assert rel(M.cpu().numpy(), m.numpy()) < 1e-5 and rel(V.cpu().numpy(), v.numpy()) < 1e-5
+    if shadow:
+        assert torch.equal(sh.cpu().view(torch.int16), P.cpu().to(torch.bfloat16).view(torch.int16))
+
+
+def test_adam_device_step_counter(C, dev):
+    """step_dev overrides the scalar step: the graph-replay path gives the same numbers as the host-scalar path."""
+    torch.manual_seed(4)
+    n = 4096
+    p = torch.randn(n)
+    g = torch.randn(n)
+    A = [t.clone().to(dev) for t in (p, torch.zeros(n), torch.zeros(n))]
+    Bf = [t.clone().to(dev) for t in (p, torch.zeros(n), torch.zeros(n))]
+    cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+    for step in range(1, 4):
+        C.adam_step(A[0], g.to(dev), A[1], A[2], None, 1e-3, 0.9, 0.999, 1e-8, 0.0, step, -1.0, None, 1.0)
+        C.counter_add(cnt, 1)
+        C.adam_step(Bf[0], g.to(dev), Bf[1], Bf[2], None, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, -1.0, None, 1.0, cnt)
+    assert int(cnt.item()) == 3
+    assert rel(Bf[0].cpu().numpy(), A[0].cpu().numpy()) < 1e-7
+
+
+@pytest.mark.parametrize("M,N,K", [(8, 48, 48), (64, 11, 11), (50, 7, 11), (128, 1536, 1536), (33, 597, 1066), (1, 128, 832)])
+def test_linear_f32_engine(C, dev, M, N, K):
+    """Exact-fp32 engine vs the reference's own addmm / mm on CPU (fp32 rounding differences only)."""
+    torch.manual_seed(5)
+    ldk, ldn = (K + 7) // 8 * 8, (N + 7) // 8 * 8
+    X = torch.randn(M, K)
+    W = torch.randn(N, K) / K ** 0.5
+    b = torch.randn(N)
+    dY = torch.randn(M, N)
+    Xd = torch.zeros(M, ldk, device=dev); Xd[:, :K] = X.to(dev)
+    Wd = torch.zeros(N, ldk, device=dev); Wd[:, :K] = W.to(dev)
+    dYd = torch.zeros(M, ldn, device=dev); dYd[:, :N] = dY.to(dev)
+    Y = torch.zeros(M, ldn, device=dev)
+    assert C.linear_engine(dev, C.F32, M, N, K) == C.ENGINE_SIMT_F32
+    C.linear_fwd(Xd, Wd[:, :K], b.to(dev), Y, M, N, K, C.ACT_RELU, C.F32)
+    want = torch.relu(torch.addmm(b, X, W.t()))
+    assert rel(Y[:, :N].cpu().numpy(), want.numpy()) < 1e-5
+    assert float(Y[:, N:].abs().sum()) == 0
+    C.linear_fwd(Xd, Wd[:, :K], None, Y, M, N, K, C.ACT_NONE, C.F32)
+    assert rel(Y[:, :N].cpu().numpy(), X.mm(W.t()).numpy()) < 1e-5
+    dX = torch.zeros(M, ldk, device=dev)
+    C.linear_dgrad(dYd, Wd[:, :K], Xd, dX, M, N, K, C.F32)
+    assert rel(dX[:, :K].cpu().numpy(), (dY.mm(W) * (X > 0)).numpy()) < 1e-5
+    C.linear_dgrad(dYd, Wd[:, :K], None, dX, M, N, K, C.F32)
+    assert rel(dX[:, :K].cpu().numpy(), dY.mm(W).numpy()) < 1e-5
+    dW = torch.zeros(N, ldk, device=dev)
+    db = torch.zeros(N, device=dev)
+    C.linear_wgrad(dYd, Xd, dW[:, :K], db, M, N, K, C.F32)
+    assert rel(dW[:, :K].cpu().numpy(), dY.t().mm(X).numpy()) < 1e-5
+    assert rel(db.cpu().numpy(), dY.sum(0).numpy()) < 1e-5
+    assert float(dW[:, K:].abs().sum()) == 0
+
+
+def _bf(t):
+    return t.to(torch.bfloat16).float()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 256, 128), (128, 1536, 1536), (32, 1536, 1536), (200, 192, 192),
+                                   (33, 600, 1064), (1, 128, 832), (512, 4096, 4096), (300, 328, 72)])
+def test_linear_tcgen05_engine(C, dev, M, N, K):
+    """bf16 tensor-core engine (tcgen05 + TMEM + TMA) vs an fp64 product of the same bf16-rounded operands.
+    Operands are exactly representable in bf16, so the only difference is fp32 accumulation order: tol 1e-4 of
+    the output scale (the north-star's 1e-2 is for the end-to-end bf16 step)."""
+    torch.manual_seed(6)
+    assert C.linear_engine(dev, C.BF16, M, N, K) == C.ENGINE_TCGEN05_BF16
+    X = _bf(torch.randn(M, K))
+    W = _bf(torch.randn(N, K) / K ** 0.5)
+    b = torch.randn(N)
+    dY = _bf(torch.randn(M, N))
+    bf = torch.bfloat16
+    Xd, Wd, dYd = X.to(dev, bf), W.to(dev, bf), dY.to(dev, bf)
+    # forward, bf16 out and f32 out
+    Y = torch.zeros(M, N, device=dev)
+    C.linear_fwd(Xd, Wd, b.to(dev), Y, M, N, K, C.ACT_RELU, C.BF16)
+    want = torch.relu(X.double().mm(W.double().t()) + b.double())
+    assert rel(Y.cpu().numpy(), want.numpy()) < 1e-4
+    Yb = torch.zeros(M, N, device=dev, dtype=bf)
+    C.linear_fwd(Xd, Wd, None, Yb, M, N, K, C.ACT_NONE, C.BF16)
+    assert rel(Yb.float().cpu().numpy(), X.double().mm(W.double().t()).numpy()) < 1e-2
+    # dgrad (B operand MN-major) with the ReLU mask epilogue
+    dX = torch.zeros(M, K, device=dev)
+    C.linear_dgrad(dYd, Wd, Xd, dX, M, N, K, C.BF16)
+    wantdx = dY.double().mm(W.double()) * (X > 0)
+    assert rel(dX.cpu().numpy(), wantdx.numpy()) < 1e-4
+    # wgrad (both operands MN-major) + bias column sums
+    dW = torch.zeros(N, K, device=dev)
+    db = torch.zeros(N, device=dev)
+    C.linear_wgrad(dYd, Xd, dW, db, M, N, K, C.BF16)
+    assert rel(dW.cpu().numpy(), dY.double().t().mm(X.double()).numpy()) < 1e-4
+    assert rel(db.cpu().numpy(), dY.double().sum(0).numpy()) < 1e-5
+
+
+def test_mixed_loss_and_monitor(C, dev):
+    from oracle import codae_oracle as O
+    from oracle.gen_golden import abalone_arch
+    from codae.tool.metering import arch_tables
+    g = np.load(os.path.join(GOLDEN, "abalone_k3.npz"))
+    arch = abalone_arch()
+    pos, size, typ = arch_tables(arch, dev)
+    w = torch.tensor(g["weight"], dtype=torch.float32)
+    for s in range(3):
+        x, y = torch.from_numpy(g["x%d" % s]), torch.from_numpy(g["y%d" % s])
+        loss, dy = O.combined_mean_loss_and_grad(arch, g["weight"], x, y)
+        assert abs(float(loss) - float(g["loss%d" % s])) < 2e-6 * float(loss)
+        B = x.shape[0]
+        xd = torch.zeros(B, 16, device=dev); xd[:, :11] = x.to(dev)
+        yd = torch.zeros(B, 16, device=dev); yd[:, :11] = y.to(dev)
+        dyd = torch.zeros(B, 16, device=dev)
+        out = torch.zeros(10, device=dev)
+        C.mixed_loss_fwd_bwd(xd, yd, pos, size, typ, w.to(dev), dyd, out)
+        assert abs(float(out[0]) - float(g["loss%d" % s])) <= 1e-5 * float(g["loss%d" % s])
+        assert rel(dyd[:, :11].cpu().numpy(), dy.numpy()) < 1e-5
+        # monitor
+        from codae.tool import Corrupter
+        cor = Corrupter(int(g["data"].shape[0]), arch, 3, dev)
+        cor.mask_to_use = torch.from_numpy(g["mask_to_use"])
+        table, bits, col_var, nmiss = cor.device_tables()
+        idx = torch.from_numpy(g["idx%d" % s])
+        mid = cor.mask_to_use[idx, int(g["run%d" % s])].to(torch.int32).to(dev)
+        mon = torch.zeros(B, 9, device=dev)
+        acc = torch.zeros(2 + 2 * 3 * 9, dtype=torch.float64, device=dev)
+        C.mixed_monitor(xd, yd, pos, size, typ, torch.from_numpy(g["norm_scale"]).to(dev), torch.from_numpy(g["norm_min"]).to(dev),
+                        3, mid, bits, nmiss, 3, mon, acc)
+        a = acc.cpu().numpy()
+        assert rel(mon.cpu().numpy(), g["mon%d" % s]) < 1e-5
+        assert abs(a[0] - g["mon%d" % s].sum()) <= 1e-5 * g["mon%d" % s].sum()
+        assert abs(a[1] - g["mon_partial%d" % s].sum()) <= 1e-5 * g["mon_partial%d" % s].sum()
+        assert rel(a[2:29].reshape(3, 9), g["mon_per_k%d" % s]) < 1e-5
+        assert rel(a[29:].reshape(3, 9), g["mon_partial_per_k%d" % s]) < 1e-5

@@ -1,0 +1,263 @@
+"""GPU parity tests of the whole training step against the golden vectors minted from the reference
+(tests/golden, oracle/gen_golden.py) and against the oracle at the shipped configs' full layer sizes.
+fp32 engine: loss / reconstructions / gradients / post-Adam weights within 1e-5 relative;
+bf16 tensor-core engine: within 1e-2 (BASELINE.json north_star tolerances)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def load_params(model, flat, shapes):
+    o = 0
+    for p, sh in zip(model.parameters(), shapes):
+        sh = [int(s) for s in sh if s > 0]
+        n = int(np.prod(sh))
+        p.data.copy_(torch.from_numpy(flat[o:o + n].copy()).reshape(sh))
+        o += n
+
+
+def flat_params(model):
+    return np.concatenate([p.detach().float().cpu().numpy().ravel() for p in model.parameters()])
+
+
+def flat_grads(model):
+    return np.concatenate([p.grad.detach().float().cpu().numpy().ravel() for p in model.parameters()])
+
+
+def build_embedding(g, dtype="fp32"):
+    from codae.dataset import ConcatenatedEmbeddingDataset
+    from codae.model import EmbeddingDenoisingAutoencoder
+    from codae.tool import Corrupter
+    io, e = int(g["io"]), int(g["e"])
+    ncat = io // e
+    ds = ConcatenatedEmbeddingDataset.from_tensors([torch.from_numpy(g["cat%d" % c]) for c in range(ncat)])
+    assert np.array_equal(ds.data.numpy(), g["data"])          # same scaling rule as the reference dataset
+    model = EmbeddingDenoisingAutoencoder(io, int(g["z"]), e, int(g["nin"]), int(g["nout"]), False)
+    load_params(model, g["init"], g["shapes"])
+    model.set_compute_dtype(dtype)
+    model.to(DEV)
+    ds.to(DEV)
+    cor = Corrupter(ds.nb_observation, ds.arch, int(g["k_max"]), DEV)
+    cor.mask_to_use = torch.from_numpy(g["mask_to_use"])        # inject the reference's table (plain attribute)
+    return ds, model, cor
+
+
+@pytest.mark.parametrize("name", ["emb_small", "emb_bottleneck", "emb_k2", "emb_mid"])
+def test_legacy_api_matches_reference(name):
+    """The reference's own call pattern: get_masks -> corrupt -> model() -> MSELoss -> backward -> clip -> Adam.step."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    ds, model, cor = build_embedding(g)
+    opt = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
+    crit = torch.nn.MSELoss(reduction="mean")
+    s = 0
+    while "idx%d" % s in g:
+        bi = tuple(int(i) for i in g["idx%d" % s])
+        x = torch.stack([ds[i][0] for i in bi])
+        masks, fmask = cor.get_masks(bi, 0)
+        assert np.array_equal(fmask.cpu().numpy(), g["fmask%d" % s])
+        cx = model.corrupt(input_data=x, mask=fmask)
+        assert np.array_equal(cx.cpu().numpy(), g["cx%d" % s])
+        y = model(cx)
+        loss = crit(x, y)
+        opt.zero_grad()
+        loss.backward()
+        assert rel(y.detach().cpu().numpy(), g["y%d" % s]) < 1e-5
+        assert abs(float(loss) - float(g["loss%d" % s])) <= 1e-5 * float(g["loss%d" % s])
+        assert rel(flat_grads(model), g["grads%d" % s]) < 1e-5
+        if bool(g["clip"]):
+            gn = torch.nn.utils.clip_grad_norm_(model.parameters(), 1)
+            assert abs(float(gn) - float(g["gnorm%d" % s])) <= 1e-5 * float(g["gnorm%d" % s])
+        opt.step()
+        assert rel(flat_params(model), g["post%d" % s]) < 1e-5
+        s += 1
+    assert s >= 2
+
+
+@pytest.mark.parametrize("name,graph", [("emb_small", False), ("emb_bottleneck", False), ("emb_k2", False), ("emb_mid", False),
+                                        ("emb_mid", True)])
+def test_fused_step_matches_reference(name, graph):
+    """FusedStep (the scripts' fast path): same observables, no autograd, flat-buffer clip + Adam kernels."""
+    from codae.tool import FusedStep
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    ds, model, cor = build_embedding(g)
+    fs = FusedStep(model, cor, ds.data, lr=float(g["lr"]), weight_decay=float(g["wd"]), clip=bool(g["clip"]), use_graph=graph)
+    B = int(g["B"])
+    s = 0
+    prev = g["init"]
+    while "idx%d" % s in g:
+        idx = torch.from_numpy(g["idx%d" % s]).to(DEV)
+        fs.step(idx, run=0)
+        assert abs(fs.last_loss(B) - float(g["loss%d" % s])) <= 1e-5 * float(g["loss%d" % s])
+        post = flat_params(model)
+        assert rel(post, g["post%d" % s]) < 1e-5
+        assert rel(post - prev, g["post%d" % s] - prev) < 5e-3       # the update itself
+        if not graph:
+            assert rel(flat_grads(model), g["grads%d" % s]) < 1e-5    # .grad are views of the flat gradient buffer
+            y = fs._bufs[B]["acts"][-1][:, :int(g["io"])]
+            assert rel(y.cpu().numpy(), g["y%d" % s]) < 1e-5
+            assert torch.equal(fs.last_mask_ids(B).cpu().long(), torch.from_numpy(g["mask_to_use"])[idx.cpu(), 0])
+        prev = g["post%d" % s]
+        s += 1
+    mon = fs.read_monitors()
+    ftl = sum(float(g["ftl%d" % i]) for i in range(s))
+    ptl = sum(float(g["ptl%d" % i]) for i in range(s))
+    assert abs(mon["full"] - ftl) <= 1e-5 * ftl and abs(mon["partial"] - ptl) <= 1e-5 * ptl and mon["rows"] == s * B
+
+
+def test_fused_step_bf16_within_1e2():
+    """bf16 tensor-core engine on the golden run: loss within 1e-2 relative, weights track the fp32 reference."""
+    from codae import _C
+    from codae.tool import FusedStep
+    g = np.load(os.path.join(GOLDEN, "emb_mid.npz"))
+    ds, model, cor = build_embedding(g, dtype="bf16")
+    assert model.engine_dtype() == _C.BF16
+    fs = FusedStep(model, cor, ds.data, lr=float(g["lr"]), weight_decay=float(g["wd"]), clip=True)
+    B = int(g["B"])
+    for s in range(2):
+        fs.step(torch.from_numpy(g["idx%d" % s]).to(DEV), run=0)
+        assert abs(fs.last_loss(B) - float(g["loss%d" % s])) <= 1e-2 * float(g["loss%d" % s])
+        y = fs._bufs[B]["acts"][-1][:, :int(g["io"])]
+        assert rel(y.cpu().numpy(), g["y%d" % s]) < 1e-2
+    assert rel(flat_params(model), g["post1"]) < 1e-2
+    assert torch.equal(model.flat_bf16.view(torch.int16), model.flat.to(torch.bfloat16).view(torch.int16))
+
+
+@pytest.mark.parametrize("name", ["abalone_k1", "abalone_k3"])
+def test_abalone_fused_and_legacy(name):
+    from oracle.gen_golden import abalone_arch
+    from codae.dataset import MixedVariableDataset
+    from codae.model import MixedVariableDenoisingAutoencoder
+    from codae.tool import CombinedCriterion, Corrupter, FusedStep
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    arch = abalone_arch()
+    k_max, B = int(g["k_max"]), int(g["B"])
+
+    def build():
+        ds = MixedVariableDataset.from_arch(arch, torch.from_numpy(g["data"]))
+        m = MixedVariableDenoisingAutoencoder(arch, 11, int(g["z"]), DEV, 2, 2, bool(g["steep"]))
+        load_params(m, g["init"], g["shapes"])
+        m.to(DEV)
+        ds.to(DEV)
+        cor = Corrupter(ds.nb_observation, arch, k_max, DEV)
+        cor.mask_to_use = torch.from_numpy(g["mask_to_use"])
+        return ds, m, cor
+
+    # fused path
+    ds, model, cor = build()
+    fs = FusedStep(model, cor, ds.data, lr=float(g["lr"]), weight_decay=float(g["wd"]), clip=True,
+                   mixed=dict(arch=arch, weight=list(g["weight"]), norm_scale=torch.from_numpy(g["norm_scale"]),
+                              norm_min=torch.from_numpy(g["norm_min"]), norm_first=3))
+    tot = dict(ftl=0.0, ptl=0.0, fk=0.0, pk=0.0)
+    for s in range(3):
+        fs.step(torch.from_numpy(g["idx%d" % s]).to(DEV), run=int(g["run%d" % s]))
+        assert abs(fs.last_loss(B) - float(g["loss%d" % s])) <= 1e-5 * float(g["loss%d" % s])
+        assert rel(flat_grads(model), g["grads%d" % s]) < 1e-5
+        assert rel(flat_params(model), g["post%d" % s]) < 1e-5
+        tot["ftl"] += g["mon%d" % s].sum(); tot["ptl"] += g["mon_partial%d" % s].sum()
+        tot["fk"] = tot["fk"] + g["mon_per_k%d" % s]; tot["pk"] = tot["pk"] + g["mon_partial_per_k%d" % s]
+    mon = fs.read_monitors()
+    assert abs(mon["ftl"] - tot["ftl"]) <= 1e-5 * tot["ftl"] and abs(mon["ptl"] - tot["ptl"]) <= 1e-5 * tot["ptl"]
+    assert rel(mon["ftl_per_k"], tot["fk"]) < 1e-5 and rel(mon["ptl_per_k"], tot["pk"]) < 1e-5
+
+    # legacy path: CombinedCriterion + autograd + torch Adam, as train_dae_on_abalone.py:206-236 calls them
+    ds, model, cor = build()
+    opt = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
+    crit = CombinedCriterion(arch=arch, k_max=k_max, device=DEV, observation_mask=torch.tensor([0, 0, 0] + [1] * 8),
+                             weight=list(g["weight"]), reduction="mean")
+    mon_c = CombinedCriterion(arch=arch, k_max=k_max, device=DEV, observation_mask=torch.tensor([0, 0, 0] + [1] * 8), reduction="none")
+    for s in range(3):
+        bi = tuple(int(i) for i in g["idx%d" % s])
+        x = torch.stack([ds[i][0] for i in bi])
+        masks, fmask = cor.get_masks(bi, int(g["run%d" % s]))
+        y = model(model.corrupt(input_data=x, mask=fmask))
+        loss = crit(x=x, y=y)
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1)
+        opt.step()
+        assert abs(float(loss) - float(g["loss%d" % s])) <= 1e-5 * float(g["loss%d" % s])
+        assert rel(flat_params(model), g["post%d" % s]) < 1e-5
+        xd, yd = x.clone(), y.detach().clone()
+        sc, mn = torch.from_numpy(g["norm_scale"]).to(DEV), torch.from_numpy(g["norm_min"]).to(DEV)
+        xd[:, 3:] = xd[:, 3:] * sc + mn
+        yd[:, 3:] = yd[:, 3:] * sc + mn
+        ml = mon_c(xd, yd, as_numpy=True)
+        assert rel(ml, g["mon%d" % s]) < 1e-5
+        assert rel(mon_c.get_per_k(ml, masks), g["mon_per_k%d" % s]) < 1e-5
+
+
+@pytest.mark.parametrize("cfg,B,dtype,tol", [("embedding", 128, "fp32", 1e-5), ("modanet", 32, "fp32", 1e-5),
+                                             ("modanet", 32, "bf16", 1e-2), ("bottleneck", 64, "fp32", 1e-5)])
+def test_full_size_step_vs_oracle(cfg, B, dtype, tol):
+    """BASELINE configs at their real layer sizes (10 x 1536^2 / 8 x 1536^2 / the 1067-598-... bottleneck):
+    two fused steps vs the oracle on the same seeded inputs."""
+    from oracle import codae_oracle as O
+    from oracle.philox import philox_mask_table
+    from codae.dataset import ConcatenatedEmbeddingDataset
+    from codae.model import EmbeddingDenoisingAutoencoder
+    from codae.tool import Corrupter, FusedStep
+    torch.manual_seed(11)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    z, nin, nout, lr, wd, clip = {"embedding": (1536, 4, 4, 1e-5, 1e-4, True), "modanet": (1536, 3, 3, 1e-4, 1e-2, False),
+                                  "bottleneck": (128, 3, 3, 1e-4, 1e-4, True)}[cfg]
+    N, E, S = 512, 512, 3
+    cats = [torch.randn(N, E).abs() * (torch.rand(N, E) < 0.7) for _ in range(S)]
+    ds = ConcatenatedEmbeddingDataset.from_tensors(cats)
+    model = EmbeddingDenoisingAutoencoder(S * E, z, E, nin, nout, False)
+    W = [l.weight.detach().clone() for l in model.linears()]
+    b = [l.bias.detach().clone() for l in model.linears()]
+    data_cpu = ds.data.clone()
+    model.set_compute_dtype(dtype)
+    model.to(DEV)
+    ds.to(DEV)
+    cor = Corrupter(N, ds.arch, 1, DEV, seed=2024)
+    tbl = torch.from_numpy(philox_mask_table(2024, N, 3).astype(np.int64))
+    assert torch.equal(tbl, cor.mask_to_use)
+    fs = FusedStep(model, cor, ds.data, lr=lr, weight_decay=wd, clip=clip)
+    dae = O.OracleDAE(W, b, model.relu, lr, wd, clip)
+    bm, nm, _ = O.binary_masks(ds.arch, 1)
+    perm = torch.randperm(N)
+    for s in range(2):
+        idx = perm[s * B:(s + 1) * B]
+        fs.step(idx.to(DEV), run=0)
+        _, fmask = O.get_masks(bm, nm, tbl, idx.tolist(), 0, 1)
+        r = dae.step_embedding(data_cpu[idx], fmask)
+        assert abs(fs.last_loss(B) - r["loss"]) <= tol * abs(r["loss"]), (s, fs.last_loss(B), r["loss"])
+        y = fs._bufs[B]["acts"][-1][:, :S * E]
+        assert rel(y.cpu().numpy(), r["y"].numpy()) < tol
+    want = np.concatenate([t.numpy().ravel() for t in dae.params()])
+    assert rel(flat_params(model), want) < tol
+    if dtype == "fp32":
+        init = np.concatenate([t.numpy().ravel() for pair in zip(W, b) for t in pair])
+        assert rel(flat_params(model) - init, want - init) < 1e-2      # the two Adam updates themselves
+
+
+def test_ragged_last_batch_and_validation_pass():
+    """No drop_last in the reference: the last batch is smaller; evaluate() = forward + monitors only."""
+    from codae.tool import FusedStep
+    g = np.load(os.path.join(GOLDEN, "emb_small.npz"))
+    ds, model, cor = build_embedding(g)
+    fs = FusedStep(model, cor, ds.data, lr=1e-3, weight_decay=0.0, clip=False)
+    before = flat_params(model)
+    out = fs.evaluate(torch.arange(5, device=DEV), run=0)
+    assert np.array_equal(flat_params(model), before) and out.shape == (5, 48)
+    x = ds.data[:5]
+    m = fs.read_monitors()
+    assert abs(m["full"] - float(((x - out) ** 2).sum())) <= 1e-5 * m["full"] and m["rows"] == 5
+    fs.step(torch.arange(8, device=DEV))
+    fs.step(torch.arange(8, 11, device=DEV))     # ragged: B = 3
+    assert not np.array_equal(flat_params(model), before)
+    assert np.isfinite(fs.last_loss(3))
