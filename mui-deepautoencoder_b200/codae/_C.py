@@ -54,7 +54,7 @@ SIGNATURES = {
 }
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()   # re-entrant: ctx() loads the library under the same lock
 _ctxs = {}
 
 
