@@ -30,6 +30,7 @@ SIGNATURES = {
     "codae_ctx_destroy": (_i, [_vp]),
     "codae_last_error": (_c.c_char_p, [_vp]),
     "codae_ctx_sm_count": (_i, [_vp]),
+    "codae_ctx_set_workspace": (_i, [_vp, _vp, _sz]),
     "codae_linear_engine": (_i, [_vp, _i, _i, _i, _i]),
     "codae_mask_table_philox": (_i, [_vp, _u64, _i64, _i64, _i, _vp, _vp]),
     "codae_corrupt_fwd": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i64, _vp, _i64, _vp, _vp]),
@@ -96,6 +97,32 @@ def ctx(device=None):
                 c = out
                 _ctxs[dev] = c
     return c
+
+
+_workspaces = {}
+WORKSPACE_BYTES = 64 << 20
+
+
+def ensure_workspace(device):
+    """Registers (once per device) the zero-initialised scratch the tensor-core engine uses for split-K partial
+    tiles; owned here so it outlives every call that borrows it."""
+    c = ctx(device)
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _workspaces:
+        ws = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
+        check(lib().codae_ctx_set_workspace(c, p(ws), ws.numel()), c)
+        _workspaces[key] = ws
+    return _workspaces[key]
+
+
+def disable_workspace(device):
+    """Un-registers the scratch buffer (split-K off); used by tests to compare against the single-pass kernel."""
+    c = ctx(device)
+    dev = torch.device(device)
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    check(lib().codae_ctx_set_workspace(c, None, 0), c)
+    _workspaces.pop(key, None)
 
 
 def check(rc, c):

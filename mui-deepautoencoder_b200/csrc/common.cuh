@@ -17,6 +17,8 @@ struct codae_ctx {
     int cc_major, cc_minor;
     char err[512];
     void* encode_tiled;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
+    void* ws;            // caller-registered scratch (split-K partials + tickets); zero-initialised by the caller
+    size_t ws_bytes;
     std::mutex mu;
 };
 

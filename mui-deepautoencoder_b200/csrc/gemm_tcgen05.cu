@@ -24,6 +24,8 @@ constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
 constexpr uint32_t kATileBytes = BM * BK * 2;  // 16 KB
+constexpr int kMaxTickets = 4096;
+constexpr size_t kTicketBytes = kMaxTickets * sizeof(unsigned int);
 
 struct Params {
     int M, N, K;
@@ -35,6 +37,8 @@ struct Params {
     int act;
     const __nv_bfloat16* mask_src;
     long long ldm;
+    float* ws_partials;          // split-K: [tile][split][128][BN] fp32 partial accumulators
+    unsigned int* ws_tickets;    // split-K: one arrival counter per output tile (self-resetting)
 };
 
 template <int BN>
@@ -132,6 +136,62 @@ __device__ __forceinline__ uint32_t make_idesc(int n, bool a_kmajor, bool b_kmaj
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// Fused epilogue of one 32-column chunk of one output row: bias + activation / ReLU mask, cast, vector stores.
+__device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, float (&f)[32]) {
+    const bool full = col0 + 32 <= p.N;
+    if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+    }
+    if (p.act == CODAE_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    if (p.mask_src) {
+        const __nv_bfloat16* mrow = p.mask_src + (long long)row * p.ldm + col0;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint4 mv = *reinterpret_cast<const uint4*>(mrow + 8 * j);
+                const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    if (!(bf16_lo(w[t]) > 0.f)) f[8 * j + 2 * t] = 0.f;
+                    if (!(bf16_hi(w[t]) > 0.f)) f[8 * j + 2 * t + 1] = 0.f;
+                }
+            }
+        } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j)
+                if (!(__bfloat162float(mrow[j]) > 0.f)) f[j] = 0.f;
+        }
+    }
+    if (p.c_bf16) {
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                *reinterpret_cast<uint4*>(crow + 8 * j) = o;
+            }
+        } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __float2bfloat16_rn(f[j]);
+        }
+    } else {
+        float* crow = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                *reinterpret_cast<float4*>(crow + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+            for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = f[j];
+        }
+    }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                 const __grid_constant__ CUtensorMap tma_b, const Params p) {
@@ -142,10 +202,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     uint64_t* empty_bar = full_bar + C::kStages;
     uint64_t* tmem_full_bar = empty_bar + C::kStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    volatile uint32_t* last_flag = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int num_kb = (p.K + BK - 1) / BK;
+    const int total_kb = (p.K + BK - 1) / BK;
+    const int nsplit = gridDim.z;
+    const int kb_per = (total_kb + nsplit - 1) / nsplit;
+    const int kb_begin = blockIdx.z * kb_per;
+    const int num_kb = min(total_kb, kb_begin + kb_per) - kb_begin;      // >= 1 by construction (host)
+    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
@@ -171,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 uint8_t* a_dst = smem + s * C::kStageBytes;
                 uint8_t* b_dst = a_dst + kATileBytes;
                 mbar_expect_tx(&full_bar[s], C::kStageBytes);
-                const int k0 = kb * BK;
+                const int k0 = (kb_begin + kb) * BK;
                 if (p.a_kmajor) {
                     tma_load_2d(&tma_a, &full_bar[s], a_dst, k0, m0);                       // box {64 k, 128 m}
                 } else {
@@ -209,72 +275,63 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
             umma_commit(tmem_full_bar);              // accumulator complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> HBM =====
+        // ===== epilogue: TMEM -> registers -> HBM (or split-K partials) =====
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < p.M;
+        float* ws_row = nsplit > 1 ? p.ws_partials + ((size_t)(tile_id * nsplit + blockIdx.z) * BM + (q * 32 + lane)) * BN
+                                   : nullptr;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
             const int col0 = n0 + c * 32;
-            if (!row_ok || col0 >= p.N) continue;
-            float f[32];
+            if (nsplit == 1) {
+                if (!row_ok || col0 >= p.N) continue;
+                float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            const bool full = col0 + 32 <= p.N;
-            if (p.bias) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-            }
-            if (p.act == CODAE_ACT_RELU) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (p.mask_src) {
-                const __nv_bfloat16* mrow = p.mask_src + (long long)row * p.ldm + col0;
-                if (full) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 mv = *reinterpret_cast<const uint4*>(mrow + 8 * j);
-                        const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            if (!(bf16_lo(w[t]) > 0.f)) f[8 * j + 2 * t] = 0.f;
-                            if (!(bf16_hi(w[t]) > 0.f)) f[8 * j + 2 * t + 1] = 0.f;
-                        }
-                    }
-                } else {
-                    for (int j = 0; j < 32 && col0 + j < p.N; ++j)
-                        if (!(__bfloat162float(mrow[j]) > 0.f)) f[j] = 0.f;
-                }
-            }
-            if (p.c_bf16) {
-                __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
-                if (full) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 o;
-                        o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-                        o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-                        o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-                        o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-                        *reinterpret_cast<uint4*>(crow + 8 * j) = o;
-                    }
-                } else {
-                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __float2bfloat16_rn(f[j]);
-                }
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                store_chunk(p, row, col0, f);
             } else {
-                float* crow = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
-                if (full) {
+                float4* dst = reinterpret_cast<float4*>(ws_row + c * 32);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        *reinterpret_cast<float4*>(crow + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                } else {
-                    for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = f[j];
+                for (int j = 0; j < 8; ++j)
+                    __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+            }
+        }
+        if (nsplit > 1) {
+            // split-K fix-up: the last CTA to arrive for this output tile sums all partials in split order
+            // (fixed order => bitwise reproducible) and applies the epilogue.
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) *last_flag = (atomicAdd(&p.ws_tickets[tile_id], 1u) == (unsigned)nsplit - 1u) ? 1u : 0u;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (*last_flag) {
+                __threadfence();
+                if (row_ok) {
+#pragma unroll 1
+                    for (int c = 0; c < BN / 32; ++c) {
+                        const int col0 = n0 + c * 32;
+                        if (col0 >= p.N) break;
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+                        for (int sp = 0; sp < nsplit; ++sp) {
+                            const float4* src = reinterpret_cast<const float4*>(
+                                p.ws_partials + ((size_t)(tile_id * nsplit + sp) * BM + (q * 32 + lane)) * BN + c * 32);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 t = __ldcg(src + j);
+                                f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                            }
+                        }
+                        store_chunk(p, row, col0, f);
+                    }
                 }
+                if (threadIdx.x == 64) p.ws_tickets[tile_id] = 0;
             }
         }
     }
@@ -323,13 +380,30 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_dtype == CODAE_BF16;
     p.bias = g.bias; p.act = g.act;
     p.mask_src = reinterpret_cast<const __nv_bfloat16*>(g.mask_src); p.ldm = g.ldm;
+    // split-K: small-batch contractions have too few output tiles to keep 148 SMs streaming the weights, so the
+    // k-blocks of one tile are spread over gridDim.z CTAs (fix-up by the last arriver, deterministic order).
+    const int tiles = ((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM);
+    const int total_kb = (g.K + BK - 1) / BK;
+    int nsplit = 1;
+    if (ctx->ws && tiles < ctx->sm_count && total_kb >= 4 && tiles <= kMaxTickets) {
+        int want = ctx->sm_count / tiles;
+        if (want > total_kb / 2) want = total_kb / 2;             // at least 2 k-blocks per split
+        if (want > 1) {
+            const int kb_per = (total_kb + want - 1) / want;
+            nsplit = (total_kb + kb_per - 1) / kb_per;               // no empty split
+            const size_t need = kTicketBytes + (size_t)tiles * nsplit * BM * BN * sizeof(float);
+            if (need > ctx->ws_bytes) nsplit = 1;
+        }
+    }
+    p.ws_tickets = reinterpret_cast<unsigned int*>(ctx->ws);
+    p.ws_partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->ws) + kTicketBytes);
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc05_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
         if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaFuncSetAttribute(smem=%u): %s", C::kSmemBytes, cudaGetErrorString(e));
         attr_set = true;
     }
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit);
     tc05_gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, p);
     return codae_check_launch(ctx, "tc05_gemm_kernel");
 }
@@ -346,7 +420,7 @@ bool codae_tc05_supported(const codae_ctx* ctx, const Tc05Gemm& g) {
     if (g.c_dtype == CODAE_BF16 ? (g.ldc % 8) : (g.ldc % 4)) return false;
     if (g.mask_src && (!al16(g.mask_src) || (g.ldm % 8))) return false;
     // tiny problems (abalone 11x11) are not worth a 128-row tensor-core tile
-    if (g.N < 32 || g.K < 32) return false;
+    if (g.N < 32) return false;
     return true;
 }
 

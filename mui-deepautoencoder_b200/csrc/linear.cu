@@ -6,7 +6,7 @@
 #include "gemm.h"
 
 namespace {
-inline bool tc_shape_ok(int M, int N, int K) { return M >= 1 && N >= 32 && K >= 32; }
+inline bool tc_shape_ok(int M, int N, int K) { return M >= 1 && N >= 32 && K >= 32; }  // layer dims; the batch may be 1
 }
 
 extern "C" {

@@ -35,6 +35,7 @@ fm.FlatMLP.to = to
 import codae.tool.data_tool as dtl
 dtl.Corrupter._cuda_device = lambda self: torch.device("cpu")
 torch.cuda.synchronize = lambda *a: None
+torch.cuda.current_device = lambda: 0
 
 from codae.dataset import ConcatenatedEmbeddingDataset, MixedVariableDataset
 from codae.model import EmbeddingDenoisingAutoencoder, MixedVariableDenoisingAutoencoder
