@@ -109,6 +109,8 @@ def ensure_workspace(device):
     c = ctx(device)
     dev = torch.device(device)
     key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if os.environ.get("CODAE_NO_SPLITK"):      # A/B switch for benchmarking the single-pass kernels
+        return None
     if key not in _workspaces:
         ws = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
         check(lib().codae_ctx_set_workspace(c, p(ws), ws.numel()), c)

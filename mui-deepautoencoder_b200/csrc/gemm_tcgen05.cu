@@ -25,6 +25,7 @@ constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
 constexpr uint32_t kATileBytes = BM * BK * 2;  // 16 KB
 constexpr int kMaxTickets = 4096;
+constexpr int kMaxSplit = 8;
 constexpr size_t kTicketBytes = kMaxTickets * sizeof(unsigned int);
 
 struct Params {
@@ -37,6 +38,7 @@ struct Params {
     int act;
     const __nv_bfloat16* mask_src;
     long long ldm;
+    int stages;                  // pipeline depth actually used (<= Cfg::kStages)
     float* ws_partials;          // split-K: [tile][split][128][BN] fp32 partial accumulators
     unsigned int* ws_tickets;    // split-K: one arrival counter per output tile (self-resetting)
 };
@@ -136,22 +138,24 @@ __device__ __forceinline__ uint32_t make_idesc(int n, bool a_kmajor, bool b_kmaj
            ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-// Fused epilogue of one 32-column chunk of one output row: bias + activation / ReLU mask, cast, vector stores.
-__device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, float (&f)[32]) {
-    const bool full = col0 + 32 <= p.N;
+// Fused epilogue of one W-column chunk (W = 16 or 32) of one output row: bias + activation / ReLU mask of the
+// layer input, cast, 128-bit stores.
+template <int W>
+__device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, float (&f)[W]) {
+    const bool full = col0 + W <= p.N;
     if (p.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+        for (int j = 0; j < W; ++j) if (full || col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
     }
     if (p.act == CODAE_ACT_RELU) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        for (int j = 0; j < W; ++j) f[j] = fmaxf(f[j], 0.f);
     }
     if (p.mask_src) {
         const __nv_bfloat16* mrow = p.mask_src + (long long)row * p.ldm + col0;
         if (full) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < W / 8; ++j) {
                 const uint4 mv = *reinterpret_cast<const uint4*>(mrow + 8 * j);
                 const uint32_t w[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
@@ -161,15 +165,16 @@ __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, 
                 }
             }
         } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j)
-                if (!(__bfloat162float(mrow[j]) > 0.f)) f[j] = 0.f;
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (col0 + j < p.N && !(__bfloat162float(mrow[j]) > 0.f)) f[j] = 0.f;
         }
     }
     if (p.c_bf16) {
         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
         if (full) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < W / 8; ++j) {
                 uint4 o;
                 o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
                 o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
@@ -178,16 +183,18 @@ __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, 
                 *reinterpret_cast<uint4*>(crow + 8 * j) = o;
             }
         } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = __float2bfloat16_rn(f[j]);
+#pragma unroll
+            for (int j = 0; j < W; ++j) if (col0 + j < p.N) crow[j] = __float2bfloat16_rn(f[j]);
         }
     } else {
         float* crow = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col0;
         if (full) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
+            for (int j = 0; j < W / 4; ++j)
                 *reinterpret_cast<float4*>(crow + 4 * j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         } else {
-            for (int j = 0; j < 32 && col0 + j < p.N; ++j) crow[j] = f[j];
+#pragma unroll
+            for (int j = 0; j < W; ++j) if (col0 + j < p.N) crow[j] = f[j];
         }
     }
 }
@@ -198,9 +205,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
-    uint64_t* empty_bar = full_bar + C::kStages;
-    uint64_t* tmem_full_bar = empty_bar + C::kStages;
+    const int nstages = p.stages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * C::kStageBytes);
+    uint64_t* empty_bar = full_bar + nstages;
+    uint64_t* tmem_full_bar = empty_bar + nstages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     volatile uint32_t* last_flag = tmem_slot + 1;
 
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
-        for (int s = 0; s < C::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -231,8 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         // ===== TMA producer =====
         if (lane == 0) {
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % C::kStages;
-                const uint32_t ph = (kb / C::kStages) & 1;
+                const int s = kb % nstages;
+                const uint32_t ph = (kb / nstages) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * C::kStageBytes;
                 uint8_t* b_dst = a_dst + kATileBytes;
@@ -259,8 +267,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
             const uint32_t a_adv = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);   // bytes per UMMA_K step
             const uint32_t b_adv = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % C::kStages;
-                const uint32_t ph = (kb / C::kStages) & 1;
+                const int s = kb % nstages;
+                const uint32_t ph = (kb / nstages) & 1;
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
@@ -293,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                store_chunk(p, row, col0, f);
+                store_chunk<32>(p, row, col0, f);
             } else {
                 float4* dst = reinterpret_cast<float4*>(ws_row + c * 32);
 #pragma unroll
@@ -313,22 +321,33 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 __threadfence();
                 if (row_ok) {
 #pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
-                        const int col0 = n0 + c * 32;
+                    for (int h = 0; h < BN / 16; ++h) {
+                        const int col0 = n0 + h * 16;
                         if (col0 >= p.N) break;
-                        float f[32];
+                        float4 t[kMaxSplit][4];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = 0.f;
-                        for (int sp = 0; sp < nsplit; ++sp) {
-                            const float4* src = reinterpret_cast<const float4*>(
-                                p.ws_partials + ((size_t)(tile_id * nsplit + sp) * BM + (q * 32 + lane)) * BN + c * 32);
+                        for (int sp = 0; sp < kMaxSplit; ++sp) {
+                            if (sp < nsplit) {
+                                const float4* src = reinterpret_cast<const float4*>(
+                                    p.ws_partials + ((size_t)(tile_id * nsplit + sp) * BM + (q * 32 + lane)) * BN + h * 16);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 t = __ldcg(src + j);
-                                f[4 * j] += t.x; f[4 * j + 1] += t.y; f[4 * j + 2] += t.z; f[4 * j + 3] += t.w;
+                                for (int j = 0; j < 4; ++j) t[sp][j] = __ldcg(src + j);
                             }
                         }
-                        store_chunk(p, row, col0, f);
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = 0.f;
+#pragma unroll
+                        for (int sp = 0; sp < kMaxSplit; ++sp) {
+                            if (sp < nsplit) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    f[4 * j] += t[sp][j].x; f[4 * j + 1] += t[sp][j].y;
+                                    f[4 * j + 2] += t[sp][j].z; f[4 * j + 3] += t[sp][j].w;
+                                }
+                            }
+                        }
+                        store_chunk<16>(p, row, col0, f);
                     }
                 }
                 if (threadIdx.x == 64) p.ws_tickets[tile_id] = 0;
@@ -388,6 +407,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     if (ctx->ws && tiles < ctx->sm_count && total_kb >= 4 && tiles <= kMaxTickets) {
         int want = ctx->sm_count / tiles;
         if (want > total_kb / 2) want = total_kb / 2;             // at least 2 k-blocks per split
+        if (want > kMaxSplit) want = kMaxSplit;
         if (want > 1) {
             const int kb_per = (total_kb + want - 1) / want;
             nsplit = (total_kb + kb_per - 1) / kb_per;               // no empty split
@@ -403,8 +423,11 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
         if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaFuncSetAttribute(smem=%u): %s", C::kSmemBytes, cudaGetErrorString(e));
         attr_set = true;
     }
+    const int kb_per_cta = ((total_kb + nsplit - 1) / nsplit);
+    p.stages = kb_per_cta < C::kStages ? (kb_per_cta < 2 ? 2 : kb_per_cta) : C::kStages;
+    const size_t smem_bytes = (size_t)p.stages * C::kStageBytes + 1024 + 256;
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit);
-    tc05_gemm_kernel<BN><<<grid, kThreads, C::kSmemBytes, s>>>(ma, mb, p);
+    tc05_gemm_kernel<BN><<<grid, kThreads, smem_bytes, s>>>(ma, mb, p);
     return codae_check_launch(ctx, "tc05_gemm_kernel");
 }
 
