@@ -105,12 +105,12 @@ WORKSPACE_BYTES = 64 << 20
 
 def ensure_workspace(device):
     """Registers (once per device) the zero-initialised scratch the tensor-core engine uses for split-K partial
-    tiles; owned here so it outlives every call that borrows it."""
+    tiles; owned here so it outlives every call that borrows it.  OPT-IN: measured on B200 at B=128 the global-memory
+    fix-up costs more than the extra CTAs gain (0.70 vs 0.53 ms/step, profiles/r01_notes.md), so nothing registers it
+    by default; the parity test keeps the path honest."""
     c = ctx(device)
     dev = torch.device(device)
     key = dev.index if dev.index is not None else torch.cuda.current_device()
-    if os.environ.get("CODAE_NO_SPLITK"):      # A/B switch for benchmarking the single-pass kernels
-        return None
     if key not in _workspaces:
         ws = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
         check(lib().codae_ctx_set_workspace(c, p(ws), ws.numel()), c)

@@ -99,7 +99,6 @@ class FlatMLP(torch.nn.Module):
             lin.bias.data = self.bias_view(flat, l)
         self.flat = flat
         self.flat_bf16 = None
-        _C.ensure_workspace(dev)
 
     def set_compute_dtype(self, name):
         """"fp32": exact-fp32 FFMA engine (reference precision).  "bf16": tcgen05 tensor cores with fp32

@@ -238,9 +238,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % nstages;
-                const uint32_t ph = (kb / nstages) & 1;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == nstages ? 0 : s + 1), ph ^= (s == 0)) {
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * C::kStageBytes;
                 uint8_t* b_dst = a_dst + kATileBytes;
@@ -266,9 +266,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
             const uint32_t idesc = make_idesc(BN, p.a_kmajor != 0, p.b_kmajor != 0);
             const uint32_t a_adv = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);   // bytes per UMMA_K step
             const uint32_t b_adv = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % nstages;
-                const uint32_t ph = (kb / nstages) & 1;
+            int s = 0;
+            uint32_t ph = 0;
+            for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == nstages ? 0 : s + 1), ph ^= (s == 0)) {
                 mbar_wait(&full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);

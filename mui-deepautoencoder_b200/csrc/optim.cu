@@ -100,37 +100,7 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
         coef = fminf(__fdiv_rn(a.max_norm, __fadd_rn(total, 1e-6f)), 1.0f);
     }
     const int64_t n4 = n >> 2;
-    const int64_t n8 = n >> 3;
-    // main loop: 8 elements per thread (two 128-bit loads per array in flight, one 128-bit bf16 shadow store)
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n8; e += (int64_t)gridDim.x * blockDim.x) {
-        float4 pv[2], mv[2], vv[2], gv[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            pv[h] = *reinterpret_cast<const float4*>(p + 8 * e + 4 * h);
-            gv[h] = ldg_stream_f4(g + 8 * e + 4 * h);
-            mv[h] = *reinterpret_cast<const float4*>(m + 8 * e + 4 * h);
-            vv[h] = *reinterpret_cast<const float4*>(v + 8 * e + 4 * h);
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            adam_one(pv[h].x, gv[h].x, mv[h].x, vv[h].x, a, coef);
-            adam_one(pv[h].y, gv[h].y, mv[h].y, vv[h].y, a, coef);
-            adam_one(pv[h].z, gv[h].z, mv[h].z, vv[h].z, a, coef);
-            adam_one(pv[h].w, gv[h].w, mv[h].w, vv[h].w, a, coef);
-            *reinterpret_cast<float4*>(p + 8 * e + 4 * h) = pv[h];
-            *reinterpret_cast<float4*>(m + 8 * e + 4 * h) = mv[h];
-            *reinterpret_cast<float4*>(v + 8 * e + 4 * h) = vv[h];
-        }
-        if (pb) {
-            uint4 q;
-            q.x = pack_bf16x2(pv[0].x, pv[0].y); q.y = pack_bf16x2(pv[0].z, pv[0].w);
-            q.z = pack_bf16x2(pv[1].x, pv[1].y); q.w = pack_bf16x2(pv[1].z, pv[1].w);
-            *reinterpret_cast<uint4*>(pb + 8 * e) = q;
-        }
-    }
-    // at most one leftover group of 4 (n % 8 >= 4), then the scalar tail (n % 4)
-    if (blockIdx.x == 0 && threadIdx.x == 0 && (n4 & 1)) {
-        const int64_t e = n4 - 1;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
         float4 pv = *reinterpret_cast<const float4*>(p + 4 * e);
         const float4 gv = ldg_stream_f4(g + 4 * e);
         float4 mv = *reinterpret_cast<const float4*>(m + 4 * e);
@@ -226,7 +196,7 @@ int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v
     a.grad_scale = (float)grad_scale;
     a.max_norm = (float)max_norm;
     if (n == 0) return CODAE_OK;
-    adam_kernel<<<grid_for(ctx, n >> 3, 1), kThreads, 0, as_stream(stream)>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
+    adam_kernel<<<grid_for(ctx, n >> 2, 2), kThreads, 0, as_stream(stream)>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
                                                                                n, a, sqnorm, step_dev);
     return codae_check_launch(ctx, "adam_kernel");
 }
