@@ -310,7 +310,7 @@ def main():
         del f32, m32
 
     # ---- per-kernel durations inside a real step (CUDA events on the launch stream) -> roofline ----------------------
-    prof = profile_step(fs, batches[0], B, world) if rank == 0 else None
+    prof = profile_step(fs, batches[0], B, world)      # every rank: the steps inside contain the all-reduce
 
     # ---- scoring: candidate scores/s over a sharded synthetic catalog ---------------------------------------------------
     scoring = None

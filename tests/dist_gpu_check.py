@@ -50,8 +50,9 @@ for dtype, graph, tol in [("fp32", False, 1e-5), ("bf16", False, 1e-2), ("bf16",
     rng = np.random.RandomState(5)
     batches = [rng.permutation(1024)[:GB] for _ in range(4)]
     ds, m, cor, fs = build(dtype, world, graph)
-    tables = [torch.empty_like(cor.device_tables()[0]) for _ in range(world)]
-    dist.all_gather(tables, cor.device_tables()[0])
+    tbl32 = cor.device_tables()[0].to(torch.int32)          # NCCL has no int16
+    tables = [torch.empty_like(tbl32) for _ in range(world)]
+    dist.all_gather(tables, tbl32)
     same_table = all(torch.equal(t, tables[0]) for t in tables)
     for gidx in batches:
         local_idx = torch.as_tensor(gidx[rank::world], dtype=torch.int64, device=dev)
