@@ -424,7 +424,7 @@ def profile_step(fs, idx, B, world):
     for k in kernels.values():
         k["share"] = k["ms_per_step"] / step_ms
     Wsum = sum(i * o for i, o in dims)
-    P = model.flat.numel()
+    P = model.nb_parameters()
     io = dims[0][0]
     bf = fs.eng == _C.BF16
     sw = 2 if bf else 4

@@ -1,8 +1,13 @@
 """Flat-buffer MLP shared by the two denoising autoencoders.
 
 The nn.Linear / nn.ReLU modules only carry the structure (same `state_dict` keys and `print(model)` as
-the reference); on a CUDA device every Parameter is re-pointed into ONE flat fp32 buffer (row pitches padded
-to 8 elements so TMA can tile them) and all arithmetic goes through libcodae_b200's C ABI.
+the reference); on a CUDA device every Parameter is re-pointed into ONE flat fp32 buffer and all arithmetic goes
+through libcodae_b200's C ABI.
+
+Layout: layer l is stored as the AUGMENTED matrix W'[out, ld] = [ W | 0.. | b | 0.. ] with the bias in column
+bcol = round_up(in, 8) and ld = bcol + 8 (16-byte pitches for TMA).  Activations carry a matching constant-1 column,
+so  Y = X' . W'^T  adds the bias inside the contraction and  dW' = dY^T . X'  yields the bias gradient in column bcol:
+no bias epilogue, no separate column-sum kernel.  `weight` / `bias` Parameters are strided views of W'.
 """
 import torch
 
@@ -53,27 +58,41 @@ class FlatMLP(torch.nn.Module):
         return [m for m in list(self.input_layer) + list(self.output_layer) if isinstance(m, torch.nn.Linear)]
 
     def layout(self):
-        """[(w_off, ldw, b_off)] per layer and the padded total; every segment starts 16-byte aligned in
-        both the fp32 buffer and its bf16 shadow."""
+        """[(w_off, ld, bcol)] per layer and the padded total; every row starts 16-byte aligned in both the fp32
+        buffer and its bf16 shadow."""
         if self._layout is None:
             off, out = 0, []
             for (i, o) in self.dims:
-                ldw = _round_up(i, 8)
-                w_off = off
-                off += _round_up(o * ldw, 8)
-                b_off = off
-                off += _round_up(o, 8)
-                out.append((w_off, ldw, b_off))
+                bcol = _round_up(i, 8)
+                ld = bcol + 8
+                out.append((off, ld, bcol))
+                off += o * ld
             self._layout = (out, off)
         return self._layout
 
+    def aug_view(self, flat, l):
+        """W'[out, bcol + 1] (pitch ld): the operand the GEMMs contract over (weights, zero pad, bias column)."""
+        (w_off, ld, bcol), (i, o) = self.layout()[0][l], self.dims[l]
+        return flat[w_off:w_off + o * ld].view(o, ld)[:, :bcol + 1]
+
     def weight_view(self, flat, l):
-        (w_off, ldw, _), (i, o) = self.layout()[0][l], self.dims[l]
-        return flat[w_off:w_off + o * ldw].view(o, ldw)[:, :i]
+        (w_off, ld, _), (i, o) = self.layout()[0][l], self.dims[l]
+        return flat[w_off:w_off + o * ld].view(o, ld)[:, :i]
 
     def bias_view(self, flat, l):
-        (_, _, b_off), (_, o) = self.layout()[0][l], self.dims[l]
-        return flat[b_off:b_off + o]
+        (w_off, ld, bcol), (_, o) = self.layout()[0][l], self.dims[l]
+        return flat[w_off:w_off + o * ld].view(o, ld)[:, bcol]
+
+    @staticmethod
+    def act_width(w):
+        """Pitch of an activation buffer of logical width w: data, zero pad to 8, the constant-1 column, pad."""
+        return _round_up(w, 8) + 8
+
+    @staticmethod
+    def new_activation(B, w, dtype, device, width=None):
+        a = torch.zeros((B, width or FlatMLP.act_width(w)), dtype=dtype, device=device)
+        a[:, _round_up(w, 8)] = 1
+        return a
 
     def nb_parameters(self):
         return sum(i * o + o for i, o in self.dims)
@@ -140,14 +159,14 @@ class FlatMLP(torch.nn.Module):
             self.refresh_shadow()
             wflat = self.flat_bf16
         in_w = self.dims[first][0]
-        a0 = torch.zeros((B, _round_up(in_w, 8)), dtype=adt, device=dev)
+        a0 = self.new_activation(B, in_w, adt, dev)
         a0[:, :in_w] = x
         out = [a0]
         for l in range(first, last):
             i, o = self.dims[l]
             is_last = l == last - 1
-            y = torch.zeros((B, _round_up(o, 8)), dtype=torch.float32 if is_last else adt, device=dev)
-            _C.linear_fwd(out[-1], self.weight_view(wflat, l), self.bias_view(self.flat, l), y, B, o, i,
+            y = self.new_activation(B, o, torch.float32 if is_last else adt, dev)
+            _C.linear_fwd(out[-1], self.aug_view(wflat, l), None, y, B, o, _round_up(i, 8) + 1,
                           _C.ACT_RELU if self.relu[l] else _C.ACT_NONE, eng)
             out.append(y)
         return out
@@ -169,7 +188,7 @@ class FlatMLP(torch.nn.Module):
             a_in = acts[l - first]
             if a_in.dtype != adt:
                 a_in = a_in.to(adt)
-            _C.linear_wgrad(g, a_in, self.weight_view(gflat, l), self.bias_view(gflat, l), B, o, i, eng)
+            _C.linear_wgrad(g, a_in, self.aug_view(gflat, l), None, B, o, _round_up(i, 8) + 1, eng)
             if l > first or need_dx:
                 gp = torch.zeros((B, _round_up(i, 8)), dtype=adt, device=dev)
                 prev_relu = l > 0 and self.relu[l - 1] and l > first

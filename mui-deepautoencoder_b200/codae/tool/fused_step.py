@@ -2,11 +2,13 @@
 
 Replaces, per step (script/train_dae_on_embedding.py:198-223; script/train_dae_on_abalone.py:206-236):
   get_masks + corrupt      -> codae_corrupt_fwd      (row gather + slot mask, mask never materialised)
-  model(c_input)           -> L x codae_linear_fwd   (bias + ReLU fused)
+  model(c_input)           -> L x codae_linear_fwd   (bias inside the contraction, ReLU in the epilogue)
   criterion + first bwd    -> codae_mse_loss_fwd_bwd (loss, dL/dy and the full/partial monitor sums, one pass)
                               or codae_mixed_loss_fwd_bwd + codae_mixed_monitor (abalone)
-  loss.backward()          -> L x codae_linear_wgrad (+ bias column sums), (L-1) x codae_linear_dgrad
-  [data parallel]          -> one NCCL all-reduce of the flat gradient buffer
+  loss.backward()          -> L x codae_linear_wgrad (bias gradient = the constant-1 column of the augmented
+                              contraction, no column-sum kernel), (L-1) x codae_linear_dgrad
+  [data parallel]          -> NCCL all-reduce of the flat gradient buffer, issued per layer on a communication stream
+                              as soon as that layer's wgrad has finished (overlaps the rest of the backward pass)
   clip_grad_norm_ + Adam   -> codae_grad_sqnorm + codae_adam_step over the flat buffers
 No host synchronisation happens inside a step; monitors stay on the device until read_monitors().
 The whole sequence can be captured once per batch size into a CUDA graph (use_graph=True).
@@ -24,7 +26,7 @@ def _round_up(x, m):
 class FusedStep:
 
     def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
-                 max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None):
+                 max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True):
         """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
         tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
         {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
@@ -39,6 +41,7 @@ class FusedStep:
         self.world_size, self.pg = world_size, process_group
         self.use_graph = use_graph
         self.mixed = mixed
+        self.overlap_allreduce = overlap_allreduce
         dev = model.flat.device
         self.dev = dev
         self.io = model.dims[0][0]
@@ -69,6 +72,9 @@ class FusedStep:
         for l, lin in enumerate(model.linears()):   # .grad views into the flat gradient buffer
             lin.weight.grad = model.weight_view(self.gflat, l)
             lin.bias.grad = model.bias_view(self.gflat, l)
+        lay, total = model.layout()
+        self._layer_span = [(lay[l][0], lay[l + 1][0] if l + 1 < len(lay) else total) for l in range(len(lay))]
+        self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
         self._bufs = {}
         self._graphs = {}
         self._calls = {}
@@ -78,13 +84,14 @@ class FusedStep:
         b = self._bufs.get(B)
         if b is None:
             dev, adt, dims = self.dev, self.adt, self.model.dims
-            wmax = max(_round_up(max(i, o), 8) for i, o in dims)
+            M = self.model
+            wmax = max(M.act_width(max(i, o)) for i, o in dims)
             # tabular (mixed) mode keeps one pitch for every buffer: the mixed-loss kernel takes a single ld
-            width = (lambda w: wmax) if self.mixed is not None else (lambda w: _round_up(w, 8))
-            acts = [torch.zeros((B, width(dims[0][0])), dtype=adt, device=dev)]
+            width = (lambda w: wmax) if self.mixed is not None else (lambda w: None)
+            acts = [M.new_activation(B, dims[0][0], adt, dev, width(dims[0][0]))]
             for l, (i, o) in enumerate(dims):
                 last = l == len(dims) - 1
-                acts.append(torch.zeros((B, width(o)), dtype=torch.float32 if last else adt, device=dev))
+                acts.append(M.new_activation(B, o, torch.float32 if last else adt, dev, width(o)))
             b = dict(acts=acts,
                      g0=torch.zeros((B, wmax), dtype=adt, device=dev), g1=torch.zeros((B, wmax), dtype=adt, device=dev),
                      mask_id=torch.zeros(B, dtype=torch.int32, device=dev),
@@ -104,7 +111,7 @@ class FusedStep:
         _C.corrupt_fwd(data, idx, B, table, run, bits, col_var, self.io, acts[0], b["x"], b["mask_id"]); n += 1
         wflat = model.flat_bf16 if eng == _C.BF16 else model.flat
         for l, (i, o) in enumerate(dims):
-            _C.linear_fwd(acts[l], model.weight_view(wflat, l), model.bias_view(model.flat, l), acts[l + 1], B, o, i,
+            _C.linear_fwd(acts[l], model.aug_view(wflat, l), None, acts[l + 1], B, o, _round_up(i, 8) + 1,
                           _C.ACT_RELU if model.relu[l] else _C.ACT_NONE, eng); n += 1
         y = acts[L]
         o_last = dims[L - 1][1]
@@ -121,15 +128,31 @@ class FusedStep:
         if not train:
             return n
         cur, nxt = "g0", "g1"
+        overlap = self.world_size > 1 and self.overlap_allreduce
+        if overlap:
+            import torch.distributed as dist
+            main = torch.cuda.current_stream()
+            side = self._comm_stream
         for l in range(L - 1, -1, -1):
             i, o = dims[l]
             gl = b[cur][:, :_round_up(o, 8)]
-            _C.linear_wgrad(gl, acts[l], model.weight_view(self.gflat, l), model.bias_view(self.gflat, l), B, o, i, eng); n += 2
+            _C.linear_wgrad(gl, acts[l], model.aug_view(self.gflat, l), None, B, o, _round_up(i, 8) + 1, eng); n += 1
+            if overlap:
+                # layer l's gradients (W and b are contiguous in the flat buffer) are final: reduce them on the
+                # communication stream while the remaining layers' backward GEMMs run on the compute stream.
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                lo, hi = self._layer_span[l]
+                with torch.cuda.stream(side):
+                    dist.all_reduce(self.gflat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
             if l > 0:
                 gp = b[nxt][:, :_round_up(i, 8)]
                 _C.linear_dgrad(gl, model.weight_view(wflat, l), acts[l] if model.relu[l - 1] else None, gp, B, o, i, eng); n += 1
                 cur, nxt = nxt, cur
-        if self.world_size > 1:
+        if overlap:
+            main.wait_stream(side)
+        elif self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
         if self.clip:

@@ -13,7 +13,7 @@ extern "C" {
 
 int codae_linear_engine(const codae_ctx* ctx, int dtype, int M, int N, int K) {
     if (!ctx) return CODAE_EINVAL;
-    if (dtype == CODAE_BF16 && ctx->encode_tiled && tc_shape_ok(M, N, K) && N % 8 == 0 && K % 8 == 0)
+    if (dtype == CODAE_BF16 && ctx->encode_tiled && tc_shape_ok(M, N, K))   // pitches/alignment are checked per call
         return CODAE_ENGINE_TCGEN05_BF16;
     return CODAE_ENGINE_SIMT_F32;
 }

@@ -26,7 +26,7 @@ from codae.tool import Corrupter, FusedStep
 from codae.tool.inference import ComplementarityScorer, shard_rows
 
 
-def build(dtype, ws, graph):
+def build(dtype, ws, graph, overlap=True):
     torch.manual_seed(3)
     S, E, N = 3, 128, 1024
     cats = [torch.randn(N, E).abs() for _ in range(S)]
@@ -36,7 +36,7 @@ def build(dtype, ws, graph):
     m.to(dev)
     ds.to(dev)
     cor = Corrupter(N, ds.arch, 1, dev, seed=77)
-    fs = FusedStep(m, cor, ds.data, lr=1e-3, weight_decay=1e-4, clip=True, world_size=ws, use_graph=graph)
+    fs = FusedStep(m, cor, ds.data, lr=1e-3, weight_decay=1e-4, clip=True, world_size=ws, use_graph=graph, overlap_allreduce=overlap)
     return ds, m, cor, fs
 
 
@@ -46,32 +46,34 @@ def flat(m):
 
 ok = True
 for dtype, graph, tol in [("fp32", False, 1e-5), ("bf16", False, 1e-2), ("bf16", True, 1e-2)]:
-    GB = 64 * world
-    rng = np.random.RandomState(5)
-    batches = [rng.permutation(1024)[:GB] for _ in range(4)]
-    ds, m, cor, fs = build(dtype, world, graph)
-    tbl32 = cor.device_tables()[0].to(torch.int32)          # NCCL has no int16
-    tables = [torch.empty_like(tbl32) for _ in range(world)]
-    dist.all_gather(tables, tbl32)
-    same_table = all(torch.equal(t, tables[0]) for t in tables)
-    for gidx in batches:
-        local_idx = torch.as_tensor(gidx[rank::world], dtype=torch.int64, device=dev)
-        fs.step(local_idx, global_batch=GB)
-    w_dp = flat(m)
-    gathered = [torch.empty_like(w_dp) for _ in range(world)]
-    dist.all_gather(gathered, w_dp)
-    replicas_equal = all(torch.equal(g, gathered[0]) for g in gathered)       # every rank applied the same update
-    # single-process reference on the whole global batch (same device, world_size=1)
-    ds1, m1, cor1, fs1 = build(dtype, 1, False)
-    for gidx in batches:
-        fs1.step(torch.as_tensor(gidx, dtype=torch.int64, device=dev), global_batch=GB)
-    w_1 = flat(m1)
-    err = float((w_dp - w_1).abs().max() / w_1.abs().max())
-    good = same_table and replicas_equal and err < tol
-    ok &= good
-    if rank == 0:
-        print("DP %s graph=%s: tables_equal=%s replicas_bitwise_equal=%s |w_dp - w_1|/|w| = %.2e (tol %.0e) -> %s"
-              % (dtype, graph, same_table, replicas_equal, err, tol, "OK" if good else "FAIL"), flush=True)
+  for overlap in (True, False):
+      GB = 64 * world
+      rng = np.random.RandomState(5)
+      batches = [rng.permutation(1024)[:GB] for _ in range(4)]
+      ds, m, cor, fs = build(dtype, world, graph, overlap)
+      tbl32 = cor.device_tables()[0].to(torch.int32)          # NCCL has no int16
+      tables = [torch.empty_like(tbl32) for _ in range(world)]
+      dist.all_gather(tables, tbl32)
+      same_table = all(torch.equal(t, tables[0]) for t in tables)
+      for gidx in batches:
+          local_idx = torch.as_tensor(gidx[rank::world], dtype=torch.int64, device=dev)
+          fs.step(local_idx, global_batch=GB)
+      w_dp = flat(m)
+      gathered = [torch.empty_like(w_dp) for _ in range(world)]
+      dist.all_gather(gathered, w_dp)
+      replicas_equal = all(torch.equal(g, gathered[0]) for g in gathered)       # every rank applied the same update
+      # single-process reference on the whole global batch (same device, world_size=1)
+      ds1, m1, cor1, fs1 = build(dtype, 1, False)
+      for gidx in batches:
+          fs1.step(torch.as_tensor(gidx, dtype=torch.int64, device=dev), global_batch=GB)
+      w_1 = flat(m1)
+      err = float((w_dp - w_1).abs().max() / w_1.abs().max())
+      good = same_table and replicas_equal and err < tol
+      ok &= good
+      if rank == 0:
+          print("DP %s graph=%s overlap=%s: tables_equal=%s replicas_bitwise_equal=%s |w_dp - w_1|/|w| = %.2e (tol %.0e) -> %s"
+                % (dtype, graph, overlap, same_table, replicas_equal, err, tol, "OK" if good else "FAIL"), flush=True)
+      del fs, fs1
 
 # sharded catalog
 torch.manual_seed(9)
@@ -90,5 +92,7 @@ t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("DIST CHECK", "PASSED" if int(t.item()) == 1 else "FAILED", flush=True)
-dist.destroy_process_group()
-sys.exit(0 if int(t.item()) == 1 else 1)
+code = 0 if int(t.item()) == 1 else 1
+torch.cuda.synchronize()
+sys.stdout.flush()
+os._exit(code)      # skip NCCL/graph teardown order issues at interpreter exit

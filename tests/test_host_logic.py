@@ -54,9 +54,14 @@ def test_flat_layout_is_16_byte_aligned_and_padded():
     m = EmbeddingDenoisingAutoencoder(48, 8, 16, 3, 3, False)
     lay, total = m.layout()
     assert total % 8 == 0
-    for (w_off, ldw, b_off), (i, o) in zip(lay, m.dims):
-        assert w_off % 8 == 0 and b_off % 8 == 0 and ldw % 8 == 0 and ldw >= i
+    for (w_off, ld, bcol), (i, o) in zip(lay, m.dims):
+        assert w_off % 8 == 0 and ld % 8 == 0 and i <= bcol < ld        # bias column after the (padded) weights
     assert m.nb_parameters() == sum(p.numel() for p in m.parameters())
+    flat = torch.arange(total, dtype=torch.float32)
+    for l, (i, o) in enumerate(m.dims):
+        assert m.weight_view(flat, l).shape == (o, i) and m.bias_view(flat, l).shape == (o,)
+        assert m.aug_view(flat, l).shape == (o, lay[l][2] + 1)
+        assert m.bias_view(flat, l)[0] == m.aug_view(flat, l)[0, -1]
 
 
 def test_corrupter_attributes_match_reference():
