@@ -15,7 +15,7 @@ run_pytest inference tests/test_gpu_inference.py 15
 echo "== smoke"; timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/smoke.log
 echo "== bench default"; timeout -s KILL 600 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "rc=$?"; tail -3 gpurun_out/bench_default.err; cat gpurun_out/bench_default.json
 echo "== bench modanet"; timeout -s KILL 300 python bench.py --workload modanet --no-cpu --no-scoring --no-fp32 > gpurun_out/bench_modanet.json 2> gpurun_out/bench_modanet.err; echo "rc=$?"; tail -3 gpurun_out/bench_modanet.err; cat gpurun_out/bench_modanet.json
-echo "== bench polyvore"; timeout -s KILL 600 python bench.py --workload polyvore --steps 10 --warmup 3 --no-cpu --no-scoring > gpurun_out/bench_polyvore.json 2> gpurun_out/bench_polyvore.err; echo "rc=$?"; tail -3 gpurun_out/bench_polyvore.err; cat gpurun_out/bench_polyvore.json
+echo "== bench polyvore"; timeout -s KILL 300 python bench.py --workload polyvore --steps 10 --warmup 3 --no-cpu --no-scoring > gpurun_out/bench_polyvore.json 2> gpurun_out/bench_polyvore.err; echo "rc=$?"; tail -3 gpurun_out/bench_polyvore.err; cat gpurun_out/bench_polyvore.json
 echo "== reference arm"; timeout -s KILL 300 python bench.py --impl reference --steps 20 --warmup 3 > gpurun_out/bench_ref.json 2>&1; cat gpurun_out/bench_ref.json
 echo "== ncu launch list (default command, short)"
 CMD="python bench.py --steps 3 --warmup 3 --no-scoring --no-cpu --no-fp32 --no-graph"
@@ -24,7 +24,13 @@ timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c
 echo "ncu rc=$?"
 echo "== ncu full capture of the hot kernels"
 CMD2="python bench.py --steps 2 --warmup 3 --no-cpu --no-fp32 --no-graph --catalog 2000000"
-timeout -s KILL 300 $CMD2 > gpurun_out/plain2.log 2>&1 && \
-timeout -s KILL 900 ncu --set full --clock-control none --import-source on -k regex:"adam_kernel|tc05_gemm_kernel|score_topk_kernel|sqnorm_kernel|mse_loss_kernel|corrupt_fwd" -s 40 -c 14 -o gpurun_out/prof_r1 $CMD2 > gpurun_out/ncu_full.log 2>&1
-echo "ncu full rc=$?"; tail -2 gpurun_out/ncu_full.log
+timeout -s KILL 300 $CMD2 > gpurun_out/plain2.log 2>&1 && {
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"adam_kernel|sqnorm_kernel|corrupt_fwd|mse_loss" -s 12 -c 8 -o gpurun_out/prof_r1_elementwise $CMD2 > gpurun_out/ncu_full1.log 2>&1; echo "ncu elementwise rc=$?"
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"score_topk_kernel" -s 2 -c 2 -o gpurun_out/prof_r1_score $CMD2 > gpurun_out/ncu_full2.log 2>&1; echo "ncu score rc=$?"
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"tc05_gemm_kernel" -s 87 -c 6 -o gpurun_out/prof_r1_gemm_small $CMD2 > gpurun_out/ncu_full3.log 2>&1; echo "ncu gemm small rc=$?"
+}
+CMD3="python bench.py --workload polyvore --steps 1 --warmup 3 --no-cpu --no-scoring --no-graph"
+timeout -s KILL 300 $CMD3 > gpurun_out/plain3.log 2>&1 && \
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"tc05_gemm_kernel" -s 29 -c 6 -o gpurun_out/prof_r1_gemm_large $CMD3 > gpurun_out/ncu_full4.log 2>&1
+echo "ncu gemm large rc=$?"
 echo "== done"
