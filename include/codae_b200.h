@@ -47,11 +47,10 @@ int codae_ctx_create(int device, codae_ctx** out);
 int codae_ctx_destroy(codae_ctx* ctx);
 const char* codae_last_error(const codae_ctx* ctx); /* ctx may be NULL: last process-wide error */
 int codae_ctx_sm_count(const codae_ctx* ctx);
-/* Registers caller-owned scratch (zero-initialised, 256-byte aligned, >= 1 MiB; 64 MiB recommended) that the
- * tensor-core engine uses for split-K partial tiles when a contraction has fewer output tiles than SMs (the
- * small-batch layers of embedding.yaml / modanet).  Borrowed until replaced or the ctx is destroyed; calls that
- * use it must be stream-ordered.  NULL un-registers (split-K off). */
-int codae_ctx_set_workspace(codae_ctx* ctx, void* workspace, size_t bytes);
+/* Cluster split-K of the tensor-core engine (on by default): contractions with too few output tiles to occupy the
+ * GPU (the small-batch layers of embedding.yaml / modanet) spread their k-blocks over a thread-block cluster and reduce
+ * the partial tiles through distributed shared memory, in rank order (bitwise reproducible).  0 disables it. */
+int codae_ctx_set_splitk(codae_ctx* ctx, int enabled);
 /* Which engine codae_linear_* will use for (dtype, M, N, K). */
 int codae_linear_engine(const codae_ctx* ctx, int dtype, int M, int N, int K);
 

@@ -30,7 +30,7 @@ SIGNATURES = {
     "codae_ctx_destroy": (_i, [_vp]),
     "codae_last_error": (_c.c_char_p, [_vp]),
     "codae_ctx_sm_count": (_i, [_vp]),
-    "codae_ctx_set_workspace": (_i, [_vp, _vp, _sz]),
+    "codae_ctx_set_splitk": (_i, [_vp, _i]),
     "codae_linear_engine": (_i, [_vp, _i, _i, _i, _i]),
     "codae_mask_table_philox": (_i, [_vp, _u64, _i64, _i64, _i, _vp, _vp]),
     "codae_corrupt_fwd": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i64, _vp, _i64, _vp, _vp]),
@@ -99,32 +99,11 @@ def ctx(device=None):
     return c
 
 
-_workspaces = {}
-WORKSPACE_BYTES = 64 << 20
-
-
-def ensure_workspace(device):
-    """Registers (once per device) the zero-initialised scratch the tensor-core engine uses for split-K partial
-    tiles; owned here so it outlives every call that borrows it.  OPT-IN: measured on B200 at B=128 the global-memory
-    fix-up costs more than the extra CTAs gain (0.70 vs 0.53 ms/step, profiles/r01_notes.md), so nothing registers it
-    by default; the parity test keeps the path honest."""
+def set_splitk(device, enabled):
+    """Cluster split-K of the tensor-core engine (on by default); tests switch it off to compare with the
+    single-pass kernel."""
     c = ctx(device)
-    dev = torch.device(device)
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
-    if key not in _workspaces:
-        ws = torch.zeros(WORKSPACE_BYTES, dtype=torch.uint8, device=dev)
-        check(lib().codae_ctx_set_workspace(c, p(ws), ws.numel()), c)
-        _workspaces[key] = ws
-    return _workspaces[key]
-
-
-def disable_workspace(device):
-    """Un-registers the scratch buffer (split-K off); used by tests to compare against the single-pass kernel."""
-    c = ctx(device)
-    dev = torch.device(device)
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
-    check(lib().codae_ctx_set_workspace(c, None, 0), c)
-    _workspaces.pop(key, None)
+    check(lib().codae_ctx_set_splitk(c, 1 if enabled else 0), c)
 
 
 def check(rc, c):

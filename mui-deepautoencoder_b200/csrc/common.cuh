@@ -17,8 +17,7 @@ struct codae_ctx {
     int cc_major, cc_minor;
     char err[512];
     void* encode_tiled;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
-    void* ws;            // caller-registered scratch (split-K partials + tickets); zero-initialised by the caller
-    size_t ws_bytes;
+    int splitk;          // 1: small-batch contractions may use cluster split-K (default on)
     std::mutex mu;
 };
 

@@ -57,8 +57,7 @@ int codae_ctx_create(int device, codae_ctx** out) {
     c->cc_minor = prop.minor;
     c->err[0] = 0;
     c->encode_tiled = nullptr;
-    c->ws = nullptr;
-    c->ws_bytes = 0;
+    c->splitk = 1;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -77,13 +76,9 @@ const char* codae_last_error(const codae_ctx* ctx) { return ctx ? ctx->err : g_c
 
 int codae_ctx_sm_count(const codae_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
-int codae_ctx_set_workspace(codae_ctx* ctx, void* workspace, size_t bytes) {
-    if (!ctx) return codae_fail(nullptr, CODAE_EINVAL, "codae_ctx_set_workspace: ctx is NULL");
-    if (workspace && ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0 || bytes < (1u << 20)))
-        return codae_fail(ctx, CODAE_EINVAL, "codae_ctx_set_workspace: need a 256-byte aligned buffer of at least 1 MiB");
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    ctx->ws = workspace;
-    ctx->ws_bytes = workspace ? bytes : 0;
+int codae_ctx_set_splitk(codae_ctx* ctx, int enabled) {
+    if (!ctx) return codae_fail(nullptr, CODAE_EINVAL, "codae_ctx_set_splitk: ctx is NULL");
+    ctx->splitk = enabled ? 1 : 0;
     return CODAE_OK;
 }
 

@@ -12,6 +12,15 @@
 // allocator + MMA issuer (one elected lane), warps 2..5 = epilogue (tcgen05.ld 32 lanes x 32 columns each).
 // Pipeline: kStages smem slots guarded by full/empty mbarriers; tcgen05.commit releases a slot when the
 // MMAs that read it have drained, and signals the epilogue after the last k-block.
+//
+// Two epilogues:
+//   direct : TMEM -> registers -> fused epilogue -> HBM (bf16 activations of the large-batch layers)
+//   staged : TMEM -> registers -> fp32 tile in shared memory (over the drained pipeline slots) -> coalesced
+//            epilogue + store.  Used for fp32 outputs (weight gradients) and for split-K.
+// Split-K (small batches: too few output tiles to keep 148 SMs streaming the weights): the k-blocks of one tile are
+// spread over a thread-block CLUSTER along grid z; every CTA stages its partial tile in its own shared memory and,
+// after a cluster barrier, CTA r reduces rows [128 r / S, 128 (r+1) / S) of all S partials through distributed
+// shared memory (ld.shared::cluster) in rank order -- deterministic, no HBM round trip, no atomics.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -24,9 +33,7 @@ constexpr int BK = 64;           // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
 constexpr uint32_t kATileBytes = BM * BK * 2;  // 16 KB
-constexpr int kMaxTickets = 4096;
-constexpr int kMaxSplit = 8;
-constexpr size_t kTicketBytes = kMaxTickets * sizeof(unsigned int);
+constexpr int kMaxSplit = 8;     // portable cluster size limit
 
 struct Params {
     int M, N, K;
@@ -39,8 +46,7 @@ struct Params {
     const __nv_bfloat16* mask_src;
     long long ldm;
     int stages;                  // pipeline depth actually used (<= Cfg::kStages)
-    float* ws_partials;          // split-K: [tile][split][128][BN] fp32 partial accumulators
-    unsigned int* ws_tickets;    // split-K: one arrival counter per output tile (self-resetting)
+    int staged;                  // 1: epilogue through the shared-memory tile (required when gridDim.z > 1)
 };
 
 template <int BN>
@@ -119,6 +125,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// All threads of all CTAs of the cluster.  Non-.aligned forms: lanes of the producer / MMA warps arrive from
+// different program points.
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+// 128-bit load from the shared memory of CTA `rank` of this cluster (distributed shared memory).
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+    return v;
 }
 
 // Shared-memory matrix descriptor (sm_100 format: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
@@ -210,7 +231,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     uint64_t* empty_bar = full_bar + nstages;
     uint64_t* tmem_full_bar = empty_bar + nstages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-    volatile uint32_t* last_flag = tmem_slot + 1;
+    constexpr int kStagePitch = BN + 4;               // floats per row of the staged fp32 tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -283,76 +304,109 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
             umma_commit(tmem_full_bar);              // accumulator complete
         }
     } else {
-        // ===== epilogue: TMEM -> registers -> HBM (or split-K partials) =====
+        // ===== epilogue, part 1: TMEM -> registers -> HBM (direct) or -> shared-memory tile (staged) =====
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < p.M;
-        float* ws_row = nsplit > 1 ? p.ws_partials + ((size_t)(tile_id * nsplit + blockIdx.z) * BM + (q * 32 + lane)) * BN
-                                   : nullptr;
+        float* stage_row = reinterpret_cast<float*>(smem) + (size_t)(q * 32 + lane) * kStagePitch;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
             const int col0 = n0 + c * 32;
-            if (nsplit == 1) {
+            if (!p.staged) {
                 if (!row_ok || col0 >= p.N) continue;
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 store_chunk<32>(p, row, col0, f);
             } else {
-                float4* dst = reinterpret_cast<float4*>(ws_row + c * 32);
+                // row pitch BN+4 floats: the 8 lanes of a 128-bit store phase hit 8 distinct 16-byte bank groups
+                float4* dst = reinterpret_cast<float4*>(stage_row + c * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    __stcg(dst + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
             }
         }
-        if (nsplit > 1) {
-            // split-K fix-up: the last CTA to arrive for this output tile sums all partials in split order
-            // (fixed order => bitwise reproducible) and applies the epilogue.
-            __threadfence();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (threadIdx.x == 64) *last_flag = (atomicAdd(&p.ws_tickets[tile_id], 1u) == (unsigned)nsplit - 1u) ? 1u : 0u;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (*last_flag) {
-                __threadfence();
-                if (row_ok) {
-#pragma unroll 1
-                    for (int h = 0; h < BN / 16; ++h) {
-                        const int col0 = n0 + h * 16;
-                        if (col0 >= p.N) break;
-                        float4 t[kMaxSplit][4];
-#pragma unroll
-                        for (int sp = 0; sp < kMaxSplit; ++sp) {
-                            if (sp < nsplit) {
-                                const float4* src = reinterpret_cast<const float4*>(
-                                    p.ws_partials + ((size_t)(tile_id * nsplit + sp) * BM + (q * 32 + lane)) * BN + h * 16);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) t[sp][j] = __ldcg(src + j);
-                            }
-                        }
-                        float f[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = 0.f;
-#pragma unroll
-                        for (int sp = 0; sp < kMaxSplit; ++sp) {
-                            if (sp < nsplit) {
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    f[4 * j] += t[sp][j].x; f[4 * j + 1] += t[sp][j].y;
-                                    f[4 * j + 2] += t[sp][j].z; f[4 * j + 3] += t[sp][j].w;
-                                }
-                            }
-                        }
-                        store_chunk<16>(p, row, col0, f);
+    }
+
+    if (p.staged) {
+        // ===== epilogue, part 2 (staged): [cluster reduce +] fused epilogue + coalesced stores =====
+        __syncwarp();
+        if (nsplit > 1) cluster_sync();                      // every thread of every CTA of the cluster
+        else if (warp >= 2) asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp >= 2) {
+            const int t = threadIdx.x - 64;                  // 0..127
+            const int rank = blockIdx.z;                     // == %cluster_ctarank (cluster spans grid z only)
+            const int r_begin = (rank * BM) / nsplit, r_end = ((rank + 1) * BM) / nsplit;
+            constexpr int kVecPerRow = BN / 4;
+            const int items = (r_end - r_begin) * kVecPerRow;
+            const uint32_t stage_base = smem_u32(smem);
+            for (int it = t; it < items; it += 128) {
+                const int rl = r_begin + it / kVecPerRow;    // row within the tile
+                const int c4 = it % kVecPerRow;
+                const uint32_t off = (uint32_t)(rl * kStagePitch + 4 * c4) * 4u;
+                float4 acc;
+                if (nsplit == 1) {
+                    acc = *reinterpret_cast<const float4*>(smem + off);
+                } else {
+                    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int sp = 0; sp < nsplit; ++sp) {    // rank order: bitwise reproducible
+                        const float4 v = ld_dsmem_f4(stage_base + off, (uint32_t)sp);
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                     }
                 }
-                if (threadIdx.x == 64) p.ws_tickets[tile_id] = 0;
+                const int row = m0 + rl, col = n0 + 4 * c4;
+                if (row >= p.M || col >= p.N) continue;
+                float f[4] = {acc.x, acc.y, acc.z, acc.w};
+                const bool full = col + 4 <= p.N;
+                if (p.bias) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (full || col + j < p.N) f[j] += __ldg(p.bias + col + j);
+                }
+                if (p.act == CODAE_ACT_RELU) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) f[j] = fmaxf(f[j], 0.f);
+                }
+                if (p.mask_src) {
+                    const __nv_bfloat16* mrow = p.mask_src + (long long)row * p.ldm + col;
+                    if (full) {
+                        const uint2 mv = *reinterpret_cast<const uint2*>(mrow);
+                        if (!(bf16_lo(mv.x) > 0.f)) f[0] = 0.f;
+                        if (!(bf16_hi(mv.x) > 0.f)) f[1] = 0.f;
+                        if (!(bf16_lo(mv.y) > 0.f)) f[2] = 0.f;
+                        if (!(bf16_hi(mv.y) > 0.f)) f[3] = 0.f;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (col + j < p.N && !(__bfloat162float(mrow[j]) > 0.f)) f[j] = 0.f;
+                    }
+                }
+                if (p.c_bf16) {
+                    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col;
+                    if (full) {
+                        uint2 o;
+                        o.x = pack_bf16x2(f[0], f[1]);
+                        o.y = pack_bf16x2(f[2], f[3]);
+                        *reinterpret_cast<uint2*>(crow) = o;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (col + j < p.N) crow[j] = __float2bfloat16_rn(f[j]);
+                    }
+                } else {
+                    float* crow = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + col;
+                    if (full) {
+                        *reinterpret_cast<float4*>(crow) = make_float4(f[0], f[1], f[2], f[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (col + j < p.N) crow[j] = f[j];
+                    }
+                }
             }
         }
+        if (nsplit > 1) cluster_sync();                      // peers may still be reading this CTA's tile
     }
     tc_fence_before();
     __syncthreads();
@@ -399,24 +453,21 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_dtype == CODAE_BF16;
     p.bias = g.bias; p.act = g.act;
     p.mask_src = reinterpret_cast<const __nv_bfloat16*>(g.mask_src); p.ldm = g.ldm;
-    // split-K: small-batch contractions have too few output tiles to keep 148 SMs streaming the weights, so the
-    // k-blocks of one tile are spread over gridDim.z CTAs (fix-up by the last arriver, deterministic order).
+    // split-K over a thread-block cluster (see the header comment): only when the tiles alone would leave most SMs
+    // idle and every split still gets at least 2 k-blocks.
     const int tiles = ((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM);
     const int total_kb = (g.K + BK - 1) / BK;
     int nsplit = 1;
-    if (ctx->ws && tiles < ctx->sm_count && total_kb >= 4 && tiles <= kMaxTickets) {
+    if (ctx->splitk && 2 * tiles <= ctx->sm_count && total_kb >= 8) {
         int want = ctx->sm_count / tiles;
-        if (want > total_kb / 2) want = total_kb / 2;             // at least 2 k-blocks per split
+        if (want > total_kb / 2) want = total_kb / 2;
         if (want > kMaxSplit) want = kMaxSplit;
         if (want > 1) {
             const int kb_per = (total_kb + want - 1) / want;
             nsplit = (total_kb + kb_per - 1) / kb_per;               // no empty split
-            const size_t need = kTicketBytes + (size_t)tiles * nsplit * BM * BN * sizeof(float);
-            if (need > ctx->ws_bytes) nsplit = 1;
         }
     }
-    p.ws_tickets = reinterpret_cast<unsigned int*>(ctx->ws);
-    p.ws_partials = reinterpret_cast<float*>(reinterpret_cast<char*>(ctx->ws) + kTicketBytes);
+    p.staged = (nsplit > 1 || g.c_dtype == CODAE_F32) ? 1 : 0;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc05_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
@@ -425,9 +476,33 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     const int kb_per_cta = ((total_kb + nsplit - 1) / nsplit);
     p.stages = kb_per_cta < C::kStages ? (kb_per_cta < 2 ? 2 : kb_per_cta) : C::kStages;
-    const size_t smem_bytes = (size_t)p.stages * C::kStageBytes + 1024 + 256;
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit);
-    tc05_gemm_kernel<BN><<<grid, kThreads, smem_bytes, s>>>(ma, mb, p);
+    size_t pipe_bytes = (size_t)p.stages * C::kStageBytes;
+    const size_t stage_tile = (size_t)BM * (BN + 4) * sizeof(float);          // staged epilogue overlays the pipeline
+    if (p.staged && pipe_bytes < stage_tile) {
+        p.stages = (int)((stage_tile + C::kStageBytes - 1) / C::kStageBytes);  // barriers sit after the last slot
+        pipe_bytes = (size_t)p.stages * C::kStageBytes;
+    }
+    const size_t smem_bytes = pipe_bytes + 1024 + 256;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    if (nsplit > 1) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = nsplit;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    cudaError_t le = cudaLaunchKernelEx(&cfg, tc05_gemm_kernel<BN>, ma, mb, p);
+    if (le != cudaSuccess) {
+        cudaGetLastError();
+        return codae_fail(ctx, CODAE_ECUDA, "tc05_gemm_kernel<%d> launch (grid %u x %u x %d, smem %zu): %s", BN, cfg.gridDim.x,
+                          cfg.gridDim.y, nsplit, smem_bytes, cudaGetErrorString(le));
+    }
     return codae_check_launch(ctx, "tc05_gemm_kernel");
 }
 

