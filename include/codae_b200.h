@@ -47,10 +47,14 @@ int codae_ctx_create(int device, codae_ctx** out);
 int codae_ctx_destroy(codae_ctx* ctx);
 const char* codae_last_error(const codae_ctx* ctx); /* ctx may be NULL: last process-wide error */
 int codae_ctx_sm_count(const codae_ctx* ctx);
-/* Cluster split-K of the tensor-core engine (on by default): contractions with too few output tiles to occupy the
- * GPU (the small-batch layers of embedding.yaml / modanet) spread their k-blocks over a thread-block cluster and reduce
- * the partial tiles through distributed shared memory, in rank order (bitwise reproducible).  0 disables it. */
-int codae_ctx_set_splitk(codae_ctx* ctx, int enabled);
+/* Tuning switches, both on by default (tests turn them off to compare code paths):
+ *   CODAE_OPT_SPLITK  contractions with too few output tiles to occupy the GPU (the small-batch layers of
+ *                     embedding.yaml / modanet) spread their k-blocks over a thread-block cluster and reduce the partial
+ *                     tiles through distributed shared memory, in rank order (bitwise reproducible);
+ *   CODAE_OPT_PDL     training-step kernels are launched as programmatic dependents: their prologue overlaps the tail
+ *                     of the previous kernel and they wait (griddepcontrol.wait) before touching global memory. */
+enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1 };
+int codae_ctx_set_option(codae_ctx* ctx, int option, int value);
 /* Which engine codae_linear_* will use for (dtype, M, N, K). */
 int codae_linear_engine(const codae_ctx* ctx, int dtype, int M, int N, int K);
 

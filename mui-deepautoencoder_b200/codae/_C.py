@@ -30,7 +30,7 @@ SIGNATURES = {
     "codae_ctx_destroy": (_i, [_vp]),
     "codae_last_error": (_c.c_char_p, [_vp]),
     "codae_ctx_sm_count": (_i, [_vp]),
-    "codae_ctx_set_splitk": (_i, [_vp, _i]),
+    "codae_ctx_set_option": (_i, [_vp, _i, _i]),
     "codae_linear_engine": (_i, [_vp, _i, _i, _i, _i]),
     "codae_mask_table_philox": (_i, [_vp, _u64, _i64, _i64, _i, _vp, _vp]),
     "codae_corrupt_fwd": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i64, _vp, _i64, _vp, _vp]),
@@ -99,11 +99,17 @@ def ctx(device=None):
     return c
 
 
-def set_splitk(device, enabled):
-    """Cluster split-K of the tensor-core engine (on by default); tests switch it off to compare with the
-    single-pass kernel."""
+OPT_SPLITK, OPT_PDL = 0, 1
+
+
+def set_option(device, option, value):
+    """Tuning switches of the library (cluster split-K, programmatic dependent launch); both default on."""
     c = ctx(device)
-    check(lib().codae_ctx_set_splitk(c, 1 if enabled else 0), c)
+    check(lib().codae_ctx_set_option(c, option, 1 if value else 0), c)
+
+
+def set_splitk(device, enabled):
+    set_option(device, OPT_SPLITK, enabled)
 
 
 def check(rc, c):

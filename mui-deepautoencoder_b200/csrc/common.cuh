@@ -18,6 +18,7 @@ struct codae_ctx {
     char err[512];
     void* encode_tiled;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
     int splitk;          // 1: small-batch contractions may use cluster split-K (default on)
+    int pdl;             // 1: training-step kernels are launched with programmatic dependent launch (default on)
     std::mutex mu;
 };
 
@@ -33,7 +34,28 @@ int codae_check_launch(codae_ctx* ctx, const char* what);
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch: the kernel may start (prologue, barrier init, TMEM allocation) while its stream
+// predecessor is still running; it must execute pdl_wait() before touching any global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(const codae_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (ctx && ctx->pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // ---- device helpers ---------------------------------------------------------------------------
+// No-ops when the grid was not launched as a programmatic dependent.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
     float4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"

@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(256) corrupt_fwd_vec_kernel(const float* __res
                                                               void* __restrict__ out_cx, int64_t ld_cx,
                                                               float* __restrict__ out_x, int64_t ld_x,
                                                               int32_t* __restrict__ out_mask_id) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int64_t total = (int64_t)B * io4;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int row = (int)(e / io4);
@@ -174,8 +176,8 @@ int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t ld_data, const 
     cudaStream_t s = as_stream(stream);
     if (vec) {
         const int g = grid_for(ctx, (int64_t)B * (io / 4), 256, 4);
-        if (bf) corrupt_fwd_vec_kernel<true><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, out_cx, ld_cx, out_x, ld_x, out_mask_id);
-        else corrupt_fwd_vec_kernel<false><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        if (bf) launch_pdl(ctx, corrupt_fwd_vec_kernel<true>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        else launch_pdl(ctx, corrupt_fwd_vec_kernel<false>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, out_cx, ld_cx, out_x, ld_x, out_mask_id);
     } else {
         const int g = grid_for(ctx, (int64_t)B * io, 256, 4);
         if (bf) corrupt_fwd_scalar_kernel<true><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io, out_cx, ld_cx, out_x, ld_x, out_mask_id);

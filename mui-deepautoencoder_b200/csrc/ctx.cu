@@ -58,6 +58,7 @@ int codae_ctx_create(int device, codae_ctx** out) {
     c->err[0] = 0;
     c->encode_tiled = nullptr;
     c->splitk = 1;
+    c->pdl = 1;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -76,9 +77,11 @@ const char* codae_last_error(const codae_ctx* ctx) { return ctx ? ctx->err : g_c
 
 int codae_ctx_sm_count(const codae_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
 
-int codae_ctx_set_splitk(codae_ctx* ctx, int enabled) {
-    if (!ctx) return codae_fail(nullptr, CODAE_EINVAL, "codae_ctx_set_splitk: ctx is NULL");
-    ctx->splitk = enabled ? 1 : 0;
+int codae_ctx_set_option(codae_ctx* ctx, int option, int value) {
+    if (!ctx) return codae_fail(nullptr, CODAE_EINVAL, "codae_ctx_set_option: ctx is NULL");
+    if (option == CODAE_OPT_SPLITK) ctx->splitk = value ? 1 : 0;
+    else if (option == CODAE_OPT_PDL) ctx->pdl = value ? 1 : 0;
+    else return codae_fail(ctx, CODAE_EINVAL, "codae_ctx_set_option: unknown option %d", option);
     return CODAE_OK;
 }
 

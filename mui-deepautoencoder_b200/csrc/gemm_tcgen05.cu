@@ -233,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     constexpr int kStagePitch = BN + 4;               // floats per row of the staged fp32 tile
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int total_kb = (p.K + BK - 1) / BK;
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();     // everything above overlapped the previous kernel's tail; operands and outputs are global memory
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -490,15 +492,22 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = s;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    int na = 0;
     if (nsplit > 1) {
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 1;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = nsplit;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 1;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = nsplit;
+        ++na;
     }
+    if (ctx->pdl) {
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
     cudaError_t le = cudaLaunchKernelEx(&cfg, tc05_gemm_kernel<BN>, ma, mb, p);
     if (le != cudaSuccess) {
         cudaGetLastError();

@@ -21,6 +21,8 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_kernel(
     int64_t ld_y, const int32_t* __restrict__ mask_id, const uint64_t* __restrict__ mask_bits,
     const uint8_t* __restrict__ col_var, int B, int io, float grad_scale, void* __restrict__ dy, int64_t ld_dy,
     double* __restrict__ acc, LossWs* __restrict__ ws) {
+    pdl_launch_dependents();
+    pdl_wait();
     float s_full = 0.f, s_part = 0.f;
     if (kVec) {
         const int io4 = io >> 2;
@@ -275,9 +277,8 @@ int codae_mse_loss_fwd_bwd(codae_ctx* ctx, const float* x, int64_t ld_x, const i
     LossWs* ws = reinterpret_cast<LossWs*>(workspace);
     cudaStream_t s = as_stream(stream);
 #define LAUNCH(BY, BD, VEC)                                                                                         \
-    mse_loss_kernel<BY, BD, VEC><<<(unsigned)blocks, kLossThreads, 0, s>>>(x, ld_x, batch_idx, y, ld_y, mask_id,   \
-                                                                           mask_bits, col_var, B, io, grad_scale, \
-                                                                           dy, ld_dy, acc, ws)
+    launch_pdl(ctx, mse_loss_kernel<BY, BD, VEC>, dim3((unsigned)blocks), dim3(kLossThreads), 0, s, x, ld_x, batch_idx, y, ld_y, \
+               mask_id, mask_bits, col_var, B, io, grad_scale, dy, ld_dy, acc, ws)
     if (vec) {
         if (by && bd) LAUNCH(true, true, true);
         else if (by) LAUNCH(true, false, true);

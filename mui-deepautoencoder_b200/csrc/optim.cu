@@ -19,6 +19,8 @@ struct NormWs {
 
 __global__ void __launch_bounds__(kThreads) sqnorm_kernel(const float* __restrict__ g, int64_t n, float* __restrict__ out,
                                                           NormWs* __restrict__ ws) {
+    pdl_launch_dependents();
+    pdl_wait();
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     const int64_t n4 = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -87,6 +89,8 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
                                                         __nv_bfloat16* __restrict__ pb, int64_t n, AdamArgs a,
                                                         const float* __restrict__ sqnorm,
                                                         const int32_t* __restrict__ step_dev) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (step_dev) {
         // CUDA-graph replays cannot change scalar arguments: derive the bias corrections from a device counter,
         // in double like the host path.
@@ -144,7 +148,11 @@ __global__ void __launch_bounds__(kThreads) cast_bf16_kernel(const float* __rest
     }
 }
 
-__global__ void counter_add_kernel(int32_t* c, int delta) { *c += delta; }
+__global__ void counter_add_kernel(int32_t* c, int delta) {
+    pdl_launch_dependents();
+    pdl_wait();
+    *c += delta;
+}
 
 inline int grid_for(const codae_ctx* ctx, int64_t n4, int per_thread) {
     int64_t blocks = (n4 + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
@@ -167,8 +175,8 @@ int codae_grad_sqnorm(codae_ctx* ctx, const float* g, int64_t n, float* out_sqno
     CODAE_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(g) & 15) == 0, "codae_grad_sqnorm: g must be 16-byte aligned");
     if (ws_bytes < sizeof(NormWs))
         return codae_fail(ctx, CODAE_ENOMEM, "codae_grad_sqnorm: workspace %zu < %zu bytes", ws_bytes, sizeof(NormWs));
-    sqnorm_kernel<<<grid_for(ctx, n >> 2, 4), kThreads, 0, as_stream(stream)>>>(g, n, out_sqnorm,
-                                                                                 reinterpret_cast<NormWs*>(workspace));
+    launch_pdl(ctx, sqnorm_kernel, dim3(grid_for(ctx, n >> 2, 4)), dim3(kThreads), 0, as_stream(stream), g, n, out_sqnorm,
+               reinterpret_cast<NormWs*>(workspace));
     return codae_check_launch(ctx, "sqnorm_kernel");
 }
 
@@ -196,14 +204,14 @@ int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v
     a.grad_scale = (float)grad_scale;
     a.max_norm = (float)max_norm;
     if (n == 0) return CODAE_OK;
-    adam_kernel<<<grid_for(ctx, n >> 2, 2), kThreads, 0, as_stream(stream)>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
-                                                                               n, a, sqnorm, step_dev);
+    launch_pdl(ctx, adam_kernel, dim3(grid_for(ctx, n >> 2, 2)), dim3(kThreads), 0, as_stream(stream), p, (const float*)g, m, v,
+               reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a, sqnorm, step_dev);
     return codae_check_launch(ctx, "adam_kernel");
 }
 
 int codae_counter_add(codae_ctx* ctx, int32_t* counter, int delta, void* stream) {
     CODAE_REQUIRE(ctx, ctx && counter, "codae_counter_add: NULL argument");
-    counter_add_kernel<<<1, 1, 0, as_stream(stream)>>>(counter, delta);
+    launch_pdl(ctx, counter_add_kernel, dim3(1), dim3(1), 0, as_stream(stream), counter, delta);
     return codae_check_launch(ctx, "counter_add_kernel");
 }
 
