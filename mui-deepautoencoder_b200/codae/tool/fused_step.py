@@ -75,6 +75,7 @@ class FusedStep:
         lay, total = model.layout()
         self._layer_span = [(lay[l][0], lay[l + 1][0] if l + 1 < len(lay) else total) for l in range(len(lay))]
         self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
+        self._wgrad_stream = torch.cuda.Stream(device=dev)
         self._bufs = {}
         self._graphs = {}
         self._calls = {}
@@ -94,6 +95,7 @@ class FusedStep:
                 acts.append(M.new_activation(B, o, torch.float32 if last else adt, dev, width(o)))
             b = dict(acts=acts,
                      g0=torch.zeros((B, wmax), dtype=adt, device=dev), g1=torch.zeros((B, wmax), dtype=adt, device=dev),
+                     g2=torch.zeros((B, wmax), dtype=adt, device=dev),
                      mask_id=torch.zeros(B, dtype=torch.int32, device=dev),
                      idx=torch.zeros(B, dtype=torch.int64, device=dev),
                      x=torch.zeros((B, wmax), dtype=torch.float32, device=dev) if self.mixed is not None else None,
@@ -115,7 +117,8 @@ class FusedStep:
                           _C.ACT_RELU if model.relu[l] else _C.ACT_NONE, eng); n += 1
         y = acts[L]
         o_last = dims[L - 1][1]
-        g = b["g0"][:, :_round_up(o_last, 8)]
+        gbuf = [b["g0"], b["g1"], b["g2"]]            # dL/d(output of layer l) lives in gbuf[l % 3]
+        g = gbuf[(L - 1) % 3][:, :_round_up(o_last, 8)]
         if self.mixed is None:
             _C.mse_loss_fwd_bwd(data, idx, y, b["mask_id"], bits, col_var, B, self.io, 2.0 / (global_batch * self.io),
                                 g if train else None, self.acc, self.loss_ws); n += 1
@@ -127,31 +130,41 @@ class FusedStep:
                              nmiss, self.corrupter.k_max, b["mon"], self.mixed_acc); n += 1
         if not train:
             return n
-        cur, nxt = "g0", "g1"
-        overlap = self.world_size > 1 and self.overlap_allreduce
-        if overlap:
+        # Backward.  The input-gradient chain dgrad(L-1) -> ... -> dgrad(1) is the critical path; every weight gradient
+        # only needs dL/d(out_l) and the stored activation, so wgrad(l) runs on a second stream next to dgrad(l)
+        # (at B=128 each of these kernels is a ~8 us latency chain that leaves most of the GPU idle).
+        overlap_comm = self.world_size > 1 and self.overlap_allreduce
+        if overlap_comm:
             import torch.distributed as dist
-            main = torch.cuda.current_stream()
-            side = self._comm_stream
+        main = torch.cuda.current_stream()
+        side = self._wgrad_stream
+        wdone = [None] * L
         for l in range(L - 1, -1, -1):
             i, o = dims[l]
-            gl = b[cur][:, :_round_up(o, 8)]
-            _C.linear_wgrad(gl, acts[l], model.aug_view(self.gflat, l), None, B, o, _round_up(i, 8) + 1, eng); n += 1
-            if overlap:
-                # layer l's gradients (W and b are contiguous in the flat buffer) are final: reduce them on the
-                # communication stream while the remaining layers' backward GEMMs run on the compute stream.
-                ev = torch.cuda.Event()
-                ev.record(main)
-                side.wait_event(ev)
+            gl = gbuf[l % 3][:, :_round_up(o, 8)]
+            ready = torch.cuda.Event()
+            ready.record(main)                          # dL/d(out_l) has been produced (loss or dgrad(l+1))
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                _C.linear_wgrad(gl, acts[l], model.aug_view(self.gflat, l), None, B, o, _round_up(i, 8) + 1, eng); n += 1
+                wdone[l] = torch.cuda.Event()
+                wdone[l].record(side)
+            if overlap_comm:
+                # layer l's gradients (W' rows are contiguous in the flat buffer) are final: reduce them on the
+                # communication stream while the remaining backward GEMMs run.
+                comm = self._comm_stream
+                comm.wait_event(wdone[l])
                 lo, hi = self._layer_span[l]
-                with torch.cuda.stream(side):
+                with torch.cuda.stream(comm):
                     dist.all_reduce(self.gflat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
             if l > 0:
-                gp = b[nxt][:, :_round_up(i, 8)]
+                if l + 2 <= L - 1:
+                    main.wait_event(wdone[l + 2])       # dgrad(l) overwrites the buffer wgrad(l+2) was reading
+                gp = gbuf[(l - 1) % 3][:, :_round_up(i, 8)]
                 _C.linear_dgrad(gl, model.weight_view(wflat, l), acts[l] if model.relu[l - 1] else None, gp, B, o, i, eng); n += 1
-                cur, nxt = nxt, cur
-        if overlap:
-            main.wait_stream(side)
+        main.wait_stream(side)
+        if overlap_comm:
+            main.wait_stream(self._comm_stream)
         elif self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)

@@ -34,6 +34,19 @@ def to(self, *a, **k):
 fm.FlatMLP.to = to
 import codae.tool.data_tool as dtl
 dtl.Corrupter._cuda_device = lambda self: torch.device("cpu")
+class _FakeStream:
+    def __init__(self, *a, **k): pass
+    def wait_event(self, e): pass
+    def wait_stream(self, s): pass
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
+class _FakeEvent:
+    def __init__(self, *a, **k): pass
+    def record(self, s=None): pass
+torch.cuda.Stream = _FakeStream
+torch.cuda.Event = _FakeEvent
+torch.cuda.current_stream = lambda *a, **k: _FakeStream()
+torch.cuda.stream = lambda s: s
 torch.cuda.synchronize = lambda *a: None
 torch.cuda.current_device = lambda: 0
 
