@@ -137,14 +137,17 @@ class FusedStep:
         if overlap_comm:
             import torch.distributed as dist
         main = torch.cuda.current_stream()
-        side = self._wgrad_stream
+        # second stream only for the tensor-core engine: its small-batch kernels leave most SMs idle; the FFMA engine's
+        # kernels fill the GPU and only slow each other down (measured 7.1 vs 5.4 ms/step)
+        side = self._wgrad_stream if eng == _C.BF16 else main
         wdone = [None] * L
         for l in range(L - 1, -1, -1):
             i, o = dims[l]
             gl = gbuf[l % 3][:, :_round_up(o, 8)]
-            ready = torch.cuda.Event()
-            ready.record(main)                          # dL/d(out_l) has been produced (loss or dgrad(l+1))
-            side.wait_event(ready)
+            if side is not main:
+                ready = torch.cuda.Event()
+                ready.record(main)                      # dL/d(out_l) has been produced (loss or dgrad(l+1))
+                side.wait_event(ready)
             with torch.cuda.stream(side):
                 _C.linear_wgrad(gl, acts[l], model.aug_view(self.gflat, l), None, B, o, _round_up(i, 8) + 1, eng); n += 1
                 wdone[l] = torch.cuda.Event()
@@ -158,11 +161,12 @@ class FusedStep:
                 with torch.cuda.stream(comm):
                     dist.all_reduce(self.gflat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
             if l > 0:
-                if l + 2 <= L - 1:
+                if l + 2 <= L - 1 and side is not main:
                     main.wait_event(wdone[l + 2])       # dgrad(l) overwrites the buffer wgrad(l+2) was reading
                 gp = gbuf[(l - 1) % 3][:, :_round_up(i, 8)]
                 _C.linear_dgrad(gl, model.weight_view(wflat, l), acts[l] if model.relu[l - 1] else None, gp, B, o, i, eng); n += 1
-        main.wait_stream(side)
+        if side is not main:
+            main.wait_stream(side)
         if overlap_comm:
             main.wait_stream(self._comm_stream)
         elif self.world_size > 1:
