@@ -3,11 +3,12 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 N=${1:-2}
+LIST=${2:-"1 2 4 8"}
 nvidia-smi -L | head -8
 echo "== dist check N=$N"
 timeout -s KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/dist_gpu_check.py > gpurun_out/dist_check_$N.log 2>&1; echo "rc=$?"; grep -E "DP |sharded|DIST CHECK|Error|error" gpurun_out/dist_check_$N.log | tail -12
-for n in $(seq 1 $N); do
-  if [ $n -eq 1 ] || [ $n -eq 2 ] || [ $n -eq 4 ] || [ $n -eq 8 ]; then
+for n in $LIST; do
+  if [ $n -le $N ]; then
     echo "== bench N=$n"
     if [ $n -eq 1 ]; then
       timeout -s KILL 240 python bench.py --gpus 1 --no-cpu --no-fp32 > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
