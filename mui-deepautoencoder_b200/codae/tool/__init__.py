@@ -5,3 +5,4 @@ from .data_tool import collate_embedding, simple_collate, load_dataset_of_embedd
 from .metering import get_rmse, RankingLoss, CombinedCriterion
 from .fused_step import FusedStep
 from .inference import ComplementarityScorer
+from .embedding_file import write_cemb, read_cemb, convert_json_to_cemb, load_cemb_dataset

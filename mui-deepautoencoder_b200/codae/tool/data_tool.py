@@ -64,7 +64,11 @@ def simple_collate(batch):
 
 def load_dataset_of_embeddings(embedding_path, config, cache_dir="tmp/"):
     """JSON {obs_id: {category: [floats]}} -> ConcatenatedEmbeddingDataset, with the reference's pickle cache
-    keyed on sha1(st_ctime) (data_tool.py:114-162)."""
+    keyed on sha1(st_ctime) (data_tool.py:114-162).  A path ending in .cemb is read as the binary format of
+    codae.tool.embedding_file (memory-mapped, no cache needed)."""
+    if str(embedding_path).endswith(".cemb"):
+        from codae.tool.embedding_file import load_cemb_dataset
+        return load_cemb_dataset(embedding_path, config["DATASET"]["USED_CATEGORY"])
     using_cache = False
     dataset = None
     dataset_cache = glob.glob(os.path.join(cache_dir, "*_dataset.bin"))

@@ -129,5 +129,6 @@ if __name__ == "__main__":
         d = os.path.join(args.output_path, get_date() + "_train_" + config["DATASET"]["NAME"])
         os.makedirs(d, exist_ok=True)
         np.savez(os.path.join(d, "metrics.npz"), **{k: np.asarray(v) for k, v in book.items()})
-        torch.save(model.state_dict(), os.path.join(d, "model.pt"))   # new: stage IV needs a --model_path
+        torch.save({k: v.detach().cpu().clone() for k, v in model.state_dict().items()},
+                   os.path.join(d, "model.pt"))   # new: stage IV needs a --model_path (clones: params are views of one flat buffer)
         log.info("Data saved in directory %s" % d)
