@@ -388,7 +388,8 @@ def profile_step(fs, idx, B, world):
     pk = peaks()
     model = fs.model
     dims = model.dims
-    wrapped = ["corrupt_fwd", "linear_fwd", "mse_loss_fwd_bwd", "linear_wgrad", "linear_dgrad", "grad_sqnorm", "counter_add", "adam_step"]
+    wrapped = ["corrupt_fwd", "linear_fwd", "mse_loss_fwd_bwd", "linear_wgrad", "linear_dgrad", "grad_sqnorm", "counter_add", "adam_step",
+               "clip_adam_step"]
     orig = {n: getattr(_C, n) for n in wrapped}
     calls = {n: [] for n in wrapped}
 
@@ -438,6 +439,7 @@ def profile_step(fs, idx, B, world):
     small = B <= 1024      # small batch: a contraction is bound by streaming its weights / writing dW once, not by the tensor pipe
     algo = {  # name: (bound, algorithmic bytes or flops per STEP, unit note)
         "adam_step": ("hbm", (28 + (2 if bf else 0)) * P),
+        "clip_adam_step": ("hbm", (32 + (2 if bf else 0)) * P),
         "grad_sqnorm": ("hbm", 4 * P),
         "corrupt_fwd": ("hbm", B * io * (4 + sw)),
         "mse_loss_fwd_bwd": ("hbm", B * io * (4 + 4 + sw)),

@@ -166,6 +166,13 @@ int codae_grad_sqnorm(codae_ctx* ctx, const float* g, int64_t n, float* out_sqno
 int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
                     double lr, double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
                     const float* sqnorm, double grad_scale, const int32_t* step_dev, void* stream);
+/* codae_grad_sqnorm + codae_adam_step in ONE cooperative launch (grid barrier between the norm and the update): same
+ * arithmetic and argument meaning; sqnorm_out (f32[1]) receives sum g^2.  max_norm < 0 computes the norm but does not clip.
+ * workspace >= codae_sqnorm_workspace_bytes(). */
+int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr,
+                         double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
+                         float* sqnorm_out, void* workspace, size_t ws_bytes, double grad_scale, const int32_t* step_dev,
+                         void* stream);
 /* *counter += delta on the device (the Adam step counter of a CUDA-graph-captured training step). */
 int codae_counter_add(codae_ctx* ctx, int32_t* counter, int delta, void* stream);
 

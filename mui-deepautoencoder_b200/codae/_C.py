@@ -47,6 +47,7 @@ SIGNATURES = {
     "codae_sqnorm_workspace_bytes": (_sz, [_vp]),
     "codae_grad_sqnorm": (_i, [_vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "codae_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _d, _vp, _vp]),
+    "codae_clip_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _vp, _sz, _d, _vp, _vp]),
     "codae_counter_add": (_i, [_vp, _vp, _i, _vp]),
     "codae_score_topk_workspace_bytes": (_sz, [_vp, _i, _i]),
     "codae_score_topk": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -239,6 +240,12 @@ def adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sq
     c = ctx(pf.device)
     check(lib().codae_adam_step(c, p(pf), p(g), p(m), p(v), p(p_bf16), pf.numel(), lr, beta1, beta2, eps, wd, step, max_norm,
                                 p(sqnorm), grad_scale, p(step_dev), stream()), c)
+
+
+def clip_adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm_out, ws, grad_scale, step_dev=None):
+    c = ctx(pf.device)
+    check(lib().codae_clip_adam_step(c, p(pf), p(g), p(m), p(v), p(p_bf16), pf.numel(), lr, beta1, beta2, eps, wd, step, max_norm,
+                                     p(sqnorm_out), p(ws), ws.numel(), grad_scale, p(step_dev), stream()), c)
 
 
 def counter_add(counter, delta):

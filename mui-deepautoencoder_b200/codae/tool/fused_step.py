@@ -9,7 +9,8 @@ Replaces, per step (script/train_dae_on_embedding.py:198-223; script/train_dae_o
                               contraction, no column-sum kernel), (L-1) x codae_linear_dgrad
   [data parallel]          -> NCCL all-reduce of the flat gradient buffer, issued per layer on a communication stream
                               as soon as that layer's wgrad has finished (overlaps the rest of the backward pass)
-  clip_grad_norm_ + Adam   -> codae_grad_sqnorm + codae_adam_step over the flat buffers
+  clip_grad_norm_ + Adam   -> codae_clip_adam_step: one cooperative launch over the flat buffers (norm, grid barrier,
+                              update); or codae_grad_sqnorm + codae_adam_step
 No host synchronisation happens inside a step; monitors stay on the device until read_monitors().
 The whole sequence can be captured once per batch size into a CUDA graph (use_graph=True).
 """
@@ -28,7 +29,8 @@ class FusedStep:
     BUCKET_BYTES = 32 << 20     # gradient all-reduce bucket (bytes of fp32 gradients)
 
     def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
-                 max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True):
+                 max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True,
+                 fused_clip_adam=True):
         """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
         tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
         {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
@@ -44,6 +46,7 @@ class FusedStep:
         self.use_graph = use_graph
         self.mixed = mixed
         self.overlap_allreduce = overlap_allreduce
+        self.fused_clip_adam = fused_clip_adam
         dev = model.flat.device
         self.dev = dev
         self.io = model.dims[0][0]
@@ -180,12 +183,17 @@ class FusedStep:
         elif self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
-        if self.clip:
-            _C.grad_sqnorm(self.gflat, self.sqnorm, self.norm_ws); n += 1
         _C.counter_add(self.step_dev, 1); n += 1
-        _C.adam_step(model.flat, self.gflat, self.m, self.v, model.flat_bf16 if eng == _C.BF16 else None, self.lr,
-                     self.betas[0], self.betas[1], self.eps, self.wd, 0, self.max_norm if self.clip else -1.0,
-                     self.sqnorm if self.clip else None, 1.0, self.step_dev); n += 1
+        pb = model.flat_bf16 if eng == _C.BF16 else None
+        if self.clip and self.fused_clip_adam:
+            # ||g||^2, clip scale and Adam in one cooperative launch (the second read of g comes from L2)
+            _C.clip_adam_step(model.flat, self.gflat, self.m, self.v, pb, self.lr, self.betas[0], self.betas[1], self.eps,
+                              self.wd, 0, self.max_norm, self.sqnorm, self.norm_ws, 1.0, self.step_dev); n += 1
+        else:
+            if self.clip:
+                _C.grad_sqnorm(self.gflat, self.sqnorm, self.norm_ws); n += 1
+            _C.adam_step(model.flat, self.gflat, self.m, self.v, pb, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
+                         0, self.max_norm if self.clip else -1.0, self.sqnorm if self.clip else None, 1.0, self.step_dev); n += 1
         return n
 
     # ---- public API ------------------------------------------------------------------------------------------

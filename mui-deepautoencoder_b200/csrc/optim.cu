@@ -2,6 +2,7 @@
 // HBM-bound: 4 B/param for the norm pass, 28 B/param (+2 with a bf16 shadow) for the update.
 // The arithmetic follows torch 2.11's single-tensor Adam operation by operation (no re-association,
 // explicit _rn intrinsics where ATen does not fuse) so that weights track the reference to fp32 rounding.
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "common.cuh"
@@ -132,6 +133,86 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
     }
 }
 
+// clip_grad_norm_ + Adam in ONE cooperative launch: phase 1 reduces ||g||^2 (per-CTA partials, then every CTA sums the
+// partials in the same fixed order), a grid barrier, phase 2 applies the update.  g (4 B/param) is read twice, but the
+// second read is served by the 126 MB L2 for the shipped configs (94 MB of gradients), and one launch disappears.
+__global__ void __launch_bounds__(kThreads) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                             float* __restrict__ m, float* __restrict__ v,
+                                                             __nv_bfloat16* __restrict__ pb, int64_t n, AdamArgs a,
+                                                             NormWs* __restrict__ ws, float* __restrict__ sqnorm_out,
+                                                             const int32_t* __restrict__ step_dev) {
+    namespace cg = cooperative_groups;
+    __shared__ double scratch[32];
+    __shared__ float s_coef;
+    const int64_t n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; e + stride < n4; e += 2 * stride) {
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(g) + e);
+            const float4 y = __ldcg(reinterpret_cast<const float4*>(g) + e + stride);
+            s0 = fmaf(x.x, x.x, s0); s1 = fmaf(x.y, x.y, s1); s2 = fmaf(x.z, x.z, s2); s3 = fmaf(x.w, x.w, s3);
+            s0 = fmaf(y.x, y.x, s0); s1 = fmaf(y.y, y.y, s1); s2 = fmaf(y.z, y.z, s2); s3 = fmaf(y.w, y.w, s3);
+        }
+        for (; e < n4; e += stride) {
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(g) + e);
+            s0 = fmaf(x.x, x.x, s0); s1 = fmaf(x.y, x.y, s1); s2 = fmaf(x.z, x.z, s2); s3 = fmaf(x.w, x.w, s3);
+        }
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+            const float x = g[(n4 << 2) + threadIdx.x];
+            s0 = fmaf(x, x, s0);
+        }
+        const double b = block_sum<double>((double)((s0 + s1) + (s2 + s3)), scratch);
+        if (threadIdx.x == 0) ws->partial[blockIdx.x] = b;
+    }
+    cg::this_grid().sync();
+    {
+        double t = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) t += __ldcg(&ws->partial[i]);
+        t = block_sum<double>(t, scratch);
+        if (threadIdx.x == 0) {
+            const float sq = (float)t;
+            if (blockIdx.x == 0) *sqnorm_out = sq;
+            const float total = __fmul_rn(sqrtf(sq), a.grad_scale);
+            s_coef = a.max_norm >= 0.f ? fminf(__fdiv_rn(a.max_norm, __fadd_rn(total, 1e-6f)), 1.0f) : 1.0f;
+        }
+        __syncthreads();
+    }
+    const float coef = s_coef;
+    if (step_dev) {
+        const double t = (double)(*step_dev);
+        a.bc2_sqrt = (float)sqrt(1.0 - pow(a.beta2_d, t));
+        a.neg_step = (float)(-(a.lr_d / (1.0 - pow(a.beta1_d, t))));
+    }
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += stride) {
+        float4 pv = *reinterpret_cast<const float4*>(p + 4 * e);
+        const float4 gv = __ldcg(reinterpret_cast<const float4*>(g) + e);
+        float4 mv = *reinterpret_cast<const float4*>(m + 4 * e);
+        float4 vv = *reinterpret_cast<const float4*>(v + 4 * e);
+        adam_one(pv.x, gv.x, mv.x, vv.x, a, coef);
+        adam_one(pv.y, gv.y, mv.y, vv.y, a, coef);
+        adam_one(pv.z, gv.z, mv.z, vv.z, a, coef);
+        adam_one(pv.w, gv.w, mv.w, vv.w, a, coef);
+        *reinterpret_cast<float4*>(p + 4 * e) = pv;
+        *reinterpret_cast<float4*>(m + 4 * e) = mv;
+        *reinterpret_cast<float4*>(v + 4 * e) = vv;
+        if (pb) {
+            uint2 q;
+            q.x = pack_bf16x2(pv.x, pv.y);
+            q.y = pack_bf16x2(pv.z, pv.w);
+            *reinterpret_cast<uint2*>(pb + 4 * e) = q;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (n4 << 2) + threadIdx.x;
+        float pv = p[i], mv = m[i], vv = v[i];
+        adam_one(pv, g[i], mv, vv, a, coef);
+        p[i] = pv; m[i] = mv; v[i] = vv;
+        if (pb) pb[i] = __float2bfloat16_rn(pv);
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
                                                              int64_t n) {
     const int64_t n4 = n >> 2;
@@ -207,6 +288,62 @@ int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v
     launch_pdl(ctx, adam_kernel, dim3(grid_for(ctx, n >> 2, 2)), dim3(kThreads), 0, as_stream(stream), p, (const float*)g, m, v,
                reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a, sqnorm, step_dev);
     return codae_check_launch(ctx, "adam_kernel");
+}
+
+int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr,
+                         double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
+                         float* sqnorm_out, void* workspace, size_t ws_bytes, double grad_scale, const int32_t* step_dev,
+                         void* stream) {
+    CODAE_REQUIRE(ctx, ctx && p && g && m && v && sqnorm_out && workspace && n >= 0 && (step >= 1 || step_dev),
+                  "codae_clip_adam_step: bad argument");
+    CODAE_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
+                  "codae_clip_adam_step: buffers must be 16-byte aligned");
+    if (ws_bytes < sizeof(NormWs))
+        return codae_fail(ctx, CODAE_ENOMEM, "codae_clip_adam_step: workspace %zu < %zu bytes", ws_bytes, sizeof(NormWs));
+    if (step < 1) step = 1;
+    AdamArgs a;
+    a.beta1_d = beta1; a.beta2_d = beta2; a.lr_d = lr;
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    a.w1 = (float)(1.0 - beta1);
+    a.beta2 = (float)beta2;
+    a.omb2 = (float)(1.0 - beta2);
+    a.bc2_sqrt = (float)sqrt(bc2);
+    a.neg_step = (float)(-(lr / bc1));
+    a.eps = (float)eps;
+    a.wd = (float)weight_decay;
+    a.grad_scale = (float)grad_scale;
+    a.max_norm = (float)max_norm;
+    if (n == 0) return CODAE_OK;
+    // cooperative launch: the grid must be co-resident
+    static int max_blocks_per_sm = 0;
+    if (!max_blocks_per_sm) {
+        cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, clip_adam_kernel, kThreads, 0);
+        if (oe != cudaSuccess || max_blocks_per_sm < 1) {
+            max_blocks_per_sm = 0;
+            cudaGetLastError();
+            return codae_fail(ctx, CODAE_ECUDA, "codae_clip_adam_step: occupancy query failed");
+        }
+    }
+    int grid = grid_for(ctx, n >> 2, 2);
+    if (grid > max_blocks_per_sm * ctx->sm_count) grid = max_blocks_per_sm * ctx->sm_count;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = as_stream(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, clip_adam_kernel, p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a,
+                                        reinterpret_cast<NormWs*>(workspace), sqnorm_out, step_dev);
+    if (le != cudaSuccess) {
+        cudaGetLastError();
+        return codae_fail(ctx, CODAE_ECUDA, "clip_adam_kernel cooperative launch (grid %d): %s", grid, cudaGetErrorString(le));
+    }
+    return codae_check_launch(ctx, "clip_adam_kernel");
 }
 
 int codae_counter_add(codae_ctx* ctx, int32_t* counter, int delta, void* stream) {

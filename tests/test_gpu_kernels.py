@@ -210,6 +210,29 @@ def test_clip_adam_matches_torch_semantics(C, dev, n, clip, wd, shadow):
         assert torch.equal(sh.cpu().view(torch.int16), P.cpu().to(torch.bfloat16).view(torch.int16))
 
 
+@pytest.mark.parametrize("n,shadow", [(23_608_320 // 8 + 5, True), (792, False), (4096, True)])
+def test_fused_clip_adam_equals_separate_kernels(C, dev, n, shadow):
+    """The cooperative norm + Adam launch is the two-kernel sequence, bit for bit (weights, moments, shadow, norm)."""
+    torch.manual_seed(12)
+    p0, g = torch.randn(n) * 0.05, torch.randn(n) * 3.0
+    A = [p0.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)]
+    Bf = [p0.clone().to(dev), torch.zeros(n, device=dev), torch.zeros(n, device=dev)]
+    shA = torch.zeros(n, dtype=torch.bfloat16, device=dev) if shadow else None
+    shB = torch.zeros(n, dtype=torch.bfloat16, device=dev) if shadow else None
+    sqA, sqB = torch.zeros(1, device=dev), torch.zeros(1, device=dev)
+    wsA, wsB = C.sqnorm_workspace(dev), C.sqnorm_workspace(dev)
+    G = g.to(dev)
+    for step in range(1, 4):
+        C.grad_sqnorm(G, sqA, wsA)
+        C.adam_step(A[0], G, A[1], A[2], shA, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step, 1.0, sqA, 1.0)
+        C.clip_adam_step(Bf[0], G, Bf[1], Bf[2], shB, 1e-3, 0.9, 0.999, 1e-8, 1e-2, step, 1.0, sqB, wsB, 1.0)
+        assert float(sqA.item()) > 0 and abs(float(sqA.item()) - float(sqB.item())) <= 1e-6 * float(sqA.item())
+        for x, y in zip(A, Bf):
+            assert rel(y.cpu().numpy(), x.cpu().numpy()) < 2e-6
+    if shadow:
+        assert torch.equal(shB.view(torch.int16), Bf[0].to(torch.bfloat16).view(torch.int16))
+
+
 def test_adam_device_step_counter(C, dev):
     """step_dev overrides the scalar step: the graph-replay path gives the same numbers as the host-scalar path."""
     torch.manual_seed(4)

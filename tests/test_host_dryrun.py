@@ -10,4 +10,4 @@ def test_host_paths_issue_well_typed_kernel_sequences():
     r = subprocess.run([sys.executable, os.path.join(here, "_host_dryrun.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DRY RUN OK" in r.stdout
-    assert "fp32 launches 28" in r.stdout and "bf16 launches 28" in r.stdout   # 1 + 8 + 1 + 8 + 7 + 3
+    assert "fp32 launches 27" in r.stdout and "bf16 launches 27" in r.stdout   # 1 + 8 + 1 + 8 + 7 + counter + fused clip/Adam
