@@ -47,6 +47,7 @@ struct Params {
     long long ldm;
     int stages;                  // pipeline depth actually used (<= Cfg::kStages)
     int staged;                  // 1: epilogue through the shared-memory tile (required when gridDim.z > 1)
+    unsigned long long* trace;   // debugging: CTA (0,0,0) writes %globaltimer stamps of its phases here (or NULL)
 };
 
 template <int BN>
@@ -140,6 +141,14 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t
     float4 v;
     asm volatile("ld.shared::cluster.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
     return v;
+}
+
+__device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.trace[slot] = t;
+    }
 }
 
 // Shared-memory matrix descriptor (sm_100 format: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
@@ -236,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    if (threadIdx.x == 0) trace_stamp(p, 0);                       // kernel entry
     const int total_kb = (p.K + BK - 1) / BK;
     const int nsplit = gridDim.z;
     const int kb_per = (total_kb + nsplit - 1) / nsplit;
@@ -256,7 +266,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();     // everything above overlapped the previous kernel's tail; operands and outputs are global memory
+    if (threadIdx.x == 0) trace_stamp(p, 1);                       // prologue done (barriers, TMEM)
+    pdl_wait();
+    if (threadIdx.x == 0) trace_stamp(p, 2);                       // predecessor complete     // everything above overlapped the previous kernel's tail; operands and outputs are global memory
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -293,6 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
             uint32_t ph = 0;
             for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == nstages ? 0 : s + 1), ph ^= (s == 0)) {
                 mbar_wait(&full_bar[s], ph);
+                if (kb == 0) trace_stamp(p, 3);                    // first operands landed
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
                 const uint32_t b_addr = a_addr + kATileBytes;
@@ -304,10 +317,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 umma_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
             }
             umma_commit(tmem_full_bar);              // accumulator complete
+            trace_stamp(p, 4);                       // all MMAs issued
         }
     } else {
         // ===== epilogue, part 1: TMEM -> registers -> HBM (direct) or -> shared-memory tile (staged) =====
         mbar_wait(tmem_full_bar, 0);
+        if (threadIdx.x == 64) trace_stamp(p, 5);                  // accumulator complete
         tc_fence_after();
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int row = m0 + q * 32 + lane;
@@ -338,8 +353,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     if (p.staged) {
         // ===== epilogue, part 2 (staged): [cluster reduce +] fused epilogue + coalesced stores =====
         __syncwarp();
+        if (threadIdx.x == 64) trace_stamp(p, 6);                  // tile staged in shared memory
         if (nsplit > 1) cluster_sync();                      // every thread of every CTA of the cluster
         else if (warp >= 2) asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) trace_stamp(p, 7);                  // cluster barrier 1 passed
         if (warp >= 2) {
             const int t = threadIdx.x - 64;                  // 0..127
             const int rank = blockIdx.z;                     // == %cluster_ctarank (cluster spans grid z only)
@@ -408,7 +425,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 }
             }
         }
+        if (threadIdx.x == 64) trace_stamp(p, 8);                  // reduced + stored
         if (nsplit > 1) cluster_sync();                      // peers may still be reading this CTA's tile
+        if (threadIdx.x == 64) trace_stamp(p, 9);                  // cluster barrier 2 passed
     }
     tc_fence_before();
     __syncthreads();
@@ -417,6 +436,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         tmem_dealloc(tmem_base, BN);
     }
 }
+
+unsigned long long* g_trace_buf = nullptr;   // set through codae_debug_set_trace (debugging hook, not part of the ABI)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -471,6 +492,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     // staged (coalesced) epilogue: always for split-K; for fp32 outputs only while the grid is at most ~2 waves
     // (measured: the direct epilogue is faster for the 4096-wide weight gradients, 247 vs 261 us)
+    p.trace = g_trace_buf;
     p.staged = (nsplit > 1 || (g.c_dtype == CODAE_F32 && tiles <= 2 * ctx->sm_count)) ? 1 : 0;
     static bool attr_set = false;
     if (!attr_set) {
@@ -520,6 +542,13 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
+
+// Debugging hook (exported, deliberately absent from include/codae_b200.h): device buffer of >= 16 u64 that CTA (0,0,0) of
+// every subsequent tcgen05 GEMM fills with %globaltimer stamps of its phases; NULL switches it off.
+extern "C" int codae_debug_set_trace(void* device_buf) {
+    g_trace_buf = reinterpret_cast<unsigned long long*>(device_buf);
+    return 0;
+}
 
 bool codae_tc05_supported(const codae_ctx* ctx, const Tc05Gemm& g) {
     if (!ctx || !ctx->encode_tiled) return false;

@@ -1,0 +1,51 @@
+"""Diagnostic (not a pytest file): phase timeline of the tcgen05 GEMM at the embedding.yaml shapes, from %globaltimer
+stamps written by CTA (0,0,0) (debug hook codae_debug_set_trace).  Prints ns since kernel entry per phase and the
+entry-to-entry interval of back-to-back launches."""
+import ctypes, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "mui-deepautoencoder_b200"))
+import torch
+from codae import _C
+
+dev = torch.device("cuda", 0)
+bf = torch.bfloat16
+lib = _C.lib()
+lib.codae_debug_set_trace.argtypes = [ctypes.c_void_p]
+names = ["entry", "prologue", "pdl_wait", "first_operands", "mma_issued", "acc_complete", "staged", "cluster_bar1", "stored", "cluster_bar2"]
+M, N, K = 128, 1536, 1537
+ld = 1600
+X = torch.zeros(M, ld, device=dev, dtype=bf); X[:, :1536] = torch.randn(M, 1536, device=dev).to(bf); X[:, 1536] = 1
+W = torch.zeros(N, ld, device=dev, dtype=bf); W[:, :1537] = (torch.randn(N, 1537, device=dev) / 40).to(bf)
+Y = torch.zeros(M, ld, device=dev, dtype=bf)
+dY = torch.randn(M, ld, device=dev).to(bf)
+dX = torch.zeros(M, ld, device=dev, dtype=bf)
+dW = torch.zeros(N, ld, device=dev)
+R = 12
+buf = torch.zeros(R * 16, dtype=torch.int64, device=dev)
+
+
+def run(tag, fn):
+    for split in (1, 0):
+        _C.set_splitk(dev, bool(split))
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        buf.zero_()
+        for i in range(R):
+            lib.codae_debug_set_trace(ctypes.c_void_p(buf.data_ptr() + 128 * i))
+            fn()
+        lib.codae_debug_set_trace(None)
+        torch.cuda.synchronize()
+        t = buf.cpu().view(R, 16)
+        last = t[R - 1]
+        rel = [(names[j], int(last[j] - last[0])) for j in range(10) if int(last[j]) != 0]
+        gaps = [int(t[i + 1][0] - t[i][0]) for i in range(R - 1)]
+        print("%-6s splitk=%d  entry-to-entry ns: %s" % (tag, split, gaps[-5:]), flush=True)
+        print("        phases (ns since entry): " + "  ".join("%s=%d" % (n, v) for n, v in rel), flush=True)
+    _C.set_splitk(dev, True)
+
+
+run("fwd", lambda: _C.linear_fwd(X[:, :K], W[:, :K], None, Y, M, N, K, _C.ACT_RELU, _C.BF16))
+run("dgrad", lambda: _C.linear_dgrad(dY[:, :N], W[:, :1536], X[:, :1536], dX, M, N, 1536, _C.BF16))
+run("wgrad", lambda: _C.linear_wgrad(dY[:, :N], X[:, :K], dW[:, :K], None, M, N, K, _C.BF16))
+print("trace done")
