@@ -372,11 +372,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 if (nsplit == 1) {
                     acc = *reinterpret_cast<const float4*>(smem + off);
                 } else {
+                    // all remote loads in flight before the first add (a rolled loop serialises one DSMEM round trip
+                    // of ~110 ns per split: measured 2.5 us for this phase), then summed in rank order
+                    float4 part[kMaxSplit];
+#pragma unroll
+                    for (int sp = 0; sp < kMaxSplit; ++sp)
+                        if (sp < nsplit) part[sp] = ld_dsmem_f4(stage_base + off, (uint32_t)sp);
                     acc = make_float4(0.f, 0.f, 0.f, 0.f);
-                    for (int sp = 0; sp < nsplit; ++sp) {    // rank order: bitwise reproducible
-                        const float4 v = ld_dsmem_f4(stage_base + off, (uint32_t)sp);
-                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-                    }
+#pragma unroll
+                    for (int sp = 0; sp < kMaxSplit; ++sp)
+                        if (sp < nsplit) { acc.x += part[sp].x; acc.y += part[sp].y; acc.z += part[sp].z; acc.w += part[sp].w; }
                 }
                 const int row = m0 + rl, col = n0 + 4 * c4;
                 if (row >= p.M || col >= p.N) continue;
