@@ -440,6 +440,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         tc_fence_after();
         tmem_dealloc(tmem_base, BN);
     }
+    if (p.trace && threadIdx.x == 0) {          // debugging: slot 10 = exit of CTA (0,0,0), slot 11 = last CTA exit, slot 12 = first entry
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[10] = t;
+        atomicMax(&p.trace[11], t);
+    }
 }
 
 unsigned long long* g_trace_buf = nullptr;   // set through codae_debug_set_trace (debugging hook, not part of the ABI)

@@ -48,4 +48,35 @@ def run(tag, fn):
 run("fwd", lambda: _C.linear_fwd(X[:, :K], W[:, :K], None, Y, M, N, K, _C.ACT_RELU, _C.BF16))
 run("dgrad", lambda: _C.linear_dgrad(dY[:, :N], W[:, :1536], X[:, :1536], dX, M, N, 1536, _C.BF16))
 run("wgrad", lambda: _C.linear_wgrad(dY[:, :N], X[:, :K], dW[:, :K], None, M, N, K, _C.BF16))
+
+# ---- inside a CUDA graph: a chain of dependent launches (fwd -> fwd -> ...), as in the training step ----
+names2 = names + ["exit_cta0", "exit_last"]
+for split in (1, 0):
+    _C.set_splitk(dev, bool(split))
+    Ys = [torch.zeros(M, ld, device=dev, dtype=bf) for _ in range(2)]
+    for y in Ys:
+        y[:, 1536] = 1
+    def chain():
+        src = X
+        for i in range(R):
+            lib.codae_debug_set_trace(ctypes.c_void_p(buf.data_ptr() + 128 * i))
+            dst = Ys[i % 2]
+            _C.linear_fwd(src[:, :K], W[:, :K], None, dst, M, N, K, _C.ACT_RELU, _C.BF16)
+            src = dst
+        lib.codae_debug_set_trace(None)
+    chain(); torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        chain()
+    for _ in range(3):
+        buf.zero_(); gr.replay()
+    torch.cuda.synchronize()
+    t = buf.cpu().view(R, 16)
+    print("graph chain splitk=%d" % split)
+    for i in range(R - 4, R):
+        e = int(t[i][0])
+        print("   launch %2d: entry-to-entry %6d ns | in-kernel: %s | gap to next entry after last exit: %s" % (
+            i, e - int(t[i - 1][0]), " ".join("%s=%d" % (names2[j], int(t[i][j]) - e) for j in (2, 3, 5, 8, 10, 11) if int(t[i][j])),
+            (int(t[i + 1][0]) - int(t[i][11])) if i + 1 < R else "-"), flush=True)
+_C.set_splitk(dev, True)
 print("trace done")
