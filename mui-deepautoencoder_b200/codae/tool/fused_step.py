@@ -80,7 +80,7 @@ class FusedStep:
         lay, total = model.layout()
         self._layer_span = [(lay[l][0], lay[l + 1][0] if l + 1 < len(lay) else total) for l in range(len(lay))]
         self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
-        self._wgrad_stream = torch.cuda.Stream(device=dev)
+        self._wgrad_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
         self._bufs = {}
         self._graphs = {}
         self._calls = {}
@@ -144,12 +144,13 @@ class FusedStep:
         main = torch.cuda.current_stream()
         # second stream only for the tensor-core engine: its small-batch kernels leave most SMs idle; the FFMA engine's
         # kernels fill the GPU and only slow each other down (measured 7.1 vs 5.4 ms/step)
-        side = self._wgrad_stream if eng == _C.BF16 else main
+        sides = self._wgrad_streams if eng == _C.BF16 else [main]
         wdone = [None] * L
         bucket_hi = None
         for l in range(L - 1, -1, -1):
             i, o = dims[l]
             gl = gbuf[l % 3][:, :_round_up(o, 8)]
+            side = sides[l % len(sides)]                # weight gradients are mutually independent: alternate streams
             if side is not main:
                 ready = torch.cuda.Event()
                 ready.record(main)                      # dL/d(out_l) has been produced (loss or dgrad(l+1))
@@ -172,12 +173,13 @@ class FusedStep:
                         dist.all_reduce(self.gflat[lo:bucket_hi], op=dist.ReduceOp.SUM, group=self.pg)
                     bucket_hi = None
             if l > 0:
-                if l + 2 <= L - 1 and side is not main:
+                if l + 2 <= L - 1 and sides[0] is not main:
                     main.wait_event(wdone[l + 2])       # dgrad(l) overwrites the buffer wgrad(l+2) was reading
                 gp = gbuf[(l - 1) % 3][:, :_round_up(i, 8)]
                 _C.linear_dgrad(gl, model.weight_view(wflat, l), acts[l] if model.relu[l - 1] else None, gp, B, o, i, eng); n += 1
-        if side is not main:
-            main.wait_stream(side)
+        for side in sides:
+            if side is not main:
+                main.wait_stream(side)
         if overlap_comm:
             main.wait_stream(self._comm_stream)
         elif self.world_size > 1:
