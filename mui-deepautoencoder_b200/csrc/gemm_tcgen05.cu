@@ -21,6 +21,8 @@
 // spread over a thread-block CLUSTER along grid z; every CTA stages its partial tile in its own shared memory and,
 // after a cluster barrier, CTA r reduces rows [128 r / S, 128 (r+1) / S) of all S partials through distributed
 // shared memory (ld.shared::cluster) in rank order -- deterministic, no HBM round trip, no atomics.
+// (A push variant -- st.shared::cluster into the owner, one barrier -- was measured slower: 8.1 vs 6.8 us per
+// dependent launch; remote stores cost more than the second barrier saves.)
 #include <cuda.h>
 
 #include "common.cuh"
@@ -130,11 +132,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 
 // All threads of all CTAs of the cluster.  Non-.aligned forms: lanes of the producer / MMA warps arrive from
 // different program points.
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 __device__ __forceinline__ void cluster_sync() {
-    cluster_arrive();
-    cluster_wait();
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
 // 128-bit load from the shared memory of CTA `rank` of this cluster (distributed shared memory).
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t rank) {
@@ -151,13 +151,6 @@ __device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[slot] = t;
     }
-}
-
-// 128-bit store into the shared memory of CTA `rank` of this cluster.
-__device__ __forceinline__ void st_dsmem_f4(uint32_t local_smem_addr, uint32_t rank, float4 v) {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
-    asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // Shared-memory matrix descriptor (sm_100 format: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
@@ -260,9 +253,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     const int kb_per = (total_kb + nsplit - 1) / nsplit;
     const int kb_begin = blockIdx.z * kb_per;
     const int num_kb = min(total_kb, kb_begin + kb_per) - kb_begin;      // >= 1 by construction (host)
-    const int rmax = (BM + nsplit - 1) / nsplit;        // rows of the tile one cluster CTA reduces (split-K)
-    float* xchg = reinterpret_cast<float*>(smem + nstages * C::kStageBytes + 256);   // split-K exchange region
-    const uint32_t xchg_base = smem_u32(xchg);
+    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
@@ -277,9 +268,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    // split-K: a CTA may only be written through distributed shared memory once it runs.  Barrier 0: every thread
-    // arrives here; the epilogue warps wait before their first push, the other warps before barrier 1.
-    if (nsplit > 1) cluster_arrive();
     if (threadIdx.x == 0) trace_stamp(p, 1);                       // prologue done (barriers, TMEM)
     pdl_wait();
     if (threadIdx.x == 0) trace_stamp(p, 2);                       // predecessor complete     // everything above overlapped the previous kernel's tail; operands and outputs are global memory
@@ -341,15 +329,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < p.M;
-        // staged, no split: this CTA's own tile, laid over the drained pipeline slots.
-        // staged, split-K : row r of the partial tile is PUSHED into the shared memory of the cluster CTA that owns
-        //                   rows [128 o / S, 128 (o+1) / S) (slot [this rank][r - first row]); the exchange region is
-        //                   dedicated (after the barriers) because a fast peer pushes while this CTA's MMAs still run.
-        const int rt = q * 32 + lane;                // row within the tile
-        float* stage_row = reinterpret_cast<float*>(smem) + (size_t)rt * kStagePitch;
-        const int owner = ((rt + 1) * nsplit - 1) / BM;
-        const uint32_t push_addr = xchg_base + (uint32_t)((blockIdx.z * rmax + (rt - (owner * BM) / nsplit)) * kStagePitch) * 4u;
-        if (nsplit > 1) cluster_wait();              // barrier 0: every CTA of the cluster is running
+        float* stage_row = reinterpret_cast<float*>(smem) + (size_t)(q * 32 + lane) * kStagePitch;
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t v[32];
@@ -361,12 +341,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 store_chunk<32>(p, row, col0, f);
-            } else if (nsplit > 1) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    st_dsmem_f4(push_addr + (uint32_t)(c * 32 + 4 * j) * 4u, (uint32_t)owner,
-                                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                            __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
             } else {
                 // row pitch BN+4 floats: the 8 lanes of a 128-bit store phase hit 8 distinct 16-byte bank groups
                 float4* dst = reinterpret_cast<float4*>(stage_row + c * 32);
@@ -382,12 +356,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         // ===== epilogue, part 2 (staged): [cluster reduce +] fused epilogue + coalesced stores =====
         __syncwarp();
         if (threadIdx.x == 64) trace_stamp(p, 6);                  // tile staged in shared memory
-        if (nsplit > 1) {
-            if (warp < 2) cluster_wait();                    // barrier 0 (the epilogue warps waited before pushing)
-            cluster_sync();                                  // barrier 1: all partial rows have been pushed
-        } else if (warp >= 2) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
+        if (nsplit > 1) cluster_sync();                      // every thread of every CTA of the cluster
+        else if (warp >= 2) asm volatile("bar.sync 1, 128;" ::: "memory");
         if (threadIdx.x == 64) trace_stamp(p, 7);                  // cluster barrier 1 passed
         if (warp >= 2) {
             const int t = threadIdx.x - 64;                  // 0..127
@@ -395,20 +365,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
             const int r_begin = (rank * BM) / nsplit, r_end = ((rank + 1) * BM) / nsplit;
             constexpr int kVecPerRow = BN / 4;
             const int items = (r_end - r_begin) * kVecPerRow;
+            const uint32_t stage_base = smem_u32(smem);
             for (int it = t; it < items; it += 128) {
                 const int rl = r_begin + it / kVecPerRow;    // row within the tile
                 const int c4 = it % kVecPerRow;
+                const uint32_t off = (uint32_t)(rl * kStagePitch + 4 * c4) * 4u;
                 float4 acc;
                 if (nsplit == 1) {
-                    acc = *reinterpret_cast<const float4*>(smem + (uint32_t)(rl * kStagePitch + 4 * c4) * 4u);
+                    acc = *reinterpret_cast<const float4*>(smem + off);
                 } else {
-                    // this CTA's rows of all S partial tiles now sit in its own exchange region: S local 128-bit loads,
-                    // summed in rank order (bitwise reproducible)
-                    const float* src = xchg + (size_t)(rl - r_begin) * kStagePitch + 4 * c4;
+                    // all remote loads in flight before the first add (a rolled loop serialises one DSMEM round trip
+                    // of ~110 ns per split: measured 2.5 us for this phase), then summed in rank order
                     float4 part[kMaxSplit];
 #pragma unroll
                     for (int sp = 0; sp < kMaxSplit; ++sp)
-                        if (sp < nsplit) part[sp] = *reinterpret_cast<const float4*>(src + (size_t)sp * rmax * kStagePitch);
+                        if (sp < nsplit) part[sp] = ld_dsmem_f4(stage_base + off, (uint32_t)sp);
                     acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                     for (int sp = 0; sp < kMaxSplit; ++sp)
@@ -462,8 +433,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
             }
         }
         if (threadIdx.x == 64) trace_stamp(p, 8);                  // reduced + stored
-        // no second cluster barrier: all pushes into this CTA's memory completed before the barrier above, and nothing
-        // reads a peer's memory afterwards
+        if (nsplit > 1) cluster_sync();                      // peers may still be reading this CTA's tile
+        if (threadIdx.x == 64) trace_stamp(p, 9);                  // cluster barrier 2 passed
     }
     tc_fence_before();
     __syncthreads();
@@ -544,23 +515,13 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     const int kb_per_cta = ((total_kb + nsplit - 1) / nsplit);
     p.stages = kb_per_cta < C::kStages ? (kb_per_cta < 2 ? 2 : kb_per_cta) : C::kStages;
-    size_t pipe_bytes, xchg_bytes = 0;
-    if (nsplit > 1) {
-        // dedicated exchange region: [nsplit sources][rows owned][BN + 4] floats; 3 pipeline slots keep the CTA small
-        // enough for two per SM, so the next kernel's prologue (programmatic dependent launch) can overlap this one
-        if (p.stages > 3) p.stages = 3;
-        const int rmax = (BM + nsplit - 1) / nsplit;
-        xchg_bytes = (size_t)nsplit * rmax * (BN + 4) * sizeof(float);
+    size_t pipe_bytes = (size_t)p.stages * C::kStageBytes;
+    const size_t stage_tile = (size_t)BM * (BN + 4) * sizeof(float);          // staged epilogue overlays the pipeline
+    if (p.staged && pipe_bytes < stage_tile) {
+        p.stages = (int)((stage_tile + C::kStageBytes - 1) / C::kStageBytes);  // barriers sit after the last slot
         pipe_bytes = (size_t)p.stages * C::kStageBytes;
-    } else {
-        pipe_bytes = (size_t)p.stages * C::kStageBytes;
-        const size_t stage_tile = (size_t)BM * (BN + 4) * sizeof(float);      // staged epilogue overlays the pipeline
-        if (p.staged && pipe_bytes < stage_tile) {
-            p.stages = (int)((stage_tile + C::kStageBytes - 1) / C::kStageBytes);  // barriers sit after the last slot
-            pipe_bytes = (size_t)p.stages * C::kStageBytes;
-        }
     }
-    const size_t smem_bytes = pipe_bytes + 256 + xchg_bytes + 1024;
+    const size_t smem_bytes = pipe_bytes + 1024 + 256;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit);
     cfg.blockDim = dim3(kThreads);
