@@ -80,7 +80,7 @@ class FusedStep:
         lay, total = model.layout()
         self._layer_span = [(lay[l][0], lay[l + 1][0] if l + 1 < len(lay) else total) for l in range(len(lay))]
         self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
-        self._wgrad_streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+        self._wgrad_stream = torch.cuda.Stream(device=dev)
         self._bufs = {}
         self._graphs = {}
         self._calls = {}
@@ -144,7 +144,9 @@ class FusedStep:
         main = torch.cuda.current_stream()
         # second stream only for the tensor-core engine: its small-batch kernels leave most SMs idle; the FFMA engine's
         # kernels fill the GPU and only slow each other down (measured 7.1 vs 5.4 ms/step)
-        sides = self._wgrad_streams if eng == _C.BF16 else [main]
+        # (two side streams were measured no better than one; at large batch both contractions fill the GPU and
+        # concurrency only disturbs L2 locality, so the second stream is a small-batch device)
+        sides = [self._wgrad_stream] if (eng == _C.BF16 and B <= 1024) else [main]
         wdone = [None] * L
         bucket_hi = None
         for l in range(L - 1, -1, -1):
