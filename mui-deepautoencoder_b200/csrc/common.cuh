@@ -90,35 +90,6 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
-// 256-bit global accesses with an L2 eviction priority (sm_100: the L2 hints exist only on 32-byte accesses).
-//   evict_first: streamed once (optimizer state);  evict_last: will be re-read soon (gradients between the norm and the
-//   update, the bf16 weight shadow the next forward pass reads).
-struct f8 { float v[8]; };
-__device__ __forceinline__ f8 ldg256_evict_first(const float* p) {
-    f8 r;
-    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ f8 ldg256_evict_last(const float* p) {
-    f8 r;
-    asm volatile("ld.global.L1::no_allocate.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
-                 : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void stg256_evict_first(float* p, const f8& r) {
-    asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r.v[0]),
-                 "f"(r.v[1]), "f"(r.v[2]), "f"(r.v[3]), "f"(r.v[4]), "f"(r.v[5]), "f"(r.v[6]), "f"(r.v[7])
-                 : "memory");
-}
-__device__ __forceinline__ void stg256_evict_last_u32(void* p, const uint32_t (&r)[8]) {
-    asm volatile("st.global.L2::evict_last.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]),
-                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-                 : "memory");
-}
-
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

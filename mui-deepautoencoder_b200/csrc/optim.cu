@@ -144,34 +144,23 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(float* __restrict__
     namespace cg = cooperative_groups;
     __shared__ double scratch[32];
     __shared__ float s_coef;
-    const int64_t n8 = n >> 3, n16 = n >> 4;
+    const int64_t n4 = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    // ---- phase 1: ||g||^2.  256-bit loads, L2 evict_last: phase 2 re-reads g from the 126 MB L2 -------------------------
     {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-        int64_t e = tid;
-        for (; e + stride < n8; e += 2 * stride) {
-            const f8 x = ldg256_evict_last(g + 8 * e);
-            const f8 y = ldg256_evict_last(g + 8 * (e + stride));
-#pragma unroll
-            for (int j = 0; j < 8; j += 4) {
-                s0 = fmaf(x.v[j], x.v[j], s0); s1 = fmaf(x.v[j + 1], x.v[j + 1], s1);
-                s2 = fmaf(x.v[j + 2], x.v[j + 2], s2); s3 = fmaf(x.v[j + 3], x.v[j + 3], s3);
-                s0 = fmaf(y.v[j], y.v[j], s0); s1 = fmaf(y.v[j + 1], y.v[j + 1], s1);
-                s2 = fmaf(y.v[j + 2], y.v[j + 2], s2); s3 = fmaf(y.v[j + 3], y.v[j + 3], s3);
-            }
+        int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; e + stride < n4; e += 2 * stride) {
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(g) + e);
+            const float4 y = __ldcg(reinterpret_cast<const float4*>(g) + e + stride);
+            s0 = fmaf(x.x, x.x, s0); s1 = fmaf(x.y, x.y, s1); s2 = fmaf(x.z, x.z, s2); s3 = fmaf(x.w, x.w, s3);
+            s0 = fmaf(y.x, y.x, s0); s1 = fmaf(y.y, y.y, s1); s2 = fmaf(y.z, y.z, s2); s3 = fmaf(y.w, y.w, s3);
         }
-        for (; e < n8; e += stride) {
-            const f8 x = ldg256_evict_last(g + 8 * e);
-#pragma unroll
-            for (int j = 0; j < 8; j += 4) {
-                s0 = fmaf(x.v[j], x.v[j], s0); s1 = fmaf(x.v[j + 1], x.v[j + 1], s1);
-                s2 = fmaf(x.v[j + 2], x.v[j + 2], s2); s3 = fmaf(x.v[j + 3], x.v[j + 3], s3);
-            }
+        for (; e < n4; e += stride) {
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(g) + e);
+            s0 = fmaf(x.x, x.x, s0); s1 = fmaf(x.y, x.y, s1); s2 = fmaf(x.z, x.z, s2); s3 = fmaf(x.w, x.w, s3);
         }
-        if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
-            const float x = g[(n8 << 3) + threadIdx.x];
+        if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+            const float x = g[(n4 << 2) + threadIdx.x];
             s0 = fmaf(x, x, s0);
         }
         const double b = block_sum<double>((double)((s0 + s1) + (s2 + s3)), scratch);
@@ -196,38 +185,31 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(float* __restrict__
         a.bc2_sqrt = (float)sqrt(1.0 - pow(a.beta2_d, t));
         a.neg_step = (float)(-(a.lr_d / (1.0 - pow(a.beta1_d, t))));
     }
-    // ---- phase 2: update.  16 elements per thread: eight 256-bit loads in flight; p/m/v/g stream through L2 as
-    //      evict_first, the bf16 shadow is stored evict_last so the next forward pass finds the weights in L2 ------------------
-    for (int64_t e = tid; e < n16; e += stride) {
-        f8 pv[2], gv[2], mv[2], vv[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            pv[h] = ldg256_evict_first(p + 16 * e + 8 * h);
-            gv[h] = ldg256_evict_first(g + 16 * e + 8 * h);
-            mv[h] = ldg256_evict_first(m + 16 * e + 8 * h);
-            vv[h] = ldg256_evict_first(v + 16 * e + 8 * h);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += stride) {
+        float4 pv = *reinterpret_cast<const float4*>(p + 4 * e);
+        const float4 gv = __ldcg(reinterpret_cast<const float4*>(g) + e);
+        float4 mv = *reinterpret_cast<const float4*>(m + 4 * e);
+        float4 vv = *reinterpret_cast<const float4*>(v + 4 * e);
+        adam_one(pv.x, gv.x, mv.x, vv.x, a, coef);
+        adam_one(pv.y, gv.y, mv.y, vv.y, a, coef);
+        adam_one(pv.z, gv.z, mv.z, vv.z, a, coef);
+        adam_one(pv.w, gv.w, mv.w, vv.w, a, coef);
+        *reinterpret_cast<float4*>(p + 4 * e) = pv;
+        *reinterpret_cast<float4*>(m + 4 * e) = mv;
+        *reinterpret_cast<float4*>(v + 4 * e) = vv;
+        if (pb) {
+            uint2 q;
+            q.x = pack_bf16x2(pv.x, pv.y);
+            q.y = pack_bf16x2(pv.z, pv.w);
+            *reinterpret_cast<uint2*>(pb + 4 * e) = q;
         }
-        uint32_t sh[8];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) adam_one(pv[h].v[j], gv[h].v[j], mv[h].v[j], vv[h].v[j], a, coef);
-            stg256_evict_first(p + 16 * e + 8 * h, pv[h]);
-            stg256_evict_first(m + 16 * e + 8 * h, mv[h]);
-            stg256_evict_first(v + 16 * e + 8 * h, vv[h]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) sh[4 * h + j] = pack_bf16x2(pv[h].v[2 * j], pv[h].v[2 * j + 1]);
-        }
-        if (pb) stg256_evict_last_u32(pb + 16 * e, sh);
     }
-    // tail (n % 16 elements), scalar, block 0
-    if (blockIdx.x == 0) {
-        for (int64_t i = (n16 << 4) + threadIdx.x; i < n; i += blockDim.x) {
-            float pv = p[i], mv = m[i], vv = v[i];
-            adam_one(pv, g[i], mv, vv, a, coef);
-            p[i] = pv; m[i] = mv; v[i] = vv;
-            if (pb) pb[i] = __float2bfloat16_rn(pv);
-        }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (n4 << 2) + threadIdx.x;
+        float pv = p[i], mv = m[i], vv = v[i];
+        adam_one(pv, g[i], mv, vv, a, coef);
+        p[i] = pv; m[i] = mv; v[i] = vv;
+        if (pb) pb[i] = __float2bfloat16_rn(pv);
     }
 }
 
@@ -315,8 +297,8 @@ int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, flo
     CODAE_REQUIRE(ctx, ctx && p && g && m && v && sqnorm_out && workspace && n >= 0 && (step >= 1 || step_dev),
                   "codae_clip_adam_step: bad argument");
     CODAE_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-                         reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(p_bf16)) & 31) == 0,
-                  "codae_clip_adam_step: buffers must be 32-byte aligned (256-bit accesses)");
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
+                  "codae_clip_adam_step: buffers must be 16-byte aligned");
     if (ws_bytes < sizeof(NormWs))
         return codae_fail(ctx, CODAE_ENOMEM, "codae_clip_adam_step: workspace %zu < %zu bytes", ws_bytes, sizeof(NormWs));
     if (step < 1) step = 1;
@@ -344,7 +326,7 @@ int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, flo
             return codae_fail(ctx, CODAE_ECUDA, "codae_clip_adam_step: occupancy query failed");
         }
     }
-    int grid = grid_for(ctx, n >> 4, 1);
+    int grid = grid_for(ctx, n >> 2, 2);
     if (grid > max_blocks_per_sm * ctx->sm_count) grid = max_blocks_per_sm * ctx->sm_count;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
