@@ -176,6 +176,8 @@ def main():
     ap.add_argument("--no-scoring", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fp32", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="A/B: launch without programmatic dependent launch")
+    ap.add_argument("--no-splitk", action="store_true", help="A/B: single-pass small-batch contractions")
     ap.add_argument("--catalog", type=int, default=10_000_000)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -217,6 +219,10 @@ def main():
     from codae.tool import Corrupter, FusedStep
     from codae.tool.inference import ComplementarityScorer, shard_rows
 
+    if args.no_pdl:
+        _C.set_option(dev, _C.OPT_PDL, 0)
+    if args.no_splitk:
+        _C.set_option(dev, _C.OPT_SPLITK, 0)
     pk = peaks()
     B, K, Wm = w["B"], args.steps, args.warmup
     torch.manual_seed(w["seed"])
