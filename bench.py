@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--no-fp32", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch without programmatic dependent launch")
     ap.add_argument("--no-splitk", action="store_true", help="A/B: single-pass small-batch contractions")
+    ap.add_argument("--pdl-backward", action="store_true", help="A/B: keep programmatic dependent launch in the backward pass")
     ap.add_argument("--catalog", type=int, default=10_000_000)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -236,7 +237,7 @@ def main():
     model.to(dev)
     cor = Corrupter(w["N"], ds.arch, w["k_max"], dev, seed=w["seed"])
     fs = FusedStep(model, cor, data, lr=w["lr"], weight_decay=w["wd"], clip=w["clip"], world_size=world,
-                   use_graph=not args.no_graph)
+                   use_graph=not args.no_graph, pdl_backward=args.pdl_backward)
     rng = np.random.RandomState(w["seed"] + rank)
     nb = Wm + K
     batches = torch.from_numpy(rng.randint(0, w["N"], size=(nb, B))).to(dev)

@@ -103,10 +103,18 @@ def ctx(device=None):
 OPT_SPLITK, OPT_PDL = 0, 1
 
 
+_options = {}
+
+
 def set_option(device, option, value):
     """Tuning switches of the library (cluster split-K, programmatic dependent launch); both default on."""
     c = ctx(device)
     check(lib().codae_ctx_set_option(c, option, 1 if value else 0), c)
+    _options[(torch.device(device).index or 0, option)] = 1 if value else 0
+
+
+def get_option_cached(device, option):
+    return _options.get((torch.device(device).index or 0, option), 1)
 
 
 def set_splitk(device, enabled):
