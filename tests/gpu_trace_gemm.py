@@ -79,4 +79,39 @@ for split in (1, 0):
             i, e - int(t[i - 1][0]), " ".join("%s=%d" % (names2[j], int(t[i][j]) - e) for j in (2, 3, 5, 8, 10, 11) if int(t[i][j])),
             (int(t[i + 1][0]) - int(t[i][11])) if i + 1 < R else "-"), flush=True)
 _C.set_splitk(dev, True)
+
+# ---- two streams inside a graph: dgrad chain on the capture stream, wgrad on a side stream (the backward pass) ----
+side = torch.cuda.Stream(device=dev)
+gb = [torch.randn(M, ld, device=dev).to(bf) for _ in range(3)]
+dWs = [torch.zeros(N, ld, device=dev) for _ in range(R)]
+buf2 = torch.zeros(2 * R * 16, dtype=torch.int64, device=dev)
+
+
+def backward_like():
+    main = torch.cuda.current_stream()
+    for i in range(R):
+        ev = torch.cuda.Event(); ev.record(main); side.wait_event(ev)
+        with torch.cuda.stream(side):
+            lib.codae_debug_set_trace(ctypes.c_void_p(buf2.data_ptr() + 128 * (2 * i)))
+            _C.linear_wgrad(gb[i % 3][:, :N], X[:, :K], dWs[i][:, :K], None, M, N, K, _C.BF16)
+        lib.codae_debug_set_trace(ctypes.c_void_p(buf2.data_ptr() + 128 * (2 * i + 1)))
+        _C.linear_dgrad(gb[i % 3][:, :N], W[:, :1536], X[:, :1536], gb[(i + 1) % 3], M, N, 1536, _C.BF16)
+    lib.codae_debug_set_trace(None)
+    main.wait_stream(side)
+
+
+backward_like(); torch.cuda.synchronize()
+gr2 = torch.cuda.CUDAGraph()
+with torch.cuda.graph(gr2):
+    backward_like()
+for _ in range(3):
+    buf2.zero_(); gr2.replay()
+torch.cuda.synchronize()
+t = buf2.cpu().view(2 * R, 16)
+t0 = int(t[1][0])
+print("two-stream backward inside a graph (ns relative to the first dgrad entry): entry / pdl_wait / last exit")
+for i in range(4, 9):
+    w, d = t[2 * i], t[2 * i + 1]
+    print("   layer %d: wgrad %7d %7d %7d | dgrad %7d %7d %7d" % (i, int(w[0]) - t0, int(w[2]) - t0, int(w[11]) - t0,
+                                                               int(d[0]) - t0, int(d[2]) - t0, int(d[11]) - t0), flush=True)
 print("trace done")
