@@ -178,7 +178,6 @@ def main():
     ap.add_argument("--no-fp32", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch without programmatic dependent launch")
     ap.add_argument("--no-splitk", action="store_true", help="A/B: single-pass small-batch contractions")
-    ap.add_argument("--pdl-backward", action="store_true", help="A/B: keep programmatic dependent launch in the backward pass")
     ap.add_argument("--catalog", type=int, default=10_000_000)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -237,7 +236,7 @@ def main():
     model.to(dev)
     cor = Corrupter(w["N"], ds.arch, w["k_max"], dev, seed=w["seed"])
     fs = FusedStep(model, cor, data, lr=w["lr"], weight_decay=w["wd"], clip=w["clip"], world_size=world,
-                   use_graph=not args.no_graph, pdl_backward=args.pdl_backward)
+                   use_graph=not args.no_graph)
     rng = np.random.RandomState(w["seed"] + rank)
     nb = Wm + K
     batches = torch.from_numpy(rng.randint(0, w["N"], size=(nb, B))).to(dev)
@@ -388,8 +387,8 @@ def fs_dtype(dtype, model):
 
 def profile_step(fs, idx, B, world):
     """Per-kernel-group durations and rooflines.  One eager step is recorded (which ABI calls, with which arguments);
-    every group is then replayed R times back to back between ONE CUDA-event pair on the launching stream, so a
-    group's time is GPU time of exactly its launches (no host launch gaps).  Rooflines use ALGORITHMIC bytes / flops
+    every group is then captured R times into one CUDA graph and replayed between ONE CUDA-event pair on the launching
+    stream, so a group's time is GPU time of exactly its launches (no host launch gaps).  Rooflines use ALGORITHMIC bytes / flops
      against the measured peaks."""
     from codae import _C
     pk = peaks()
@@ -424,15 +423,24 @@ def profile_step(fs, idx, B, world):
             continue
         for a, k in calls[n]:
             orig[n](*a, **k)
+        torch.cuda.synchronize()
+        # R repetitions of the group captured into ONE CUDA graph: GPU time without host launch gaps (an eager replay of
+        # 10 us kernels through ctypes is host bound)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for _ in range(R):
+                for a, k in calls[n]:
+                    orig[n](*a, **k)
+        gr.replay()
+        torch.cuda.synchronize()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
-        for _ in range(R):
-            for a, k in calls[n]:
-                orig[n](*a, **k)
+        gr.replay()
         s1.record()
         torch.cuda.synchronize()
         ms = s0.elapsed_time(s1) / R
         kernels[n] = {"ms_per_step": ms, "launches_per_step": len(calls[n]), "us_per_launch": 1e3 * ms / len(calls[n])}
+        del gr
     step_ms = sum(k["ms_per_step"] for k in kernels.values())
     for k in kernels.values():
         k["share"] = k["ms_per_step"] / step_ms

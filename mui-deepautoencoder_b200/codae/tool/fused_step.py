@@ -30,7 +30,7 @@ class FusedStep:
 
     def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True,
-                 fused_clip_adam=True, pdl_backward=False):
+                 fused_clip_adam=True):
         """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
         tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
         {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
@@ -47,7 +47,6 @@ class FusedStep:
         self.mixed = mixed
         self.overlap_allreduce = overlap_allreduce
         self.fused_clip_adam = fused_clip_adam
-        self.pdl_backward = pdl_backward
         dev = model.flat.device
         self.dev = dev
         self.io = model.dims[0][0]
@@ -143,11 +142,6 @@ class FusedStep:
         if overlap_comm:
             import torch.distributed as dist
         main = torch.cuda.current_stream()
-        pdl_off = (not self.pdl_backward) and eng == _C.BF16 and B <= 1024 and _C.get_option_cached(self.dev, _C.OPT_PDL)
-        if pdl_off:
-            # a programmatic dependent is resident (parked in griddepcontrol.wait) while its predecessor runs: on the
-            # compute stream that takes exactly the SM slots the concurrent weight-gradient kernel needs
-            _C.set_option(self.dev, _C.OPT_PDL, 0)
         # second stream only for the tensor-core engine: its small-batch kernels leave most SMs idle; the FFMA engine's
         # kernels fill the GPU and only slow each other down (measured 7.1 vs 5.4 ms/step)
         # (two side streams were measured no better than one; at large batch both contractions fill the GPU and
@@ -188,8 +182,6 @@ class FusedStep:
         for side in sides:
             if side is not main:
                 main.wait_stream(side)
-        if pdl_off:
-            _C.set_option(self.dev, _C.OPT_PDL, 1)
         if overlap_comm:
             main.wait_stream(self._comm_stream)
         elif self.world_size > 1:

@@ -12,10 +12,7 @@ namespace {
 constexpr int kWarps = 8;                 // warps per CTA
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxK = 128;
-constexpr int kSlots = kMaxK / 32;        // list entries per lane
 constexpr int64_t kEmptyIdx = 0x7fffffffffffffffLL;
-
-struct Entry { float s; int64_t i; };
 
 // "a is strictly better than b" under the total order; sqerr: smaller score first, cosine: larger first.
 template <int METRIC>
