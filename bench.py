@@ -178,6 +178,7 @@ def main():
     ap.add_argument("--no-fp32", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch without programmatic dependent launch")
     ap.add_argument("--no-splitk", action="store_true", help="A/B: single-pass small-batch contractions")
+    ap.add_argument("--no-persistent", action="store_true", help="A/B: one tile per CTA for the large contractions")
     ap.add_argument("--catalog", type=int, default=10_000_000)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -223,6 +224,8 @@ def main():
         _C.set_option(dev, _C.OPT_PDL, 0)
     if args.no_splitk:
         _C.set_option(dev, _C.OPT_SPLITK, 0)
+    if args.no_persistent:
+        _C.set_option(dev, _C.OPT_PERSISTENT, 0)
     pk = peaks()
     B, K, Wm = w["B"], args.steps, args.warmup
     torch.manual_seed(w["seed"])

@@ -52,8 +52,10 @@ int codae_ctx_sm_count(const codae_ctx* ctx);
  *                     embedding.yaml / modanet) spread their k-blocks over a thread-block cluster and reduce the partial
  *                     tiles through distributed shared memory, in rank order (bitwise reproducible);
  *   CODAE_OPT_PDL     training-step kernels are launched as programmatic dependents: their prologue overlaps the tail
- *                     of the previous kernel and they wait (griddepcontrol.wait) before touching global memory. */
-enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1 };
+ *                     of the previous kernel and they wait (griddepcontrol.wait) before touching global memory;
+ *   CODAE_OPT_PERSISTENT  contractions with more than 2 output tiles per SM run one persistent CTA per SM with the
+ *                     accumulator double-buffered in TMEM, so a tile's epilogue overlaps the next tile's MMAs. */
+enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1, CODAE_OPT_PERSISTENT = 2 };
 int codae_ctx_set_option(codae_ctx* ctx, int option, int value);
 /* Which engine codae_linear_* will use for (dtype, M, N, K). */
 int codae_linear_engine(const codae_ctx* ctx, int dtype, int M, int N, int K);

@@ -100,7 +100,7 @@ def ctx(device=None):
     return c
 
 
-OPT_SPLITK, OPT_PDL = 0, 1
+OPT_SPLITK, OPT_PDL, OPT_PERSISTENT = 0, 1, 2
 
 
 _options = {}

@@ -18,6 +18,7 @@ struct codae_ctx {
     char err[512];
     void* encode_tiled;  // cuTensorMapEncodeTiled, resolved through cudaGetDriverEntryPoint
     int splitk;          // 1: small-batch contractions may use cluster split-K (default on)
+    int persistent;      // 1: large contractions use the persistent, TMEM-double-buffered kernel (default on)
     int pdl;             // 1: training-step kernels are launched with programmatic dependent launch (default on)
     std::mutex mu;
 };

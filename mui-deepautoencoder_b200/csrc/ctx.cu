@@ -59,6 +59,7 @@ int codae_ctx_create(int device, codae_ctx** out) {
     c->encode_tiled = nullptr;
     c->splitk = 1;
     c->pdl = 1;
+    c->persistent = 1;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -81,6 +82,7 @@ int codae_ctx_set_option(codae_ctx* ctx, int option, int value) {
     if (!ctx) return codae_fail(nullptr, CODAE_EINVAL, "codae_ctx_set_option: ctx is NULL");
     if (option == CODAE_OPT_SPLITK) ctx->splitk = value ? 1 : 0;
     else if (option == CODAE_OPT_PDL) ctx->pdl = value ? 1 : 0;
+    else if (option == CODAE_OPT_PERSISTENT) ctx->persistent = value ? 1 : 0;
     else return codae_fail(ctx, CODAE_EINVAL, "codae_ctx_set_option: unknown option %d", option);
     return CODAE_OK;
 }

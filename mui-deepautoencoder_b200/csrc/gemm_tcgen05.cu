@@ -69,6 +69,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
@@ -450,6 +453,143 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     }
 }
 
+// ---- persistent variant for large problems (tiles > 2 x SMs): one CTA per SM walks output tiles t, t + grid, ... -----------
+// The accumulator is double-buffered in TMEM (2 x BN columns): while the epilogue warps drain tile i (tcgen05.ld, fused
+// epilogue, stores), the MMA warp already accumulates tile i+1 and the producer keeps the shared-memory ring full across
+// tile boundaries.  Tiles are walked m-fastest so that concurrently running CTAs share the same weight tile in L2.
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tma_a,
+                                                                           const __grid_constant__ CUtensorMap tma_b,
+                                                                           const Params p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    constexpr int kS = C::kStages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kS * C::kStageBytes);
+    uint64_t* empty_bar = full_bar + kS;
+    uint64_t* tmem_full_bar = empty_bar + kS;          // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    const int total_tiles = tiles_m * tiles_n;
+    const int num_kb = (p.K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+        for (int s = 0; s < kS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===== TMA producer: the ring index and phase run on across tiles =====
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+                const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+                for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == kS ? 0 : s + 1), ph ^= (s == 0)) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* a_dst = smem + s * C::kStageBytes;
+                    uint8_t* b_dst = a_dst + kATileBytes;
+                    mbar_expect_tx(&full_bar[s], C::kStageBytes);
+                    const int k0 = kb * BK;
+                    if (p.a_kmajor) {
+                        tma_load_2d(&tma_a, &full_bar[s], a_dst, k0, m0);
+                    } else {
+                        tma_load_2d(&tma_a, &full_bar[s], a_dst, m0, k0);
+                        tma_load_2d(&tma_a, &full_bar[s], a_dst + 8192, m0 + 64, k0);
+                    }
+                    if (p.b_kmajor) {
+                        tma_load_2d(&tma_b, &full_bar[s], b_dst, k0, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tma_b, &full_bar[s], b_dst + j * 8192, n0 + 64 * j, k0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: tile i accumulates into TMEM buffer i & 1 =====
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(BN, p.a_kmajor != 0, p.b_kmajor != 0);
+            const uint32_t a_adv = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
+            const uint32_t b_adv = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
+            int s = 0;
+            uint32_t ph = 0;
+            int it = 0;
+            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_ph = (it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);          // epilogue has drained this buffer (first use: free)
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == kS ? 0 : s + 1), ph ^= (s == 0)) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
+                    const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        umma_bf16(d_tmem, make_desc(a_addr + k * a_adv, p.a_kmajor != 0),
+                                  make_desc(b_addr + k * b_adv, p.b_kmajor != 0), idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tmem_full_bar[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue warps: drain buffer i & 1 while the MMA warp fills the other one =====
+        const int q = warp & 3;
+        int it = 0;
+        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_ph = (it >> 1) & 1;
+            const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+            mbar_wait(&tmem_full_bar[acc], acc_ph);
+            tc_fence_after();
+            const int row = m0 + q * 32 + lane;
+            const bool row_ok = row < p.M;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
+                if (c == BN / 32 - 1) {
+                    // every column of this buffer is in registers: hand it back to the MMA warp before the last stores
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                }
+                const int col0 = n0 + c * 32;
+                if (!row_ok || col0 >= p.N) continue;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                store_chunk<32>(p, row, col0, f);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+
 unsigned long long* g_trace_buf = nullptr;   // set through codae_debug_set_trace (debugging hook, not part of the ABI)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -507,6 +647,21 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     // (measured: the direct epilogue is faster for the 4096-wide weight gradients, 247 vs 261 us)
     p.trace = g_trace_buf;
     p.staged = (nsplit > 1 || (g.c_dtype == CODAE_F32 && tiles <= 2 * ctx->sm_count)) ? 1 : 0;
+    if (nsplit == 1 && !p.staged && ctx->persistent && tiles > 2 * ctx->sm_count) {
+        static bool pattr_set = false;
+        if (!pattr_set) {
+            cudaError_t e = cudaFuncSetAttribute(tc05_gemm_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
+            if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaFuncSetAttribute(smem=%u): %s", C::kSmemBytes, cudaGetErrorString(e));
+            pattr_set = true;
+        }
+        p.stages = C::kStages;
+        cudaError_t le = launch_pdl(ctx, tc05_gemm_persistent_kernel<BN>, dim3(ctx->sm_count), dim3(kThreads), C::kSmemBytes, s, ma, mb, p);
+        if (le != cudaSuccess) {
+            cudaGetLastError();
+            return codae_fail(ctx, CODAE_ECUDA, "tc05_gemm_persistent_kernel<%d> launch: %s", BN, cudaGetErrorString(le));
+        }
+        return codae_check_launch(ctx, "tc05_gemm_persistent_kernel");
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(tc05_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);

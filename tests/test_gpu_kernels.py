@@ -288,7 +288,9 @@ def _bf(t):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 256, 128), (128, 1536, 1536), (32, 1536, 1536), (200, 192, 192),
-                                   (33, 600, 1064), (1, 128, 832), (512, 4096, 4096), (300, 328, 72)])
+                                   (33, 600, 1064), (1, 128, 832), (512, 4096, 4096), (300, 328, 72),
+                                   # > 2 tiles per SM: the persistent, TMEM-double-buffered kernel (fwd / dgrad / wgrad resp.)
+                                   (4096, 4096, 256), (4000, 256, 4096), (256, 4096, 4000)])
 def test_linear_tcgen05_engine(C, dev, M, N, K):
     """bf16 tensor-core engine (tcgen05 + TMEM + TMA) vs an fp64 product of the same bf16-rounded operands.
     Operands are exactly representable in bf16, so the only difference is fp32 accumulation order: tol 1e-4 of
@@ -352,6 +354,29 @@ def test_split_k_is_deterministic_and_matches_single_pass(C, dev):
     assert rel(outs[0][1].cpu().numpy(), dX1.cpu().numpy()) < 1e-5
     want = torch.relu(X.double().cpu().mm(W.double().cpu().t()) + b.double().cpu())
     assert rel(outs[0][0].float().cpu().numpy(), want.numpy()) < 1e-2
+
+
+def test_persistent_kernel_equals_one_tile_per_cta(C, dev):
+    """Same tiles, same k order: the persistent kernel must reproduce the one-tile-per-CTA kernel bit for bit."""
+    torch.manual_seed(9)
+    M, N, K = 4096, 4096, 320
+    bf = torch.bfloat16
+    X, W = torch.randn(M, K).to(dev, bf), (torch.randn(N, K) / 16).to(dev, bf)
+    b = torch.randn(N, device=dev)
+    out = {}
+    for on in (1, 0):
+        C.set_option(dev, C.OPT_PERSISTENT, on)
+        try:
+            Y = torch.zeros(M, N, device=dev, dtype=bf)
+            Yf = torch.zeros(M, N, device=dev)
+            C.linear_fwd(X, W, b, Y, M, N, K, C.ACT_RELU, C.BF16)
+            C.linear_fwd(X, W, None, Yf, M, N, K, C.ACT_NONE, C.BF16)
+            out[on] = (Y.clone(), Yf.clone())
+        finally:
+            C.set_option(dev, C.OPT_PERSISTENT, 1)
+    assert torch.equal(out[1][0].view(torch.int16), out[0][0].view(torch.int16)) and torch.equal(out[1][1], out[0][1])
+    want = X.double().cpu().mm(W.double().cpu().t())
+    assert rel(out[1][1].cpu().numpy(), want.numpy()) < 1e-4
 
 
 def test_mixed_loss_and_monitor(C, dev):

@@ -11,9 +11,10 @@ run_pytest inference tests/test_gpu_inference.py 8
 echo "== bench default"; timeout -s KILL 600 python bench.py --no-cpu > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err; echo "rc=$?"; tail -3 gpurun_out/bench_default.err
 echo "== bench default, split-K off"; timeout -s KILL 600 python bench.py --no-cpu --no-scoring --no-fp32 --no-splitk > gpurun_out/bench_nosplit.json 2> gpurun_out/bench_nosplit.err; echo "rc=$?"; tail -3 gpurun_out/bench_nosplit.err
 echo "== bench polyvore"; timeout -s KILL 600 python bench.py --workload polyvore --steps 10 --warmup 3 --no-cpu --no-scoring > gpurun_out/bench_polyvore.json 2> gpurun_out/bench_polyvore.err; echo "rc=$?"; tail -3 gpurun_out/bench_polyvore.err
+echo "== bench polyvore, one tile per CTA"; timeout -s KILL 600 python bench.py --workload polyvore --steps 10 --warmup 3 --no-cpu --no-scoring --no-persistent > gpurun_out/bench_polyvore_np.json 2> gpurun_out/bench_polyvore_np.err; echo "rc=$?"; tail -3 gpurun_out/bench_polyvore_np.err
 python - <<'PY'
 import json
-for f in ["bench_default.json","bench_nosplit.json","bench_polyvore.json"]:
+for f in ["bench_default.json","bench_nosplit.json","bench_polyvore.json","bench_polyvore_np.json"]:
     try: d=json.loads(open("gpurun_out/"+f).read().strip().splitlines()[-1])
     except Exception as e: print(f,"ERR",e); continue
     print("==",f,"value %.0f ms/step %.4f e2e %.0f"%(d["value"],d["ms_per_step"],d["e2e"]["value"]), "roofline", d["roofline"]["kernel"], "%.3f"%d["roofline"]["frac"], d["roofline"]["bound"])
