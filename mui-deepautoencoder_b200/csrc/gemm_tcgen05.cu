@@ -457,6 +457,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
 // The accumulator is double-buffered in TMEM (2 x BN columns): while the epilogue warps drain tile i (tcgen05.ld, fused
 // epilogue, stores), the MMA warp already accumulates tile i+1 and the producer keeps the shared-memory ring full across
 // tile boundaries.  Tiles are walked m-fastest so that concurrently running CTAs share the same weight tile in L2.
+// Tile order of the persistent kernel: groups of kGroupM row-tiles; inside a group all column-tiles of one row-tile
+// column are adjacent (m fastest).  The ~148 tiles in flight then span kGroupM x ~9 tiles: every operand tile is shared by
+// many concurrent CTAs and the working set (tens of MB) stays in L2.  (Plain m-fastest order re-streamed the whole 67 MB
+// activation matrix for every pair of column tiles: ncu showed 350-530 MB of DRAM reads for 100-135 MB of operands.)
+constexpr int kGroupM = 16;
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& m_idx, int& n_idx) {
+    const int per_group = kGroupM * tiles_n;
+    const int g = t / per_group, r = t - g * per_group;
+    const int gm = min(kGroupM, tiles_m - g * kGroupM);
+    m_idx = g * kGroupM + r % gm;
+    n_idx = r / gm;
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                            const __grid_constant__ CUtensorMap tma_b,
@@ -498,7 +511,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
             int s = 0;
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-                const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+                int m_idx, n_idx;
+                tile_coords(t, tiles_m, tiles_n, m_idx, n_idx);
+                const int m0 = m_idx * BM, n0 = n_idx * BN;
                 for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == kS ? 0 : s + 1), ph ^= (s == 0)) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* a_dst = smem + s * C::kStageBytes;
@@ -523,13 +538,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
     } else if (warp == 1) {
         // ===== MMA issuer: tile i accumulates into TMEM buffer i & 1 =====
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(BN, p.a_kmajor != 0, p.b_kmajor != 0);
             const uint32_t a_adv = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
             const uint32_t b_adv = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
             int s = 0;
             uint32_t ph = 0;
             int it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+                int m_idx, n_idx;
+                tile_coords(t, tiles_m, tiles_n, m_idx, n_idx);
+                // a ragged last column tile (the bias column of the augmented weight gradient: 1 of 256 columns) only
+                // pays for the MMA width it needs (multiples of 16)
+                const int n_eff = min(BN, ((p.N - n_idx * BN) + 15) & ~15);
+                const uint32_t idesc = make_idesc(n_eff, p.a_kmajor != 0, p.b_kmajor != 0);
                 const int acc = it & 1;
                 const uint32_t acc_ph = (it >> 1) & 1;
                 mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);          // epilogue has drained this buffer (first use: free)
@@ -557,16 +577,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_ph = (it >> 1) & 1;
-            const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+            int m_idx, n_idx;
+            tile_coords(t, tiles_m, tiles_n, m_idx, n_idx);
+            const int m0 = m_idx * BM, n0 = n_idx * BN;
             mbar_wait(&tmem_full_bar[acc], acc_ph);
             tc_fence_after();
             const int row = m0 + q * 32 + lane;
             const bool row_ok = row < p.M;
+            const int n_chunks = min(BN / 32, (p.N - n0 + 31) / 32);        // >= 1
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = 0; c < n_chunks; ++c) {
                 uint32_t v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c * 32), v);
-                if (c == BN / 32 - 1) {
+                if (c == n_chunks - 1) {
                     // every column of this buffer is in registers: hand it back to the MMA warp before the last stores
                     tc_fence_before();
                     __syncwarp();

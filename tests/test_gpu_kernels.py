@@ -377,6 +377,27 @@ def test_persistent_kernel_equals_one_tile_per_cta(C, dev):
     assert torch.equal(out[1][0].view(torch.int16), out[0][0].view(torch.int16)) and torch.equal(out[1][1], out[0][1])
     want = X.double().cpu().mm(W.double().cpu().t())
     assert rel(out[1][1].cpu().numpy(), want.numpy()) < 1e-4
+    # weight gradient of an augmented 4096-wide layer: 4097 output columns = 16 full column tiles + one tile that holds
+    # only the bias column (narrow MMA, one epilogue chunk); pitches padded like the product's buffers
+    Mb, Nf, Kf, ld = 256, 4096, 4097, 4160
+    dY = torch.randn(Mb, Nf).to(dev, bf)
+    Xa = torch.zeros(Mb, ld, device=dev, dtype=bf)
+    Xa[:, :4096] = torch.randn(Mb, 4096).to(dev, bf)
+    Xa[:, 4096] = 1
+    res = {}
+    for on in (1, 0):
+        C.set_option(dev, C.OPT_PERSISTENT, on)
+        try:
+            dW = torch.full((Nf, ld), 7.0, device=dev)
+            C.linear_wgrad(dY, Xa[:, :Kf], dW[:, :Kf], None, Mb, Nf, Kf, C.BF16)
+            res[on] = dW.clone()
+        finally:
+            C.set_option(dev, C.OPT_PERSISTENT, 1)
+    assert torch.equal(res[1], res[0])
+    wantw = dY.double().cpu().t().mm(Xa[:, :Kf].double().cpu())
+    assert rel(res[1][:, :Kf].cpu().numpy(), wantw.numpy()) < 1e-4
+    assert rel(res[1][:, 4096].cpu().numpy(), dY.double().cpu().sum(0).numpy()) < 1e-4      # bias gradient column
+    assert float((res[1][:, Kf:] - 7.0).abs().max()) == 0                                  # padding untouched
 
 
 def test_mixed_loss_and_monitor(C, dev):
