@@ -275,25 +275,46 @@ def main():
     for j in range(4):
         host_rows[j].copy_(data[batches[j]].cpu())
         host_tab[j].copy_(table[batches[j]].cpu())
-    st_rows = torch.empty((B, io), dtype=torch.float32, device=dev)
-    st_tab = torch.empty((B, table.shape[1]), dtype=torch.int16, device=dev)
+    # two staging buffers: the host->device copy of step s+1 (copy stream) overlaps the kernels of step s; every step's
+    # copy and every step's loss read-back are inside the timed region
+    st_rows = [torch.empty((B, io), dtype=torch.float32, device=dev) for _ in range(2)]
+    st_tab = [torch.empty((B, table.shape[1]), dtype=torch.int16, device=dev) for _ in range(2)]
     loss_host = torch.zeros(4, dtype=torch.float64).pin_memory()
     Ke = max(10, K // 2)
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def e2e_step(s):
-        st_rows.copy_(host_rows[s % 4], non_blocking=True)
-        st_tab.copy_(host_tab[s % 4], non_blocking=True)
-        fs.step(None, global_batch=B * world, staged=(st_rows, st_tab))
-        loss_host.copy_(fs.acc, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return float(loss_host[3]) / (B * io)
+    def stage(s):
+        j = s % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[j])          # the step that last used this buffer has finished
+            st_rows[j].copy_(host_rows[s % 4], non_blocking=True)
+            st_tab[j].copy_(host_tab[s % 4], non_blocking=True)
+            copied[j].record(copy_stream)
 
-    for s in range(5):
-        e2e_step(s)
+    def e2e_loop(n):
+        main = torch.cuda.current_stream()
+        for j in range(2):
+            consumed[j].record(main)
+        stage(0)
+        last = 0.0
+        for s in range(n):
+            j = s % 2
+            if s + 1 < n:
+                stage(s + 1)
+            main.wait_event(copied[j])
+            fs.step(None, global_batch=B * world, staged=(st_rows[j], st_tab[j]))
+            consumed[j].record(main)
+            loss_host.copy_(fs.acc, non_blocking=True)
+            main.synchronize()                           # the user sees this step's loss before issuing the next step
+            last = float(loss_host[3]) / (B * io)
+        return last
+
+    e2e_loop(6)
     barrier()
     t0 = time.perf_counter()
-    for s in range(Ke):
-        e2e_step(s)
+    e2e_loop(Ke)
     barrier()
     e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
     if world > 1:
