@@ -187,6 +187,13 @@ class FusedStep:
         elif self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+        n += self._enqueue_update()
+        return n
+
+    def _enqueue_update(self):
+        """Step counter + clip + Adam over the flat buffers (after the gradients are final)."""
+        model, eng = self.model, self.eng
+        n = 0
         _C.counter_add(self.step_dev, 1); n += 1
         pb = model.flat_bf16 if eng == _C.BF16 else None
         if self.clip and self.fused_clip_adam:
@@ -200,6 +207,24 @@ class FusedStep:
                          0, self.max_norm if self.clip else -1.0, self.sqnorm if self.clip else None, 1.0, self.step_dev); n += 1
         return n
 
+    def _step_without_samples(self):
+        """This rank holds no sample of the (ragged, last) global batch: contribute zero gradients to the all-reduce and
+        apply the same update as every other rank."""
+        self.gflat.zero_()
+        if self.world_size > 1:
+            import torch.distributed as dist
+            if self.overlap_allreduce:      # same bucket boundaries as the ranks that do have samples
+                L, hi = len(self.model.dims), None
+                for l in range(L - 1, -1, -1):
+                    lo = self._layer_span[l][0]
+                    hi = self._layer_span[l][1] if hi is None else hi
+                    if (hi - lo) * 4 >= self.BUCKET_BYTES or l == 0:
+                        dist.all_reduce(self.gflat[lo:hi], op=dist.ReduceOp.SUM, group=self.pg)
+                        hi = None
+            else:
+                dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
+        self.kernel_launches = self._enqueue_update()
+
     # ---- public API ------------------------------------------------------------------------------------------
     def step(self, batch_idx, run=0, global_batch=None, staged=None):
         """One training step on observations `batch_idx` (int64 CUDA tensor [B]).
@@ -207,6 +232,10 @@ class FusedStep:
         then read the staged rows instead of gathering from the resident dataset."""
         B = int(batch_idx.numel()) if staged is None else int(staged[0].shape[0])
         gb = B * self.world_size if global_batch is None else global_batch
+        if B == 0:
+            self.step_count += 1
+            self._step_without_samples()
+            return
         b = self._buffers(B)
         table = self.corrupter.device_tables()[0]
         if staged is not None:

@@ -305,6 +305,49 @@ def test_pdl_and_splitk_switches_do_not_change_results():
     assert abs(results["on"][0] - results["no_splitk"][0]) <= 1e-3 * abs(results["on"][0])
 
 
+def test_polyvore_shape_step_bf16_vs_oracle():
+    """The largest config's layer shape (4096 wide, k_max=2, bf16) at a batch that takes the persistent, TMEM-double-
+    buffered kernel for all three contractions (B=4096: 512 output tiles): one fused step vs the oracle, 1e-2."""
+    from oracle import codae_oracle as O
+    from oracle.philox import philox_mask_table
+    from codae import _C
+    from codae.dataset import ConcatenatedEmbeddingDataset
+    from codae.model import EmbeddingDenoisingAutoencoder
+    from codae.tool import Corrupter, FusedStep
+    torch.manual_seed(21)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    S, E, N, B = 8, 512, 4096, 4096
+    cats = [torch.randn(N, E).abs() * (torch.rand(N, E) < 0.7) for _ in range(S)]
+    ds = ConcatenatedEmbeddingDataset.from_tensors(cats)
+    model = EmbeddingDenoisingAutoencoder(S * E, S * E, E, 2, 2, False)          # 6 x Linear(4096, 4096)
+    W = [l.weight.detach().clone() for l in model.linears()]
+    b = [l.bias.detach().clone() for l in model.linears()]
+    data_cpu = ds.data.clone()
+    model.set_compute_dtype("bf16")
+    model.to(DEV)
+    ds.to(DEV)
+    cor = Corrupter(N, ds.arch, 2, DEV, seed=7)
+    assert cor.nb_run == 36
+    tbl = torch.from_numpy(philox_mask_table(7, N, 36).astype(np.int64))
+    assert torch.equal(tbl, cor.mask_to_use)
+    fs = FusedStep(model, cor, ds.data, lr=1e-4, weight_decay=1e-2, clip=True)
+    assert fs.eng == _C.BF16
+    idx = torch.randperm(N)[:B]
+    fs.step(idx.to(DEV), run=3)
+    bm, nm, _ = O.binary_masks(ds.arch, 2)
+    _, fmask = O.get_masks(bm, nm, tbl, idx.tolist(), 3, 2)
+    dae = O.OracleDAE(W, b, model.relu, 1e-4, 1e-2, True)
+    r = dae.step_embedding(data_cpu[idx], fmask)
+    assert abs(fs.last_loss(B) - r["loss"]) <= 1e-2 * abs(r["loss"])
+    y = fs._bufs[B]["acts"][-1][:, :S * E]
+    assert rel(y.cpu().numpy(), r["y"].numpy()) < 1e-2
+    assert torch.equal(fs.last_mask_ids(B).cpu().long(), tbl[idx, 3])
+    gg, gw = flat_grads(model), np.concatenate([t.numpy().ravel() for t in r["grads"]])
+    assert float(np.linalg.norm(gg - gw) / np.linalg.norm(gw)) < 2e-2
+    got, want = flat_params(model), np.concatenate([t.numpy().ravel() for t in dae.params()])
+    assert (np.abs(got - want) <= 1e-2 * np.abs(want).max()).mean() > 0.999
+
+
 def test_ragged_last_batch_and_validation_pass():
     """No drop_last in the reference: the last batch is smaller; evaluate() = forward + monitors only."""
     from codae.tool import FusedStep
