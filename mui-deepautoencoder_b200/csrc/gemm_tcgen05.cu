@@ -23,6 +23,10 @@
 // shared memory (ld.shared::cluster) in rank order -- deterministic, no HBM round trip, no atomics.
 // (A push variant -- st.shared::cluster into the owner, one barrier -- was measured slower: 8.1 vs 6.8 us per
 // dependent launch; remote stores cost more than the second barrier saves.)
+//
+// Large problems (more than 2 output tiles per SM) use tc05_gemm_persistent_kernel further down: one CTA per SM walks
+// tiles in L2-friendly groups, the accumulator is double-buffered in TMEM so that the epilogue of tile i overlaps the
+// MMAs of tile i+1, and the shared-memory ring keeps running across tile boundaries.
 #include <cuda.h>
 
 #include "common.cuh"
