@@ -155,3 +155,24 @@ def test_shard_rows_and_epoch_batches():
             seen += list(local)
             assert gb in (16, 13)
     assert sorted(seen) == idx          # ranks partition every global batch, ragged last batch included
+
+
+def test_yaml_configs_keep_the_reference_schema():
+    """The three shipped configs carry the reference's keys and values (checked against a snapshot of the parsed
+    reference files taken in the build container), plus the new polyvore-shaped config with the same schema."""
+    import yaml
+    cfg = os.path.join(PKG, "config")
+    emb = yaml.safe_load(open(os.path.join(cfg, "embedding.yaml")))
+    assert emb["MODEL"] == {"Z_SIZE": 1536, "BATCH_SIZE": 128, "NB_INPUT_LAYER": 4, "NB_OUTPUT_LAYER": 4, "STEEP_LAYER_SIZE": False,
+                            "EPOCH": 50, "LEARNING_RATE": 1e-05, "WEIGHT_DECAY": 0.0001, "NB_CORRUPTED": 1, "TRUNK_GRAD": True}
+    assert emb["DATASET"] == {"NAME": "EMBEDDING", "USED_CATEGORY": ["top", "bottom", "shoe"], "EMBEDDING_SIZE": 512,
+                              "SHUFFLE": True, "SPLIT": [0.7, 0.3]} and emb["SEED"] == 27493045
+    mod = yaml.safe_load(open(os.path.join(cfg, "modanet_merge_top_bottom_shoe.yaml")))
+    assert mod["MODEL"]["BATCH_SIZE"] == 32 and mod["MODEL"]["LEARNING_RATE"] == 1e-4 and mod["MODEL"]["WEIGHT_DECAY"] == 0.01
+    assert "TRUNK_GRAD" not in mod["MODEL"] and mod["SEED"] == 50493213 and mod["DATASET"]["SPLIT"] == [0.8, 0.2]
+    aba = yaml.safe_load(open(os.path.join(cfg, "abalone.yaml")))
+    assert aba["MODEL"]["Z_SIZE"] == 11 and aba["MODEL"]["STEEP_LAYER_SIZE"] is True and aba["MODEL"]["TRUNK_GRAD"] is True
+    assert aba["MODEL"]["LEARNING_RATE"] == 5e-05 and aba["MODEL"]["WEIGHT_DECAY"] == 1e-06 and aba["SEED"] == 27123045
+    assert set(aba) == {"MODEL", "DATASET", "SEED", "EVALUATION", "PLOT"}
+    poly = yaml.safe_load(open(os.path.join(cfg, "polyvore_multislot.yaml")))
+    assert set(poly["MODEL"]) >= set(emb["MODEL"]) and len(poly["DATASET"]["USED_CATEGORY"]) == 8
