@@ -105,3 +105,35 @@ def test_scale_properties_planted_winners():
     # permutation invariance of the selected set: reversed catalog
     s2, i2 = ComplementarityScorer(cat.flip(0).contiguous(), E, "sqerr", k).topk_local(q)
     assert (n - 1 - i2[0]).tolist() == rows.tolist()
+
+
+@pytest.mark.parametrize("bf16", [False, True])
+def test_full_size_catalog_properties(bf16):
+    """BASELINE's inference size: 10 M x 512 (20.5 GB fp32 / 10.2 GB bf16).  Size-independent properties: planted
+    near-copies of the query are returned in order of their planted distance; the sharded sweep (8 contiguous shards +
+    merge) returns the same list as the single sweep; a second sweep returns the same bits."""
+    from codae import _C
+    from codae.tool.inference import ComplementarityScorer, shard_rows
+    n, E, k = 10_000_000, 512, 10
+    g = torch.Generator(device=DEV).manual_seed(11)
+    cat = torch.rand((n, E), generator=g, device=DEV)
+    if bf16:
+        cat = cat.to(torch.bfloat16)
+    q = torch.rand((1, E), generator=g, device=DEV)
+    rows = torch.tensor([9_999_999, 3, 5_000_001, 7_777_777, 1_250_000, 0, 2_500_000, 8_750_001, 6_000_000, 42], device=DEV)
+    for j, r in enumerate(rows.tolist()):
+        cat[r] = (q[0] + 2e-2 * (j + 1)).to(cat.dtype)       # squared error grows with j (well above bf16 rounding)
+    sc = ComplementarityScorer(cat, E, "sqerr", k)
+    s, i = sc.topk_local(q)
+    s, i = s.clone(), i.clone()
+    assert i[0].tolist() == rows.tolist() and torch.all(s[0, 1:] > s[0, :-1])
+    s2, i2 = sc.topk_local(q)
+    assert torch.equal(s2, s) and torch.equal(i2, i)
+    ps, pi = [], []
+    for r in range(8):
+        lo, c = shard_rows(n, 8, r)
+        a, b = ComplementarityScorer(cat[lo:lo + c], E, "sqerr", k, row_offset=lo).topk_local(q)
+        ps.append(a.clone()); pi.append(b.clone())
+    ms, mi = torch.empty_like(s), torch.empty_like(i)
+    _C.topk_merge(torch.stack(ps), torch.stack(pi), _C.METRIC_SQERR, ms, mi)
+    assert torch.equal(mi, i) and torch.equal(ms, s)

@@ -348,6 +348,42 @@ def test_polyvore_shape_step_bf16_vs_oracle():
     assert (np.abs(got - want) <= 1e-2 * np.abs(want).max()).mean() > 0.999
 
 
+def test_full_size_polyvore_gradient_linearity():
+    """BASELINE's largest training config (10 x Linear(4096, 4096), B = 8192 per GPU, k_max = 2, bf16) is too big for the
+    oracle in seconds; size-independent property instead: with the GLOBAL batch size in the loss scale, the gradient of
+    the whole batch equals the sum of the gradients of its two halves (what data parallelism relies on).  lr = 0 keeps
+    the weights fixed between the three steps."""
+    from codae import _C
+    from codae.model import EmbeddingDenoisingAutoencoder
+    from codae.tool import Corrupter, FusedStep
+    torch.manual_seed(31)
+    S, E, N, B = 8, 512, 16384, 8192
+    io = S * E
+    g = torch.Generator(device=DEV).manual_seed(31)
+    data = torch.rand((N, io), generator=g, device=DEV) * (torch.rand((N, io), generator=g, device=DEV) < 0.7)
+    arch = [dict(name=str(i), size=E, type="regression", position=i * E) for i in range(S)]
+    model = EmbeddingDenoisingAutoencoder(io, io, E, 4, 4, False)
+    assert len(model.dims) == 10 and model.nb_parameters() == 167_813_120
+    model.set_compute_dtype("bf16")
+    model.to(DEV)
+    cor = Corrupter(N, arch, 2, DEV, seed=5)
+    fs = FusedStep(model, cor, data, lr=0.0, weight_decay=0.0, clip=True)
+    assert fs.eng == _C.BF16
+    w0 = model.flat.clone()
+    idx = torch.randperm(N, device=DEV)[:B]
+    fs.step(idx, run=1, global_batch=B)
+    g_full, loss_full = fs.gflat.clone(), fs.last_loss(B)
+    fs.step(idx[:B // 2], run=1, global_batch=B)
+    g_a, sum_a = fs.gflat.clone(), float(fs.acc[3].item())
+    fs.step(idx[B // 2:], run=1, global_batch=B)
+    g_b, sum_b = fs.gflat.clone(), float(fs.acc[3].item())
+    assert torch.equal(model.flat, w0)                                   # lr = 0: nothing moved
+    assert abs((sum_a + sum_b) / (B * io) - loss_full) <= 1e-4 * loss_full
+    err = float((g_a + g_b - g_full).norm() / g_full.norm())
+    assert err < 1e-2, err
+    assert bool(torch.isfinite(g_full).all()) and float(g_full.abs().max()) > 0
+
+
 def test_ragged_last_batch_and_validation_pass():
     """No drop_last in the reference: the last batch is smaller; evaluate() = forward + monitors only."""
     from codae.tool import FusedStep
