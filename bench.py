@@ -218,7 +218,7 @@ def main():
     from codae.dataset import ConcatenatedEmbeddingDataset
     from codae.model import EmbeddingDenoisingAutoencoder
     from codae.tool import Corrupter, FusedStep
-    from codae.tool.inference import ComplementarityScorer, shard_rows
+    from codae.tool.inference import ComplementarityScorer, SwapScorer, shard_rows
 
     if args.no_pdl:
         _C.set_option(dev, _C.OPT_PDL, 0)
@@ -380,6 +380,27 @@ def main():
                    "roofline": {"bound": "hbm", "achieved": bytes_per / (k_ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                 "frac": bytes_per / (k_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None,
                                 "kernel": "score_topk_kernel (+merge)", "peak_source": pk["src"]}}
+        # swaps scored by FULL reconstruction (candidate substituted, whole outfit through the DAE): GEMM-bound variant
+        n_sw = min(n_local, 1 << 20)
+        sw = SwapScorer(model, catalog[:n_sw], w["E"], k=10, row_offset=lo, chunk=8192)
+        outfit = torch.rand(io, generator=g, device=dev)
+        for _ in range(2):
+            sw.topk(outfit, 1)
+        barrier()
+        e0.record()
+        for _ in range(3):
+            sw.topk(outfit, 1)
+        e1.record()
+        barrier()
+        sms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+        sw_ms = float(sms.item()) / 3
+        sw_flops = 2.0 * sum(i * o for i, o in model.dims) * n_sw
+        scoring["swap_reconstruction"] = {"metric": "candidate swaps/s (full DAE reconstruction per swap)",
+                                          "value": world * n_sw / (sw_ms / 1e3), "unit": "swaps/s", "swaps_per_rank": n_sw,
+                                          "chunk": 8192, "ms": sw_ms, "engine": fs_dtype(dtype, model),
+                                          "tflops": sw_flops / (sw_ms / 1e3) / 1e12}
         if rank == 0 and not args.no_cpu:
             scoring["cpu_baseline"] = {"value": cpu_scoring(w["E"]), "unit": "scores/s", "cores": os.cpu_count(), "kind": "port",
                                        "sample": "3 x cosine_similarity + topk over 1M x %d rows (the reference's op)" % w["E"]}

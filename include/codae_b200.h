@@ -199,6 +199,22 @@ int codae_score_rank(codae_ctx* ctx, const void* catalog, int cat_dtype, int64_t
                      const float* query, int Q, float inv_scale, int metric, const int64_t* true_idx,
                      const int64_t* subset_idx, int64_t n_subset, int64_t* out_rank, void* stream);
 
+/* Candidate SWAPS scored by full reconstruction error (the GEMM-bound reading of stage IV): candidate j replaces slot
+ * `slot` of the (scaled) outfit, the DAE reconstructs the swapped outfit (codae_linear_fwd per layer, batched over the
+ * candidates), and the swap's score is sum_d (DAE(x'_j)_d - x'_j,d)^2 over all io dimensions (lower is better).
+ *   codae_swap_build      x'[b, :] for candidates first_row .. first_row+B-1 of `catalog` ([.., ld_cat] f32|bf16, un-scaled,
+ *                         multiplied by inv_scale), written as f32|bf16 with pitch ld_x (columns >= io untouched)
+ *   codae_swap_error_topk errors of the B reconstructions y [B, ld_y] f32 and the best k of them:
+ *                         out_score [k], out_idx [k] = row_offset + first_row + b, best first, ties -> lower index,
+ *                         unused slots idx = -1.  workspace >= codae_score_topk_workspace_bytes(ctx, 1, k).
+ * Lists of several candidate chunks / ranks are combined with codae_topk_merge.                                  */
+int codae_swap_build(codae_ctx* ctx, const float* outfit, const void* catalog, int cat_dtype, int64_t ld_cat, int64_t first_row,
+                     int B, int E, int slot, int io, float inv_scale, void* out_x, int x_dtype, int64_t ld_x, void* stream);
+int codae_swap_error_topk(codae_ctx* ctx, const float* outfit, const void* catalog, int cat_dtype, int64_t ld_cat,
+                          int64_t first_row, int B, int E, int slot, int io, float inv_scale, const float* y, int64_t ld_y,
+                          int64_t row_offset, int k, float* out_score, int64_t* out_idx, void* workspace, size_t ws_bytes,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

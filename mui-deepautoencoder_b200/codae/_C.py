@@ -53,6 +53,9 @@ SIGNATURES = {
     "codae_score_topk": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "codae_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "codae_score_rank": (_i, [_vp, _vp, _i, _i64, _i64, _i, _vp, _i, _f, _i, _vp, _vp, _i64, _vp, _vp]),
+    "codae_swap_build": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _f, _vp, _i, _i64, _vp]),
+    "codae_swap_error_topk": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _f, _vp, _i64, _i64, _i, _vp, _vp, _vp,
+                                   _sz, _vp]),
 }
 
 _lib = None
@@ -286,6 +289,21 @@ def score_rank(catalog, E, query, inv_scale, metric, true_idx, subset_idx, out_r
     check(lib().codae_score_rank(c, p(catalog), dt(catalog), catalog.shape[0], catalog.stride(0), E, p(query),
                                  query.shape[0], inv_scale, metric, p(true_idx), p(subset_idx),
                                  0 if subset_idx is None else subset_idx.numel(), p(out_rank), stream()), c)
+
+
+def swap_build(outfit, catalog, first_row, B, E, slot, io, inv_scale, out_x):
+    _dev_check(outfit, catalog, out_x)
+    c = ctx(catalog.device)
+    check(lib().codae_swap_build(c, p(outfit), p(catalog), dt(catalog), catalog.stride(0), first_row, B, E, slot, io,
+                                 inv_scale, p(out_x), dt(out_x), out_x.stride(0), stream()), c)
+
+
+def swap_error_topk(outfit, catalog, first_row, B, E, slot, io, inv_scale, y, row_offset, k, out_score, out_idx, ws):
+    _dev_check(outfit, catalog, y, out_score, out_idx, ws)
+    c = ctx(catalog.device)
+    check(lib().codae_swap_error_topk(c, p(outfit), p(catalog), dt(catalog), catalog.stride(0), first_row, B, E, slot, io,
+                                      inv_scale, p(y), y.stride(0), row_offset, k, p(out_score), p(out_idx), p(ws),
+                                      ws.numel(), stream()), c)
 
 
 def linear_engine(device, dtype, M, N, K):

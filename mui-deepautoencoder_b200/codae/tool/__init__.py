@@ -9,5 +9,5 @@ from .dictionnary import Dict
 from .parser import parse
 # additions
 from .fused_step import FusedStep
-from .inference import ComplementarityScorer
+from .inference import ComplementarityScorer, SwapScorer
 from .embedding_file import convert_json_to_cemb, load_cemb_dataset, read_cemb, write_cemb

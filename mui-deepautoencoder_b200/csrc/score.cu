@@ -239,6 +239,77 @@ __global__ void __launch_bounds__(kThreads) score_rank_kernel(const void* __rest
         if (cnt[q]) atomicAdd(&out_rank[q], (unsigned long long)cnt[q]);
 }
 
+// ---- candidate SWAPS scored by full reconstruction error --------------------------------------------------------
+// Second reading of "scores candidate item swaps by reconstruction error": put candidate j into slot c of the outfit, run
+// the DAE on the swapped outfit (the tensor-core GEMMs, batched over candidates) and score the swap by
+// || DAE(outfit_j) - outfit_j ||^2 over all io dimensions.  Two small kernels bracket the forward pass:
+//   swap_build_kernel      x'[b, :] = outfit with columns [slot*E, (slot+1)*E) replaced by catalog[first_row + b] * inv_scale
+//   swap_error_topk_kernel err_b = sum_d (y[b, d] - x'[b, d])^2 (x' recomputed in fp32), best k per CTA, then topk_merge_kernel
+template <bool kBf16Cat, bool kBf16Out>
+__global__ void __launch_bounds__(256) swap_build_kernel(const float* __restrict__ outfit, const void* __restrict__ catalog,
+                                                         int64_t ld_cat, int64_t first_row, int B, int E, int slot, int io,
+                                                         float inv_scale, void* __restrict__ out, int64_t ld_out) {
+    const int64_t total = (int64_t)B * io;
+    const int lo = slot * E, hi = lo + E;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int b = (int)(e / io), d = (int)(e - (int64_t)b * io);
+        float v;
+        if (d >= lo && d < hi) {
+            const int64_t off = (first_row + b) * ld_cat + (d - lo);
+            v = (kBf16Cat ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(catalog)[off])
+                          : reinterpret_cast<const float*>(catalog)[off]) * inv_scale;
+        } else {
+            v = outfit[d];
+        }
+        if (kBf16Out) reinterpret_cast<__nv_bfloat16*>(out)[(int64_t)b * ld_out + d] = __float2bfloat16_rn(v);
+        else reinterpret_cast<float*>(out)[(int64_t)b * ld_out + d] = v;
+    }
+}
+
+template <bool kBf16Cat>
+__global__ void __launch_bounds__(kThreads) swap_error_topk_kernel(const float* __restrict__ outfit, const void* __restrict__ catalog,
+                                                                   int64_t ld_cat, int64_t first_row, int B, int E, int slot, int io,
+                                                                   float inv_scale, const float* __restrict__ y, int64_t ld_y,
+                                                                   int64_t row_offset, int k, float* __restrict__ ws_score,
+                                                                   int64_t* __restrict__ ws_idx) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int64_t* li = reinterpret_cast<int64_t*>(smem_raw);                    // [kWarps][k]
+    float* ls = reinterpret_cast<float*>(li + kWarps * k);                 // [kWarps][k]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int e = threadIdx.x; e < kWarps * k; e += kThreads) { ls[e] = INFINITY; li[e] = kEmptyIdx; }
+    __syncthreads();
+    const int lo = slot * E, hi = lo + E;
+    for (int b = blockIdx.x * kWarps + warp; b < B; b += gridDim.x * kWarps) {
+        float acc = 0.f;
+        for (int d = lane; d < io; d += 32) {
+            float t;
+            if (d >= lo && d < hi) {
+                const int64_t off = (first_row + b) * ld_cat + (d - lo);
+                t = (kBf16Cat ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(catalog)[off])
+                              : reinterpret_cast<const float*>(catalog)[off]) * inv_scale;
+            } else {
+                t = outfit[d];
+            }
+            const float df = y[(int64_t)b * ld_y + d] - t;
+            acc = fmaf(df, df, acc);
+        }
+        acc = warp_sum(acc);
+        if (acc == acc) list_insert<CODAE_METRIC_SQERR>(ls + warp * k, li + warp * k, k, acc, row_offset + first_row + b, lane);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < kWarps; ++w)
+            for (int e = 0; e < k; ++e) {
+                if (li[w * k + e] == kEmptyIdx) break;
+                if (!list_insert<CODAE_METRIC_SQERR>(ls, li, k, ls[w * k + e], li[w * k + e], lane)) break;
+            }
+        for (int e = lane; e < k; e += 32) {
+            ws_score[(int64_t)blockIdx.x * k + e] = ls[e];
+            ws_idx[(int64_t)blockIdx.x * k + e] = li[e];
+        }
+    }
+}
+
 inline int sweep_grid(const codae_ctx* ctx, int64_t n_rows) {
     int64_t g = (n_rows + kWarps - 1) / kWarps;
     const int64_t cap = (int64_t)ctx->sm_count * 4;
@@ -323,6 +394,46 @@ int codae_topk_merge(codae_ctx* ctx, const float* scores, const int64_t* idx, in
         topk_merge_kernel<CODAE_METRIC_COSINE><<<Q, kThreads, 0, as_stream(stream)>>>(scores, idx, G, Q, k, out_score, out_idx, 0, 1);
     else
         return codae_fail(ctx, CODAE_EINVAL, "codae_topk_merge: bad metric %d", metric);
+    return codae_check_launch(ctx, "topk_merge_kernel");
+}
+
+int codae_swap_build(codae_ctx* ctx, const float* outfit, const void* catalog, int cat_dtype, int64_t ld_cat, int64_t first_row,
+                     int B, int E, int slot, int io, float inv_scale, void* out_x, int x_dtype, int64_t ld_x, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && outfit && catalog && out_x, "codae_swap_build: NULL argument");
+    CODAE_REQUIRE(ctx, B >= 1 && E >= 1 && slot >= 0 && (slot + 1) * E <= io && ld_x >= io && ld_cat >= E && first_row >= 0,
+                  "codae_swap_build: bad shape (B=%d E=%d slot=%d io=%d)", B, E, slot, io);
+    const bool bc = cat_dtype == CODAE_BF16, bo = x_dtype == CODAE_BF16;
+    int64_t blocks = ((int64_t)B * io + 256 * 4 - 1) / (256 * 4);
+    if (blocks > (int64_t)ctx->sm_count * 8) blocks = (int64_t)ctx->sm_count * 8;
+    cudaStream_t s = as_stream(stream);
+#define LAUNCH(BC, BO) swap_build_kernel<BC, BO><<<(unsigned)blocks, 256, 0, s>>>(outfit, catalog, ld_cat, first_row, B, E, slot, io, inv_scale, out_x, ld_x)
+    if (bc && bo) LAUNCH(true, true); else if (bc) LAUNCH(true, false); else if (bo) LAUNCH(false, true); else LAUNCH(false, false);
+#undef LAUNCH
+    return codae_check_launch(ctx, "swap_build_kernel");
+}
+
+int codae_swap_error_topk(codae_ctx* ctx, const float* outfit, const void* catalog, int cat_dtype, int64_t ld_cat,
+                          int64_t first_row, int B, int E, int slot, int io, float inv_scale, const float* y, int64_t ld_y,
+                          int64_t row_offset, int k, float* out_score, int64_t* out_idx, void* workspace, size_t ws_bytes,
+                          void* stream) {
+    CODAE_REQUIRE(ctx, ctx && outfit && catalog && y && out_score && out_idx && workspace, "codae_swap_error_topk: NULL argument");
+    CODAE_REQUIRE(ctx, B >= 1 && E >= 1 && slot >= 0 && (slot + 1) * E <= io && ld_y >= io && ld_cat >= E && k >= 1 && k <= kMaxK,
+                  "codae_swap_error_topk: bad shape");
+    if (ws_bytes < codae_score_topk_workspace_bytes(ctx, 1, k))
+        return codae_fail(ctx, CODAE_ENOMEM, "codae_swap_error_topk: workspace %zu < %zu bytes", ws_bytes,
+                          codae_score_topk_workspace_bytes(ctx, 1, k));
+    cudaStream_t s = as_stream(stream);
+    const int grid = sweep_grid(ctx, B);
+    int64_t* ws_idx = reinterpret_cast<int64_t*>(workspace);
+    float* ws_score = reinterpret_cast<float*>(ws_idx + (size_t)grid * k);
+    const size_t smem = (size_t)kWarps * k * 12;
+    if (cat_dtype == CODAE_BF16)
+        swap_error_topk_kernel<true><<<grid, kThreads, smem, s>>>(outfit, catalog, ld_cat, first_row, B, E, slot, io, inv_scale, y, ld_y, row_offset, k, ws_score, ws_idx);
+    else
+        swap_error_topk_kernel<false><<<grid, kThreads, smem, s>>>(outfit, catalog, ld_cat, first_row, B, E, slot, io, inv_scale, y, ld_y, row_offset, k, ws_score, ws_idx);
+    int rc = codae_check_launch(ctx, "swap_error_topk_kernel");
+    if (rc) return rc;
+    topk_merge_kernel<CODAE_METRIC_SQERR><<<1, kThreads, 0, s>>>(ws_score, ws_idx, grid, 1, k, out_score, out_idx, 0, 1);
     return codae_check_launch(ctx, "topk_merge_kernel");
 }
 

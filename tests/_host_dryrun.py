@@ -53,7 +53,7 @@ torch.cuda.current_device = lambda: 0
 from codae.dataset import ConcatenatedEmbeddingDataset, MixedVariableDataset
 from codae.model import EmbeddingDenoisingAutoencoder, MixedVariableDenoisingAutoencoder
 from codae.tool import Corrupter, FusedStep, RankingLoss, CombinedCriterion
-from codae.tool.inference import ComplementarityScorer, predict_slot
+from codae.tool.inference import ComplementarityScorer, SwapScorer, predict_slot
 
 dev = torch.device("cpu")
 for dtype in ("fp32", "bf16"):
@@ -74,6 +74,7 @@ for dtype in ("fp32", "bf16"):
     f1 = torch.ones(3, 96); f1[0, :32] = 0; f1[1, 32:64] = 0; f1[2, 64:] = 0
     print("rank", rl.get(y.detach(), f1, (1, 2, 3)))
     p = predict_slot(m, x, 1, 32); sc = ComplementarityScorer(ds.data_per_category[1], 32, k=5); print(sc.topk(p)[1].shape)
+    sw = SwapScorer(m, ds.data_per_category[1], 32, k=5, chunk=16); print("swap", sw.topk(x[0], 1)[1].shape)
 # abalone
 arch = [dict(name="Sex", size=3, type="classification", position=0)] + [dict(name=str(i), size=1, type="regression", position=3 + i) for i in range(8)]
 ds = MixedVariableDataset.from_arch(arch, torch.rand(100, 11))

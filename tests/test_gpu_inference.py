@@ -137,3 +137,67 @@ def test_full_size_catalog_properties(bf16):
     ms, mi = torch.empty_like(s), torch.empty_like(i)
     _C.topk_merge(torch.stack(ps), torch.stack(pi), _C.METRIC_SQERR, ms, mi)
     assert torch.equal(mi, i) and torch.equal(ms, s)
+
+
+def _swap_model(S, E, z, nin, nout, dtype, seed):
+    from codae.model import EmbeddingDenoisingAutoencoder
+    torch.manual_seed(seed)
+    model = EmbeddingDenoisingAutoencoder(S * E, z, E, nin, nout, False)
+    for lin in model.linears():
+        torch.nn.init.uniform_(lin.bias, -0.05, 0.05)
+    W = [lin.weight.detach().clone() for lin in model.linears()]
+    b = [lin.bias.detach().clone() for lin in model.linears()]
+    model = model.to(DEV).set_compute_dtype(dtype)
+    return model, W, b
+
+
+@pytest.mark.parametrize("n,S,E,slot,k,chunk,cat_bf16", [(3000, 4, 64, 2, 10, 1024, False), (777, 3, 128, 0, 5, 8192, False),
+                                                         (5, 4, 64, 3, 10, 256, False), (2500, 4, 64, 1, 16, 512, True)])
+def test_swap_scores_match_oracle_fp32(n, S, E, slot, k, chunk, cat_bf16):
+    """Full-reconstruction swap scoring on the exact-fp32 engine: the ranking equals the oracle's, errors to 1e-5."""
+    from oracle import codae_oracle as O
+    from codae.tool.inference import SwapScorer
+    model, W, b = _swap_model(S, E, 96, 2, 2, "fp32", n + slot)
+    cat = torch.rand(n, E) * 2
+    if cat_bf16:
+        cat = cat.to(torch.bfloat16)
+    if n > 10:
+        cat[n - 1] = cat[4]                         # duplicate candidate: tie -> lower index first
+    outfit = torch.rand(S * E)
+    sc = SwapScorer(model, cat.to(DEV), E, k=k, inv_scale=0.5, row_offset=100, chunk=chunk)
+    s, i = sc.topk_local(outfit.to(DEV), slot)
+    s, i = s.cpu(), i.cpu()
+    err = O.score_swaps(W, b, model.relu, outfit, slot, E, cat.float(), inv_scale=0.5)
+    ws, wi = O.topk(err, k, "sqerr", row_offset=100)
+    m = min(k, n)
+    assert i[:m].tolist() == wi.tolist(), (i, wi)
+    assert torch.all(i[m:] == -1)
+    assert np.allclose(s[:m].numpy(), ws.numpy(), rtol=1e-5, atol=1e-6)
+    if n > 10 and (n - 1 + 100) in i.tolist():
+        pos = i.tolist()
+        assert pos.index(104) + 1 == pos.index(n - 1 + 100)
+
+
+def test_swap_scores_bf16_engine_and_chunk_invariance():
+    """Tensor-core engine: errors within the bf16 tolerance (1e-2 relative) of the fp32 oracle at the returned indices,
+    the returned set is the oracle's top-k up to near-ties, and the ranking does not depend on the chunk size."""
+    from oracle import codae_oracle as O
+    from codae.tool.inference import SwapScorer
+    n, S, E, slot, k = 6000, 4, 128, 1, 10
+    model, W, b = _swap_model(S, E, 256, 2, 2, "bf16", 3)
+    from codae import _C
+    assert model.engine_dtype() == _C.BF16
+    cat = torch.rand(n, E)
+    outfit = torch.rand(S * E)
+    res = []
+    for chunk in (1024, 4096, 8192):
+        s, i = SwapScorer(model, cat.to(DEV), E, k=k, chunk=chunk).topk_local(outfit.to(DEV), slot)
+        res.append((s.cpu(), i.cpu()))
+    for s, i in res[1:]:
+        # the chunk size changes the GEMM schedule (split-K factor -> fp32 summation order), not the ranking
+        assert torch.equal(i, res[0][1]) and np.allclose(s.numpy(), res[0][0].numpy(), rtol=1e-4)
+    s, i = res[0]
+    err = O.score_swaps(W, b, model.relu, outfit, slot, E, cat)
+    assert np.allclose(s.numpy(), err[i].numpy(), rtol=1e-2)
+    kth = float(O.topk(err, k)[0][-1])
+    assert float(err[i].max()) <= kth * 1.01
