@@ -53,3 +53,14 @@ def test_complementarity_inference_script(tmp_path):
     assert res["slot"] == 1 and len(res["indices"]) == 3 and all(len(r) == 7 for r in res["indices"])
     assert all(0 <= i < 5000 for r in res["indices"] for i in r)
     assert all(r[j] >= r[j + 1] for r in res["scores"] for j in range(6))       # cosine: best first
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_complementarity_inference_script_swap_mode(tmp_path, dtype):
+    out = run([os.path.join(SCRIPT, "4_complementarity_inference.py"), "--config", os.path.join(CONFIG, "embedding.yaml"),
+               "--synthetic", "3000", "--slot", "2", "--k", "5", "--queries", "2", "--mode", "swap", "--compute_dtype", dtype],
+              str(tmp_path))
+    res = json.loads(out.strip().splitlines()[-1])
+    assert res["mode"] == "swap" and len(res["indices"]) == 2 and all(len(r) == 5 for r in res["indices"])
+    assert all(0 <= i < 3000 for r in res["indices"] for i in r)
+    assert all(r[j] <= r[j + 1] for r in res["scores"] for j in range(4))       # reconstruction error: best first
