@@ -174,6 +174,7 @@ def main():
     ap.add_argument("--dtype", type=str, default=None, choices=["fp32", "bf16"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--no-prefetch", action="store_true", help="weight tiles are not requested ahead of the PDL wait")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-fp32", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch without programmatic dependent launch")
@@ -222,6 +223,8 @@ def main():
 
     if args.no_pdl:
         _C.set_option(dev, _C.OPT_PDL, 0)
+    if args.no_prefetch:
+        _C.set_option(dev, _C.OPT_WEIGHT_PREFETCH, 0)
     if args.no_splitk:
         _C.set_option(dev, _C.OPT_SPLITK, 0)
     if args.no_persistent:

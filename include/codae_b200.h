@@ -47,15 +47,21 @@ int codae_ctx_create(int device, codae_ctx** out);
 int codae_ctx_destroy(codae_ctx* ctx);
 const char* codae_last_error(const codae_ctx* ctx); /* ctx may be NULL: last process-wide error */
 int codae_ctx_sm_count(const codae_ctx* ctx);
-/* Tuning switches, both on by default (tests turn them off to compare code paths):
+/* Tuning switches, all on by default (tests turn them off to compare code paths):
  *   CODAE_OPT_SPLITK  contractions with too few output tiles to occupy the GPU (the small-batch layers of
  *                     embedding.yaml / modanet) spread their k-blocks over a thread-block cluster and reduce the partial
  *                     tiles through distributed shared memory, in rank order (bitwise reproducible);
  *   CODAE_OPT_PDL     training-step kernels are launched as programmatic dependents: their prologue overlaps the tail
  *                     of the previous kernel and they wait (griddepcontrol.wait) before touching global memory;
  *   CODAE_OPT_PERSISTENT  contractions with more than 2 output tiles per SM run one persistent CTA per SM with the
- *                     accumulator double-buffered in TMEM, so a tile's epilogue overlaps the next tile's MMAs. */
-enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1, CODAE_OPT_PERSISTENT = 2 };
+ *                     accumulator double-buffered in TMEM, so a tile's epilogue overlaps the next tile's MMAs;
+ *   CODAE_OPT_WEIGHT_PREFETCH  (needs CODAE_OPT_PDL) codae_linear_fwd / codae_linear_dgrad on the tensor-core engine request
+ *                     the TMA loads of their WEIGHT tiles before griddepcontrol.wait, i.e. while the stream predecessors
+ *                     that produce the activations are still finishing.  Sound because every entry point that writes
+ *                     weights (codae_adam_step, codae_clip_adam_step, codae_cast_bf16) makes the next launch on its stream
+ *                     a full (non-programmatic) dependency.  A caller that writes the bf16 weight buffer with kernels of
+ *                     its own must either switch this off or call codae_cast_bf16 / an optimizer entry point afterwards. */
+enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1, CODAE_OPT_PERSISTENT = 2, CODAE_OPT_WEIGHT_PREFETCH = 3 };
 int codae_ctx_set_option(codae_ctx* ctx, int option, int value);
 /* Which engine codae_linear_* will use for (dtype, M, N, K). */
 int codae_linear_engine(const codae_ctx* ctx, int dtype, int M, int N, int K);

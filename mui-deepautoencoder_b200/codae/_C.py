@@ -103,7 +103,7 @@ def ctx(device=None):
     return c
 
 
-OPT_SPLITK, OPT_PDL, OPT_PERSISTENT = 0, 1, 2
+OPT_SPLITK, OPT_PDL, OPT_PERSISTENT, OPT_WEIGHT_PREFETCH = 0, 1, 2, 3
 
 
 _options = {}

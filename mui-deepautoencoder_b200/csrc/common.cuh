@@ -20,6 +20,9 @@ struct codae_ctx {
     int splitk;          // 1: small-batch contractions may use cluster split-K (default on)
     int persistent;      // 1: large contractions use the persistent, TMEM-double-buffered kernel (default on)
     int pdl;             // 1: training-step kernels are launched with programmatic dependent launch (default on)
+    int weight_prefetch; // 1: fwd / dgrad GEMMs issue the TMA loads of their WEIGHT tiles before griddepcontrol.wait
+    int weights_dirty;   // a weight-writing kernel (Adam, clip+Adam, bf16 cast) was the last codae launch on dirty_stream
+    cudaStream_t dirty_stream;
     std::mutex mu;
 };
 
@@ -37,6 +40,24 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 // Programmatic dependent launch: the kernel may start (prologue, barrier init, TMEM allocation) while its stream
 // predecessor is still running; it must execute pdl_wait() before touching any global memory.
+// Weight tiles may be fetched BEFORE griddepcontrol.wait (weight_prefetch), i.e. while any number of stream predecessors
+// are still running.  That is only sound if no predecessor can still be writing weights: every entry point that writes
+// weights calls codae_mark_weights_written, and the next launch on that stream is then made WITHOUT the programmatic
+// attribute -- a full stream dependency (complete + flushed).  All later pre-wait portions start after that launch began.
+inline void codae_mark_weights_written(codae_ctx* ctx, cudaStream_t s) {
+    ctx->weights_dirty = 1;
+    ctx->dirty_stream = s;
+}
+inline bool codae_pdl_allowed(const codae_ctx* cctx, cudaStream_t s) {
+    codae_ctx* ctx = const_cast<codae_ctx*>(cctx);
+    if (!ctx || !ctx->pdl) return false;
+    if (ctx->weights_dirty && ctx->dirty_stream == s) {
+        ctx->weights_dirty = 0;
+        return false;
+    }
+    return true;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(const codae_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                               cudaStream_t s, Args... args) {
@@ -49,7 +70,7 @@ inline cudaError_t launch_pdl(const codae_ctx* ctx, void (*kernel)(KArgs...), di
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (ctx && ctx->pdl) ? 1 : 0;
+    cfg.numAttrs = codae_pdl_allowed(ctx, s) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 

@@ -44,41 +44,78 @@ __global__ void mask_table_philox_kernel(uint64_t seed, int64_t first_obs, int64
 __device__ __forceinline__ float keep_of(uint64_t bits, uint32_t var) { return ((bits >> var) & 1ull) ? 0.0f : 1.0f; }
 
 // Vector path: io % 4 == 0, all pitches % 4 == 0, 16-byte aligned bases.
+// A group of G = 2^log2g threads (32..256) owns one row at a time: the row's (observation, mask id, mask bits) chain is
+// looked up once per row -- and for the NEXT row while the current row's data is in flight -- and every thread keeps
+// four independent 128-bit loads outstanding.
+constexpr int kRowUnroll = 4;
 template <bool kBf16Out>
 __global__ void __launch_bounds__(256) corrupt_fwd_vec_kernel(const float* __restrict__ data, int64_t ld_data,
                                                               const int64_t* __restrict__ batch_idx, int B,
                                                               const int16_t* __restrict__ mask_table, int nb_run, int run,
                                                               const uint64_t* __restrict__ mask_bits,
-                                                              const uint8_t* __restrict__ col_var, int io4,
+                                                              const uint8_t* __restrict__ col_var, int io4, int log2g,
                                                               void* __restrict__ out_cx, int64_t ld_cx,
                                                               float* __restrict__ out_x, int64_t ld_x,
                                                               int32_t* __restrict__ out_mask_id) {
     pdl_launch_dependents();
     pdl_wait();
-    const int64_t total = (int64_t)B * io4;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-        const int row = (int)(e / io4);
-        const int c4 = (int)(e - (int64_t)row * io4);
-        const int64_t obs = batch_idx ? batch_idx[row] : (int64_t)row;
-        const int mid = mask_table[obs * nb_run + run];
-        const uint64_t bits = mask_bits[mid];
-        const uchar4 var = *reinterpret_cast<const uchar4*>(col_var + 4 * c4);
-        const float4 x = ldg_stream_f4(data + obs * ld_data + 4 * (int64_t)c4);
-        float4 cx;
-        cx.x = x.x * keep_of(bits, var.x);
-        cx.y = x.y * keep_of(bits, var.y);
-        cx.z = x.z * keep_of(bits, var.z);
-        cx.w = x.w * keep_of(bits, var.w);
-        if (kBf16Out) {
-            uint2 p;
-            p.x = pack_bf16x2(cx.x, cx.y);
-            p.y = pack_bf16x2(cx.z, cx.w);
-            stg_stream_u2(reinterpret_cast<__nv_bfloat16*>(out_cx) + (int64_t)row * ld_cx + 4 * c4, p);
-        } else {
-            stg_stream_f4(reinterpret_cast<float*>(out_cx) + (int64_t)row * ld_cx + 4 * c4, cx);
+    const int G = 1 << log2g, rows_per_cta = 256 >> log2g;
+    const int gl = threadIdx.x & (G - 1);
+    const int row_stride = gridDim.x * rows_per_cta;
+    int row = blockIdx.x * rows_per_cta + (threadIdx.x >> log2g);
+    int64_t obs = 0;
+    int mid = 0;
+    uint64_t bits = 0;
+    if (row < B) {
+        obs = batch_idx ? batch_idx[row] : (int64_t)row;
+        mid = mask_table[obs * nb_run + run];
+        bits = mask_bits[mid];
+    }
+    for (; row < B; row += row_stride) {
+        const float* src = data + obs * ld_data;
+        int64_t n_obs = 0;
+        int n_mid = 0;
+        uint64_t n_bits = 0;
+        bool first_chunk = true;
+        for (int c0 = 0; c0 < io4; c0 += kRowUnroll * G) {
+            float4 x[kRowUnroll];
+#pragma unroll
+            for (int j = 0; j < kRowUnroll; ++j) {
+                const int c4 = c0 + gl + j * G;
+                if (c4 < io4) x[j] = ldg_stream_f4(src + 4 * (int64_t)c4);
+            }
+            if (first_chunk) {                     // next row's lookups ride under the loads just issued
+                first_chunk = false;
+                const int nrow = row + row_stride;
+                if (nrow < B) {
+                    n_obs = batch_idx ? batch_idx[nrow] : (int64_t)nrow;
+                    n_mid = mask_table[n_obs * nb_run + run];
+                    n_bits = mask_bits[n_mid];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < kRowUnroll; ++j) {
+                const int c4 = c0 + gl + j * G;
+                if (c4 >= io4) continue;
+                const uchar4 var = *reinterpret_cast<const uchar4*>(col_var + 4 * c4);
+                float4 cx;
+                cx.x = x[j].x * keep_of(bits, var.x);
+                cx.y = x[j].y * keep_of(bits, var.y);
+                cx.z = x[j].z * keep_of(bits, var.z);
+                cx.w = x[j].w * keep_of(bits, var.w);
+                if (kBf16Out) {
+                    uint2 p;
+                    p.x = pack_bf16x2(cx.x, cx.y);
+                    p.y = pack_bf16x2(cx.z, cx.w);
+                    stg_stream_u2(reinterpret_cast<__nv_bfloat16*>(out_cx) + (int64_t)row * ld_cx + 4 * c4, p);
+                } else {
+                    stg_stream_f4(reinterpret_cast<float*>(out_cx) + (int64_t)row * ld_cx + 4 * c4, cx);
+                }
+                if (out_x) stg_stream_f4(out_x + (int64_t)row * ld_x + 4 * c4, x[j]);
+            }
         }
-        if (out_x) stg_stream_f4(out_x + (int64_t)row * ld_x + 4 * c4, x);
-        if (out_mask_id && c4 == 0) out_mask_id[row] = mid;
+        if (out_mask_id && gl == 0) out_mask_id[row] = mid;
+        obs = n_obs; mid = n_mid; bits = n_bits;
     }
 }
 
@@ -175,9 +212,14 @@ int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t ld_data, const 
                      ((reinterpret_cast<uintptr_t>(col_var) & 3) == 0);
     cudaStream_t s = as_stream(stream);
     if (vec) {
-        const int g = grid_for(ctx, (int64_t)B * (io / 4), 256, 4);
-        if (bf) launch_pdl(ctx, corrupt_fwd_vec_kernel<true>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, out_cx, ld_cx, out_x, ld_x, out_mask_id);
-        else launch_pdl(ctx, corrupt_fwd_vec_kernel<false>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        // threads per row: the smallest power of two that covers the row with four 128-bit loads per thread
+        int log2g = 5;
+        while (log2g < 8 && (kRowUnroll << log2g) < io / 4) ++log2g;
+        const int rows_per_cta = 256 >> log2g;
+        int g = (B + rows_per_cta - 1) / rows_per_cta;
+        if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
+        if (bf) launch_pdl(ctx, corrupt_fwd_vec_kernel<true>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        else launch_pdl(ctx, corrupt_fwd_vec_kernel<false>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
     } else {
         const int g = grid_for(ctx, (int64_t)B * io, 256, 4);
         if (bf) corrupt_fwd_scalar_kernel<true><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io, out_cx, ld_cx, out_x, ld_x, out_mask_id);

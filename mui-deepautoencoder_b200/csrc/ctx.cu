@@ -60,6 +60,9 @@ int codae_ctx_create(int device, codae_ctx** out) {
     c->splitk = 1;
     c->pdl = 1;
     c->persistent = 1;
+    c->weight_prefetch = 1;
+    c->weights_dirty = 0;
+    c->dirty_stream = nullptr;
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
     e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -83,6 +86,7 @@ int codae_ctx_set_option(codae_ctx* ctx, int option, int value) {
     if (option == CODAE_OPT_SPLITK) ctx->splitk = value ? 1 : 0;
     else if (option == CODAE_OPT_PDL) ctx->pdl = value ? 1 : 0;
     else if (option == CODAE_OPT_PERSISTENT) ctx->persistent = value ? 1 : 0;
+    else if (option == CODAE_OPT_WEIGHT_PREFETCH) ctx->weight_prefetch = value ? 1 : 0;
     else return codae_fail(ctx, CODAE_EINVAL, "codae_ctx_set_option: unknown option %d", option);
     return CODAE_OK;
 }

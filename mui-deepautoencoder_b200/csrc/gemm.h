@@ -20,6 +20,7 @@ struct Tc05Gemm {
     int M, N, K;
     const float* bias; int act;                  // bias[n] + activation (fwd)
     const void* mask_src; int64_t ldm;           // bf16 [M, ldm]: C *= (mask_src > 0) (dgrad)
+    bool b_is_weight = false;                    // B holds layer weights: its tiles may be fetched ahead of the stream dependency
 };
 bool codae_tc05_supported(const codae_ctx* ctx, const Tc05Gemm& g);
 int codae_tc05_gemm(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s);

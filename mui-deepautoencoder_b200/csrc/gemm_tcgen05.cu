@@ -53,6 +53,7 @@ struct Params {
     long long ldm;
     int stages;                  // pipeline depth actually used (<= Cfg::kStages)
     int staged;                  // 1: epilogue through the shared-memory tile (required when gridDim.z > 1)
+    int prefetch_b;              // 1: B holds weights no running predecessor writes: fetch its first tiles before the PDL wait
     unsigned long long* trace;   // debugging: CTA (0,0,0) writes %globaltimer stamps of its phases here (or NULL)
 };
 
@@ -276,6 +277,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     if (threadIdx.x == 0) trace_stamp(p, 1);                       // prologue done (barriers, TMEM)
+    // Weight tiles of the first ring pass are requested NOW, while the stream predecessor (which produces A) is still
+    // finishing: the full barrier of a slot is armed for both operands, B arrives early, A is requested after the wait.
+    const int npre = p.prefetch_b ? min(num_kb, nstages) : 0;
+    if (warp == 0 && lane == 0) {
+        for (int kb = 0; kb < npre; ++kb) {
+            uint8_t* b_dst = smem + kb * C::kStageBytes + kATileBytes;
+            mbar_expect_tx(&full_bar[kb], C::kStageBytes);
+            const int k0 = (kb_begin + kb) * BK;
+            if (p.b_kmajor) {
+                tma_load_2d(&tma_b, &full_bar[kb], b_dst, k0, n0);
+            } else {
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tma_b, &full_bar[kb], b_dst + j * 8192, n0 + 64 * j, k0);
+            }
+        }
+    }
     pdl_wait();
     if (threadIdx.x == 0) trace_stamp(p, 2);                       // predecessor complete     // everything above overlapped the previous kernel's tail; operands and outputs are global memory
 
@@ -285,10 +302,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
             int s = 0;
             uint32_t ph = 0;
             for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == nstages ? 0 : s + 1), ph ^= (s == 0)) {
-                mbar_wait(&empty_bar[s], ph ^ 1);
+                const bool b_requested = kb < npre;                                          // first ring pass, before the wait
+                if (!b_requested) mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * C::kStageBytes;
                 uint8_t* b_dst = a_dst + kATileBytes;
-                mbar_expect_tx(&full_bar[s], C::kStageBytes);
+                if (!b_requested) mbar_expect_tx(&full_bar[s], C::kStageBytes);
                 const int k0 = (kb_begin + kb) * BK;
                 if (p.a_kmajor) {
                     tma_load_2d(&tma_a, &full_bar[s], a_dst, k0, m0);                       // box {64 k, 128 m}
@@ -296,6 +314,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                     tma_load_2d(&tma_a, &full_bar[s], a_dst, m0, k0);                       // box {64 m, 64 k} x 2
                     tma_load_2d(&tma_a, &full_bar[s], a_dst + 8192, m0 + 64, k0);
                 }
+                if (b_requested) continue;
                 if (p.b_kmajor) {
                     tma_load_2d(&tma_b, &full_bar[s], b_dst, k0, n0);                       // box {64 k, BN n}
                 } else {
@@ -674,6 +693,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     // (measured: the direct epilogue is faster for the 4096-wide weight gradients, 247 vs 261 us)
     p.trace = g_trace_buf;
     p.staged = (nsplit > 1 || (g.c_dtype == CODAE_F32 && tiles <= 2 * ctx->sm_count)) ? 1 : 0;
+    p.prefetch_b = (g.b_is_weight && ctx->pdl && ctx->weight_prefetch) ? 1 : 0;
     if (nsplit == 1 && !p.staged && ctx->persistent && tiles > 2 * ctx->sm_count) {
         static bool pattr_set = false;
         if (!pattr_set) {
@@ -718,7 +738,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
         attr[na].val.clusterDim.z = nsplit;
         ++na;
     }
-    if (ctx->pdl) {
+    if (codae_pdl_allowed(ctx, s)) {
         attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[na].val.programmaticStreamSerializationAllowed = 1;
         ++na;

@@ -28,7 +28,7 @@ int codae_linear_fwd(codae_ctx* ctx, const void* X, int64_t ldx, const void* W, 
         return codae_simt_linear_fwd(ctx, (const float*)X, ldx, (const float*)W, ldw, bias, (float*)Y, ldy, M, N, K, act, as_stream(stream));
     }
     CODAE_REQUIRE(ctx, dtype == CODAE_BF16, "codae_linear_fwd: bad dtype %d", dtype);
-    Tc05Gemm g{X, ldx, true, W, ldw, true, Y, ldy, out_dtype, M, N, K, bias, act, nullptr, 0};
+    Tc05Gemm g{X, ldx, true, W, ldw, true, Y, ldy, out_dtype, M, N, K, bias, act, nullptr, 0, true};
     return codae_tc05_gemm(ctx, g, as_stream(stream));
 }
 
@@ -44,7 +44,7 @@ int codae_linear_dgrad(codae_ctx* ctx, const void* dY, int64_t lddy, const void*
     CODAE_REQUIRE(ctx, dtype == CODAE_BF16, "codae_linear_dgrad: bad dtype %d", dtype);
     // dX[M,K] = sum_n dY[m,n] W[n,k]: contraction over N.  A = dY (contraction contiguous), B(k_out, n) = W[n, k_out]
     // (contraction index is the row of W -> MN-major operand).
-    Tc05Gemm g{dY, lddy, true, W, ldw, false, dX, lddx, out_dtype, M, K, N, nullptr, CODAE_ACT_NONE, A_prev, lda};
+    Tc05Gemm g{dY, lddy, true, W, ldw, false, dX, lddx, out_dtype, M, K, N, nullptr, CODAE_ACT_NONE, A_prev, lda, true};
     return codae_tc05_gemm(ctx, g, as_stream(stream));
 }
 

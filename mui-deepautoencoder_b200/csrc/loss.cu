@@ -5,6 +5,7 @@
 namespace {
 
 constexpr int kLossThreads = 256;
+constexpr int kLossUnroll = 4;
 constexpr int kLossMaxGrid = 148 * 8 * 2;  // workspace is sized for this many CTA partials
 
 struct LossWs {
@@ -19,44 +20,77 @@ template <bool kBf16Y, bool kBf16Dy, bool kVec>
 __global__ void __launch_bounds__(kLossThreads) mse_loss_kernel(
     const float* __restrict__ x, int64_t ld_x, const int64_t* __restrict__ batch_idx, const void* __restrict__ y,
     int64_t ld_y, const int32_t* __restrict__ mask_id, const uint64_t* __restrict__ mask_bits,
-    const uint8_t* __restrict__ col_var, int B, int io, float grad_scale, void* __restrict__ dy, int64_t ld_dy,
+    const uint8_t* __restrict__ col_var, int B, int io, int log2g, float grad_scale, void* __restrict__ dy, int64_t ld_dy,
     double* __restrict__ acc, LossWs* __restrict__ ws) {
     pdl_launch_dependents();
     pdl_wait();
     float s_full = 0.f, s_part = 0.f;
     if (kVec) {
+        // a group of G = 2^log2g threads owns one row at a time (same schedule as corrupt_fwd_vec_kernel): per-row lookups
+        // once, the next row's lookups under the loads in flight, four independent 128-bit loads of x and y per thread
         const int io4 = io >> 2;
-        const int64_t total = (int64_t)B * io4;
-        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-            const int row = (int)(e / io4);
-            const int c = 4 * (int)(e - (int64_t)row * io4);
-            const int64_t obs = batch_idx ? batch_idx[row] : (int64_t)row;
-            const uint64_t bits = mask_bits[mask_id[row]];
-            const uchar4 var = *reinterpret_cast<const uchar4*>(col_var + c);
-            const float4 xv = ldg_stream_f4(x + obs * ld_x + c);
-            float4 yv;
-            if (kBf16Y) {
-                const uint2 p = ldg_stream_u2(reinterpret_cast<const __nv_bfloat16*>(y) + (int64_t)row * ld_y + c);
-                yv = make_float4(bf16_lo(p.x), bf16_hi(p.x), bf16_lo(p.y), bf16_hi(p.y));
-            } else {
-                yv = ldg_stream_f4(reinterpret_cast<const float*>(y) + (int64_t)row * ld_y + c);
-            }
-            const float d0 = yv.x - xv.x, d1 = yv.y - xv.y, d2 = yv.z - xv.z, d3 = yv.w - xv.w;
-            const float q0 = d0 * d0, q1 = d1 * d1, q2 = d2 * d2, q3 = d3 * d3;
-            s_full += (q0 + q1) + (q2 + q3);
-            s_part += ((1.f - keep_of(bits, var.x)) * q0 + (1.f - keep_of(bits, var.y)) * q1) +
-                      ((1.f - keep_of(bits, var.z)) * q2 + (1.f - keep_of(bits, var.w)) * q3);
-            if (dy) {
-                if (kBf16Dy) {
-                    uint2 p;
-                    p.x = pack_bf16x2(grad_scale * d0, grad_scale * d1);
-                    p.y = pack_bf16x2(grad_scale * d2, grad_scale * d3);
-                    stg_stream_u2(reinterpret_cast<__nv_bfloat16*>(dy) + (int64_t)row * ld_dy + c, p);
-                } else {
-                    stg_stream_f4(reinterpret_cast<float*>(dy) + (int64_t)row * ld_dy + c,
-                                  make_float4(grad_scale * d0, grad_scale * d1, grad_scale * d2, grad_scale * d3));
+        const int G = 1 << log2g, rows_per_cta = kLossThreads >> log2g;
+        const int gl = threadIdx.x & (G - 1);
+        const int row_stride = gridDim.x * rows_per_cta;
+        int row = blockIdx.x * rows_per_cta + (threadIdx.x >> log2g);
+        int64_t obs = 0;
+        uint64_t bits = 0;
+        if (row < B) {
+            obs = batch_idx ? batch_idx[row] : (int64_t)row;
+            bits = mask_bits[mask_id[row]];
+        }
+        for (; row < B; row += row_stride) {
+            const float* xrow = x + obs * ld_x;
+            int64_t n_obs = 0;
+            uint64_t n_bits = 0;
+            bool first_chunk = true;
+            for (int c0 = 0; c0 < io4; c0 += kLossUnroll * G) {
+                float4 xv[kLossUnroll], yv[kLossUnroll];
+#pragma unroll
+                for (int j = 0; j < kLossUnroll; ++j) {
+                    const int c = 4 * (c0 + gl + j * G);
+                    if (c < io) {
+                        xv[j] = ldg_stream_f4(xrow + c);
+                        if (kBf16Y) {
+                            const uint2 p = ldg_stream_u2(reinterpret_cast<const __nv_bfloat16*>(y) + (int64_t)row * ld_y + c);
+                            yv[j] = make_float4(bf16_lo(p.x), bf16_hi(p.x), bf16_lo(p.y), bf16_hi(p.y));
+                        } else {
+                            yv[j] = ldg_stream_f4(reinterpret_cast<const float*>(y) + (int64_t)row * ld_y + c);
+                        }
+                    }
+                }
+                if (first_chunk) {
+                    first_chunk = false;
+                    const int nrow = row + row_stride;
+                    if (nrow < B) {
+                        n_obs = batch_idx ? batch_idx[nrow] : (int64_t)nrow;
+                        n_bits = mask_bits[mask_id[nrow]];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < kLossUnroll; ++j) {
+                    const int c = 4 * (c0 + gl + j * G);
+                    if (c >= io) continue;
+                    const uchar4 var = *reinterpret_cast<const uchar4*>(col_var + c);
+                    const float d0 = yv[j].x - xv[j].x, d1 = yv[j].y - xv[j].y, d2 = yv[j].z - xv[j].z, d3 = yv[j].w - xv[j].w;
+                    const float q0 = d0 * d0, q1 = d1 * d1, q2 = d2 * d2, q3 = d3 * d3;
+                    s_full += (q0 + q1) + (q2 + q3);
+                    s_part += ((1.f - keep_of(bits, var.x)) * q0 + (1.f - keep_of(bits, var.y)) * q1) +
+                              ((1.f - keep_of(bits, var.z)) * q2 + (1.f - keep_of(bits, var.w)) * q3);
+                    if (dy) {
+                        if (kBf16Dy) {
+                            uint2 p;
+                            p.x = pack_bf16x2(grad_scale * d0, grad_scale * d1);
+                            p.y = pack_bf16x2(grad_scale * d2, grad_scale * d3);
+                            stg_stream_u2(reinterpret_cast<__nv_bfloat16*>(dy) + (int64_t)row * ld_dy + c, p);
+                        } else {
+                            stg_stream_f4(reinterpret_cast<float*>(dy) + (int64_t)row * ld_dy + c,
+                                          make_float4(grad_scale * d0, grad_scale * d1, grad_scale * d2, grad_scale * d3));
+                        }
+                    }
                 }
             }
+            obs = n_obs; bits = n_bits;
         }
     } else {
         const int64_t total = (int64_t)B * io;
@@ -268,8 +302,10 @@ int codae_mse_loss_fwd_bwd(codae_ctx* ctx, const float* x, int64_t ld_x, const i
                      ((reinterpret_cast<uintptr_t>(y) & (by ? 7 : 15)) == 0) &&
                      (!dy || (reinterpret_cast<uintptr_t>(dy) & (bd ? 7 : 15)) == 0) &&
                      ((reinterpret_cast<uintptr_t>(col_var) & 3) == 0);
-    const int64_t items = vec ? (int64_t)B * (io / 4) : (int64_t)B * io;
-    int64_t blocks = (items + kLossThreads * 4 - 1) / (kLossThreads * 4);
+    int log2g = 5;
+    while (log2g < 8 && (kLossUnroll << log2g) < io / 4) ++log2g;
+    const int rows_per_cta = kLossThreads >> log2g;
+    int64_t blocks = vec ? ((int64_t)B + rows_per_cta - 1) / rows_per_cta : ((int64_t)B * io + kLossThreads * 4 - 1) / (kLossThreads * 4);
     const int64_t cap = (int64_t)ctx->sm_count * 8;
     if (blocks > cap) blocks = cap;
     if (blocks > kLossMaxGrid) blocks = kLossMaxGrid;
@@ -278,7 +314,7 @@ int codae_mse_loss_fwd_bwd(codae_ctx* ctx, const float* x, int64_t ld_x, const i
     cudaStream_t s = as_stream(stream);
 #define LAUNCH(BY, BD, VEC)                                                                                         \
     launch_pdl(ctx, mse_loss_kernel<BY, BD, VEC>, dim3((unsigned)blocks), dim3(kLossThreads), 0, s, x, ld_x, batch_idx, y, ld_y, \
-               mask_id, mask_bits, col_var, B, io, grad_scale, dy, ld_dy, acc, ws)
+               mask_id, mask_bits, col_var, B, io, log2g, grad_scale, dy, ld_dy, acc, ws)
     if (vec) {
         if (by && bd) LAUNCH(true, true, true);
         else if (by) LAUNCH(true, false, true);

@@ -287,6 +287,7 @@ int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v
     if (n == 0) return CODAE_OK;
     launch_pdl(ctx, adam_kernel, dim3(grid_for(ctx, n >> 2, 2)), dim3(kThreads), 0, as_stream(stream), p, (const float*)g, m, v,
                reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a, sqnorm, step_dev);
+    codae_mark_weights_written(ctx, as_stream(stream));
     return codae_check_launch(ctx, "adam_kernel");
 }
 
@@ -343,6 +344,7 @@ int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, flo
         cudaGetLastError();
         return codae_fail(ctx, CODAE_ECUDA, "clip_adam_kernel cooperative launch (grid %d): %s", grid, cudaGetErrorString(le));
     }
+    codae_mark_weights_written(ctx, as_stream(stream));
     return codae_check_launch(ctx, "clip_adam_kernel");
 }
 
@@ -358,6 +360,7 @@ int codae_cast_bf16(codae_ctx* ctx, const float* src, void* dst, int64_t n, void
                   "codae_cast_bf16: misaligned buffers");
     if (n == 0) return CODAE_OK;
     cast_bf16_kernel<<<grid_for(ctx, n >> 2, 4), kThreads, 0, as_stream(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+    codae_mark_weights_written(ctx, as_stream(stream));
     return codae_check_launch(ctx, "cast_bf16_kernel");
 }
 

@@ -283,14 +283,17 @@ def test_full_size_step_vs_oracle(cfg, B, dtype, tol):
 
 def test_pdl_and_splitk_switches_do_not_change_results():
     """Programmatic dependent launch and cluster split-K are scheduling choices: with either switched off the captured
-    step gives the same loss (split-K changes fp32 summation order only; PDL must be bit-identical)."""
+    step gives the same loss (split-K changes fp32 summation order only; PDL and the early weight-tile requests must be
+    bit-identical)."""
     from codae import _C
     from codae.tool import FusedStep
     g = np.load(os.path.join(GOLDEN, "emb_mid.npz"))
     results = {}
-    for name, (pdl, splitk) in {"on": (1, 1), "no_pdl": (0, 1), "no_splitk": (1, 0)}.items():
+    for name, (pdl, splitk, prefetch) in {"on": (1, 1, 1), "no_pdl": (0, 1, 1), "no_splitk": (1, 0, 1),
+                                          "no_prefetch": (1, 1, 0)}.items():
         _C.set_option(DEV, _C.OPT_PDL, pdl)
         _C.set_option(DEV, _C.OPT_SPLITK, splitk)
+        _C.set_option(DEV, _C.OPT_WEIGHT_PREFETCH, prefetch)
         try:
             ds, model, cor = build_embedding(g, dtype="bf16")
             fs = FusedStep(model, cor, ds.data, lr=float(g["lr"]), weight_decay=float(g["wd"]), clip=True, use_graph=True)
@@ -301,7 +304,10 @@ def test_pdl_and_splitk_switches_do_not_change_results():
         finally:
             _C.set_option(DEV, _C.OPT_PDL, 1)
             _C.set_option(DEV, _C.OPT_SPLITK, 1)
+            _C.set_option(DEV, _C.OPT_WEIGHT_PREFETCH, 1)
     assert results["on"][0] == results["no_pdl"][0] and np.array_equal(results["on"][1], results["no_pdl"][1])
+    # weight tiles requested ahead of the stream dependency must never see weights of the previous step
+    assert results["on"][0] == results["no_prefetch"][0] and np.array_equal(results["on"][1], results["no_prefetch"][1])
     assert abs(results["on"][0] - results["no_splitk"][0]) <= 1e-3 * abs(results["on"][0])
 
 
