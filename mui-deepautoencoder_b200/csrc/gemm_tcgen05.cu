@@ -54,6 +54,7 @@ struct Params {
     int stages;                  // pipeline depth actually used (<= Cfg::kStages)
     int staged;                  // 1: epilogue through the shared-memory tile (required when gridDim.z > 1)
     int prefetch_b;              // 1: B holds weights no running predecessor writes: fetch its first tiles before the PDL wait
+    int group_m;                 // persistent kernel: row-tiles per raster group
     unsigned long long* trace;   // debugging: CTA (0,0,0) writes %globaltimer stamps of its phases here (or NULL)
 };
 
@@ -480,16 +481,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
 // The accumulator is double-buffered in TMEM (2 x BN columns): while the epilogue warps drain tile i (tcgen05.ld, fused
 // epilogue, stores), the MMA warp already accumulates tile i+1 and the producer keeps the shared-memory ring full across
 // tile boundaries.  Tiles are walked m-fastest so that concurrently running CTAs share the same weight tile in L2.
-// Tile order of the persistent kernel: groups of kGroupM row-tiles; inside a group all column-tiles of one row-tile
-// column are adjacent (m fastest).  The ~148 tiles in flight then span kGroupM x ~9 tiles: every operand tile is shared by
+// Tile order of the persistent kernel: groups of group_m (16) row-tiles; inside a group all column-tiles of one row-tile
+// column are adjacent (m fastest).  The ~148 tiles in flight then span group_m x ~9 tiles: every operand tile is shared by
 // many concurrent CTAs and the working set (tens of MB) stays in L2.  (Plain m-fastest order re-streamed the whole 67 MB
 // activation matrix for every pair of column tiles: ncu showed 350-530 MB of DRAM reads for 100-135 MB of operands.)
-constexpr int kGroupM = 16;
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& m_idx, int& n_idx) {
-    const int per_group = kGroupM * tiles_n;
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& m_idx, int& n_idx) {
+    const int per_group = group_m * tiles_n;
     const int g = t / per_group, r = t - g * per_group;
-    const int gm = min(kGroupM, tiles_m - g * kGroupM);
-    m_idx = g * kGroupM + r % gm;
+    const int gm = min(group_m, tiles_m - g * group_m);
+    m_idx = g * group_m + r % gm;
     n_idx = r / gm;
 }
 
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
             uint32_t ph = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 int m_idx, n_idx;
-                tile_coords(t, tiles_m, tiles_n, m_idx, n_idx);
+                tile_coords(t, tiles_m, tiles_n, p.group_m, m_idx, n_idx);
                 const int m0 = m_idx * BM, n0 = n_idx * BN;
                 for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == kS ? 0 : s + 1), ph ^= (s == 0)) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
             int it = 0;
             for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
                 int m_idx, n_idx;
-                tile_coords(t, tiles_m, tiles_n, m_idx, n_idx);
+                tile_coords(t, tiles_m, tiles_n, p.group_m, m_idx, n_idx);
                 // a ragged last column tile (the bias column of the augmented weight gradient: 1 of 256 columns) only
                 // pays for the MMA width it needs (multiples of 16)
                 const int n_eff = min(BN, ((p.N - n_idx * BN) + 15) & ~15);
@@ -601,7 +601,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
             const int acc = it & 1;
             const uint32_t acc_ph = (it >> 1) & 1;
             int m_idx, n_idx;
-            tile_coords(t, tiles_m, tiles_n, m_idx, n_idx);
+            tile_coords(t, tiles_m, tiles_n, p.group_m, m_idx, n_idx);
             const int m0 = m_idx * BM, n0 = n_idx * BN;
             mbar_wait(&tmem_full_bar[acc], acc_ph);
             tc_fence_after();
@@ -694,6 +694,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     p.trace = g_trace_buf;
     p.staged = (nsplit > 1 || (g.c_dtype == CODAE_F32 && tiles <= 2 * ctx->sm_count)) ? 1 : 0;
     p.prefetch_b = (g.b_is_weight && ctx->pdl && ctx->weight_prefetch) ? 1 : 0;
+    p.group_m = 16;
     if (nsplit == 1 && !p.staged && ctx->persistent && tiles > 2 * ctx->sm_count) {
         static bool pattr_set = false;
         if (!pattr_set) {
@@ -701,6 +702,14 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
             if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaFuncSetAttribute(smem=%u): %s", C::kSmemBytes, cudaGetErrorString(e));
             pattr_set = true;
         }
+        // raster group: 16 row-tiles measured best on the 4096-wide step (8: 7.48, 16: 7.14, 32: 7.33, 64: 7.43 ms/step);
+        // CODAE_GROUP_M overrides it for tuning runs (read once)
+        static int env_group_m = -1;
+        if (env_group_m < 0) {
+            const char* e = getenv("CODAE_GROUP_M");
+            env_group_m = (e && atoi(e) > 0) ? atoi(e) : 16;
+        }
+        p.group_m = env_group_m;
         p.stages = C::kStages;
         cudaError_t le = launch_pdl(ctx, tc05_gemm_persistent_kernel<BN>, dim3(ctx->sm_count), dim3(kThreads), C::kSmemBytes, s, ma, mb, p);
         if (le != cudaSuccess) {
