@@ -547,7 +547,8 @@ def profile_step(fs, idx, B, world):
     # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture (profiles/r01_ncu_full_
     # metrics.txt); null when no capture exists for this workload / engine.
     measured_traffic = {("tc05", 1536, True): 5.65e6 * 19 / 29 + 0.85e6 * 10 / 29,     # fwd/dgrad 5.65 MB, wgrad 0.85 MB read
-                        ("tc05", 4096, False): (104.5e6 + 50e6 + 2 * (348e6 + 60e6)) / 3}
+                        # 4096-wide persistent GEMMs: fwd 166 + 98, dgrad 240 + 52, wgrad 294 + 50 MB (read + write)
+                        ("tc05", 4096, False): (10 * 264e6 + 9 * 292e6 + 10 * 344e6) / 29}
     key = ("tc05" if bf else "simt", io, small)
     if roof.get("kernel", "").startswith("tc05") and key in measured_traffic:
         roof["traffic"] = measured_traffic[key]

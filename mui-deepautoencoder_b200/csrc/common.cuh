@@ -74,6 +74,18 @@ inline cudaError_t launch_pdl(const codae_ctx* ctx, void (*kernel)(KArgs...), di
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+// Resident CTAs per SM of a kernel (register / shared-memory limited): grid-stride kernels are launched as ONE resident wave,
+// a larger grid only adds a partial last wave.
+template <typename K>
+inline int resident_ctas_per_sm(K kernel, int threads, size_t smem) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        n = 1;
+    }
+    return n;
+}
+
 // ---- device helpers ---------------------------------------------------------------------------
 // No-ops when the grid was not launched as a programmatic dependent.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -216,8 +216,14 @@ int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t ld_data, const 
         int log2g = 5;
         while (log2g < 8 && (kRowUnroll << log2g) < io / 4) ++log2g;
         const int rows_per_cta = 256 >> log2g;
+        static int occ_bf = 0, occ_f32 = 0;
+        if (!occ_bf) {
+            occ_bf = resident_ctas_per_sm(corrupt_fwd_vec_kernel<true>, 256, 0);
+            occ_f32 = resident_ctas_per_sm(corrupt_fwd_vec_kernel<false>, 256, 0);
+        }
         int g = (B + rows_per_cta - 1) / rows_per_cta;
-        if (g > ctx->sm_count * 8) g = ctx->sm_count * 8;
+        const int cap = ctx->sm_count * (bf ? occ_bf : occ_f32);
+        if (g > cap) g = cap;
         if (bf) launch_pdl(ctx, corrupt_fwd_vec_kernel<true>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
         else launch_pdl(ctx, corrupt_fwd_vec_kernel<false>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
     } else {

@@ -313,8 +313,13 @@ int codae_mse_loss_fwd_bwd(codae_ctx* ctx, const float* x, int64_t ld_x, const i
     LossWs* ws = reinterpret_cast<LossWs*>(workspace);
     cudaStream_t s = as_stream(stream);
 #define LAUNCH(BY, BD, VEC)                                                                                         \
-    launch_pdl(ctx, mse_loss_kernel<BY, BD, VEC>, dim3((unsigned)blocks), dim3(kLossThreads), 0, s, x, ld_x, batch_idx, y, ld_y, \
-               mask_id, mask_bits, col_var, B, io, log2g, grad_scale, dy, ld_dy, acc, ws)
+    do {                                                                                                            \
+        static int occ = 0;                                                                                         \
+        if (!occ) occ = resident_ctas_per_sm(mse_loss_kernel<BY, BD, VEC>, kLossThreads, 0);                        \
+        if (blocks > (int64_t)ctx->sm_count * occ) blocks = (int64_t)ctx->sm_count * occ;   /* one resident wave */ \
+        launch_pdl(ctx, mse_loss_kernel<BY, BD, VEC>, dim3((unsigned)blocks), dim3(kLossThreads), 0, s, x, ld_x, batch_idx, y, \
+                   ld_y, mask_id, mask_bits, col_var, B, io, log2g, grad_scale, dy, ld_dy, acc, ws);                \
+    } while (0)
     if (vec) {
         if (by && bd) LAUNCH(true, true, true);
         else if (by) LAUNCH(true, false, true);

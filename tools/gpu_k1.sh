@@ -7,9 +7,10 @@ run_pytest kernels tests/test_gpu_kernels.py 8
 run_pytest training tests/test_gpu_training.py 8
 timeout -s KILL 300 python bench.py --no-cpu --no-scoring --no-fp32 > gpurun_out/bench_k1_default.json 2> gpurun_out/bench_k1_default.err; echo "bench default rc=$?"; tail -2 gpurun_out/bench_k1_default.err
 timeout -s KILL 400 python bench.py --workload polyvore --steps 10 --warmup 3 --no-cpu --no-scoring > gpurun_out/bench_k1_polyvore.json 2> gpurun_out/bench_k1_polyvore.err; echo "bench polyvore rc=$?"; tail -2 gpurun_out/bench_k1_polyvore.err
+timeout -s KILL 300 python bench.py --workload modanet --no-cpu --no-scoring --no-fp32 > gpurun_out/bench_k1_modanet.json 2> gpurun_out/bench_k1_modanet.err; echo "bench modanet rc=$?"; tail -2 gpurun_out/bench_k1_modanet.err
 python - <<'PY'
 import json
-for f in ["bench_k1_default.json","bench_k1_polyvore.json"]:
+for f in ["bench_k1_default.json","bench_k1_modanet.json","bench_k1_polyvore.json"]:
     try: d=json.loads(open("gpurun_out/"+f).read().strip().splitlines()[-1])
     except Exception as e: print(f,"ERR",e); continue
     print("==",f,"value %.0f ms/step %.4f e2e %.0f"%(d["value"],d["ms_per_step"],d["e2e"]["value"]))
