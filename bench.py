@@ -180,6 +180,8 @@ def main():
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch without programmatic dependent launch")
     ap.add_argument("--no-splitk", action="store_true", help="A/B: single-pass small-batch contractions")
     ap.add_argument("--no-persistent", action="store_true", help="A/B: one tile per CTA for the large contractions")
+    ap.add_argument("--wgrad-sqnorm", action="store_true",
+                    help="A/B (1 GPU): weight-gradient kernels leave sum(dW^2) behind, Adam takes the clip scale from those partials")
     ap.add_argument("--catalog", type=int, default=10_000_000)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -244,7 +246,7 @@ def main():
     model.to(dev)
     cor = Corrupter(w["N"], ds.arch, w["k_max"], dev, seed=w["seed"])
     fs = FusedStep(model, cor, data, lr=w["lr"], weight_decay=w["wd"], clip=w["clip"], world_size=world,
-                   use_graph=not args.no_graph)
+                   use_graph=not args.no_graph, wgrad_sqnorm=args.wgrad_sqnorm and world == 1 and dtype == "bf16")
     rng = np.random.RandomState(w["seed"] + rank)
     nb = Wm + K
     batches = torch.from_numpy(rng.randint(0, w["N"], size=(nb, B))).to(dev)
@@ -445,7 +447,7 @@ def profile_step(fs, idx, B, world):
     model = fs.model
     dims = model.dims
     wrapped = ["corrupt_fwd", "linear_fwd", "mse_loss_fwd_bwd", "linear_wgrad", "linear_dgrad", "grad_sqnorm", "counter_add", "adam_step",
-               "clip_adam_step"]
+               "clip_adam_step", "linear_wgrad_sq", "adam_step_partials"]
     orig = {n: getattr(_C, n) for n in wrapped}
     calls = {n: [] for n in wrapped}
 
@@ -505,6 +507,7 @@ def profile_step(fs, idx, B, world):
     algo = {  # name: (bound, algorithmic bytes or flops per STEP, unit note)
         "adam_step": ("hbm", (28 + (2 if bf else 0)) * P),
         "clip_adam_step": ("hbm", (32 + (2 if bf else 0)) * P),
+        "adam_step_partials": ("hbm", (28 + (2 if bf else 0)) * P),
         "grad_sqnorm": ("hbm", 4 * P),
         "corrupt_fwd": ("hbm", B * io * (4 + sw)),
         "mse_loss_fwd_bwd": ("hbm", B * io * (4 + 4 + sw)),
@@ -512,6 +515,7 @@ def profile_step(fs, idx, B, world):
         "linear_dgrad": ("hbm", (Wsum - W1) * sw + B * act * sw) if small else ("tensor", 2.0 * B * (Wsum - W1)),
         "linear_wgrad": ("hbm", Wsum * 4 + B * act * sw) if small else ("tensor", 2.0 * B * Wsum),
     }
+    algo["linear_wgrad_sq"] = algo["linear_wgrad"]
     tensor_peak = pk["tensor_sustained"] if bf else pk["tensor_sustained"] / 2
     rooflines = {}
     for n, (bound, work) in algo.items():
@@ -526,7 +530,7 @@ def profile_step(fs, idx, B, world):
                         "kernel": n, "share_of_step": kernels[n]["share"], "peak_source": pk["src"],
                         "algorithmic_per_launch": work / kernels[n]["launches_per_step"]}
     # the dominant KERNEL: the three contractions are one kernel (tc05_gemm_kernel / simt_gemm_kernel)
-    gemm = [n for n in ("linear_fwd", "linear_dgrad", "linear_wgrad") if n in kernels]
+    gemm = [n for n in ("linear_fwd", "linear_dgrad", "linear_wgrad", "linear_wgrad_sq") if n in kernels]
     gemm_ms = sum(kernels[n]["ms_per_step"] for n in gemm)
     others = {n: kernels[n]["ms_per_step"] for n in rooflines if n not in gemm}
     top_other = max(others, key=others.get)

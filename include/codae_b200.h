@@ -154,6 +154,17 @@ int codae_linear_dgrad(codae_ctx* ctx, const void* dY, int64_t lddy, const void*
  * The weight/bias gradient of nn.Linear in loss.backward().                                           */
 int codae_linear_wgrad(codae_ctx* ctx, const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW,
                        int64_t lddw, float* db, int M, int N, int K, int dtype, void* stream);
+/* codae_linear_wgrad on the tensor-core engine that also leaves sum(dW^2) behind, so that clip_grad_norm_
+ * (train_dae_on_embedding.py:212-213) needs no pass of its own over the gradients on a single GPU: every CTA of the
+ * launch writes the sum of squares of the gradient elements it stored into sq_partials[cta] (double, fixed reduction
+ * tree).  n_slots must equal codae_linear_wgrad_sq_slots(ctx, M, N, K, dtype) -- the number of CTAs the launch has under
+ * the context's current options; 0 means the engine for that shape cannot do it (use codae_linear_wgrad and
+ * codae_clip_adam_step).  The bias gradient is the constant-1 column of the augmented contraction (no db argument).
+ * Consumer: codae_adam_step_partials. */
+int codae_linear_wgrad_sq_slots(const codae_ctx* ctx, int M, int N, int K, int dtype);
+int codae_linear_wgrad_sq(codae_ctx* ctx, const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW,
+                          int64_t lddw, int M, int N, int K, int dtype, double* sq_partials, int n_slots,
+                          void* stream);
 /* f32 -> bf16 copy of n elements (weight shadow / activation cast). */
 int codae_cast_bf16(codae_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
 
@@ -181,6 +192,14 @@ int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, flo
                          double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
                          float* sqnorm_out, void* workspace, size_t ws_bytes, double grad_scale, const int32_t* step_dev,
                          void* stream);
+/* codae_clip_adam_step without the norm pass: sum g^2 = the sum of `n_partials` doubles written by the
+ * codae_linear_wgrad_sq launches of this step (summed in index order by every CTA: reproducible).  Same arithmetic
+ * and argument meaning otherwise; sqnorm_out (f32[1]) receives the sum.  Not for data-parallel runs (the norm must
+ * be taken after the gradient all-reduce). */
+int codae_adam_step_partials(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
+                             double lr, double beta1, double beta2, double eps, double weight_decay, int step,
+                             double max_norm, const double* sq_partials, int n_partials, float* sqnorm_out,
+                             double grad_scale, const int32_t* step_dev, void* stream);
 /* *counter += delta on the device (the Adam step counter of a CUDA-graph-captured training step). */
 int codae_counter_add(codae_ctx* ctx, int32_t* counter, int delta, void* stream);
 

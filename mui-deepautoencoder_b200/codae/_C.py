@@ -43,11 +43,14 @@ SIGNATURES = {
     "codae_linear_fwd": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _vp]),
     "codae_linear_dgrad": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "codae_linear_wgrad": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
+    "codae_linear_wgrad_sq_slots": (_i, [_vp, _i, _i, _i, _i]),
+    "codae_linear_wgrad_sq": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp]),
     "codae_cast_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "codae_sqnorm_workspace_bytes": (_sz, [_vp]),
     "codae_grad_sqnorm": (_i, [_vp, _vp, _i64, _vp, _vp, _sz, _vp]),
     "codae_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _d, _vp, _vp]),
     "codae_clip_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _vp, _sz, _d, _vp, _vp]),
+    "codae_adam_step_partials": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _i, _vp, _d, _vp, _vp]),
     "codae_counter_add": (_i, [_vp, _vp, _i, _vp]),
     "codae_score_topk_workspace_bytes": (_sz, [_vp, _i, _i]),
     "codae_score_topk": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
@@ -232,6 +235,16 @@ def linear_wgrad(dY, X, dW, db, M, N, K, dtype):
                                    stream()), c)
 
 
+def linear_wgrad_sq_slots(device, M, N, K, dtype):
+    return int(lib().codae_linear_wgrad_sq_slots(ctx(device), M, N, K, dtype))
+
+
+def linear_wgrad_sq(dY, X, dW, M, N, K, dtype, sq_partials):
+    c = ctx(dY.device)
+    check(lib().codae_linear_wgrad_sq(c, p(dY), dY.stride(0), p(X), X.stride(0), p(dW), dW.stride(0), M, N, K, dtype,
+                                      p(sq_partials), sq_partials.numel(), stream()), c)
+
+
 def cast_bf16(src, dst):
     c = ctx(src.device)
     check(lib().codae_cast_bf16(c, p(src), p(dst), src.numel(), stream()), c)
@@ -257,6 +270,14 @@ def clip_adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_nor
     c = ctx(pf.device)
     check(lib().codae_clip_adam_step(c, p(pf), p(g), p(m), p(v), p(p_bf16), pf.numel(), lr, beta1, beta2, eps, wd, step, max_norm,
                                      p(sqnorm_out), p(ws), ws.numel(), grad_scale, p(step_dev), stream()), c)
+
+
+def adam_step_partials(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sq_partials, sqnorm_out, grad_scale,
+                       step_dev=None):
+    c = ctx(pf.device)
+    check(lib().codae_adam_step_partials(c, p(pf), p(g), p(m), p(v), p(p_bf16), pf.numel(), lr, beta1, beta2, eps, wd, step,
+                                         max_norm, p(sq_partials), sq_partials.numel(), p(sqnorm_out), grad_scale,
+                                         p(step_dev), stream()), c)
 
 
 def counter_add(counter, delta):

@@ -10,7 +10,9 @@ Replaces, per step (script/train_dae_on_embedding.py:198-223; script/train_dae_o
   [data parallel]          -> NCCL all-reduce of the flat gradient buffer, issued per layer on a communication stream
                               as soon as that layer's wgrad has finished (overlaps the rest of the backward pass)
   clip_grad_norm_ + Adam   -> codae_clip_adam_step: one cooperative launch over the flat buffers (norm, grid barrier,
-                              update); or codae_grad_sqnorm + codae_adam_step
+                              update); or codae_grad_sqnorm + codae_adam_step; or (wgrad_sqnorm=True, single GPU,
+                              tensor-core engine) codae_linear_wgrad_sq + codae_adam_step_partials: the weight-gradient
+                              kernels leave sum(dW^2) behind and the optimizer never reads g for the norm
 No host synchronisation happens inside a step; monitors stay on the device until read_monitors().
 The whole sequence can be captured once per batch size into a CUDA graph (use_graph=True).
 """
@@ -30,7 +32,7 @@ class FusedStep:
 
     def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True,
-                 fused_clip_adam=True):
+                 fused_clip_adam=True, wgrad_sqnorm=False):
         """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
         tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
         {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
@@ -47,6 +49,7 @@ class FusedStep:
         self.mixed = mixed
         self.overlap_allreduce = overlap_allreduce
         self.fused_clip_adam = fused_clip_adam
+        self.wgrad_sqnorm = wgrad_sqnorm
         dev = model.flat.device
         self.dev = dev
         self.io = model.dims[0][0]
@@ -79,6 +82,9 @@ class FusedStep:
             lin.bias.grad = model.bias_view(self.gflat, l)
         lay, total = model.layout()
         self._layer_span = [(lay[l][0], lay[l + 1][0] if l + 1 < len(lay) else total) for l in range(len(lay))]
+        if self.wgrad_sqnorm and (world_size > 1 or self.eng != _C.BF16):
+            raise RuntimeError("codae: wgrad_sqnorm needs a single GPU (the norm of a data-parallel run is taken after the "
+                               "all-reduce) and the tensor-core engine")
         self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
         self._wgrad_stream = torch.cuda.Stream(device=dev)
         self._bufs = {}
@@ -105,6 +111,16 @@ class FusedStep:
                      idx=torch.zeros(B, dtype=torch.int64, device=dev),
                      x=torch.zeros((B, wmax), dtype=torch.float32, device=dev) if self.mixed is not None else None,
                      mon=torch.zeros((B, len(self.mixed["arch"])), dtype=torch.float32, device=dev) if self.mixed is not None else None)
+            if self.wgrad_sqnorm:
+                # one slot per CTA of every weight-gradient launch of this batch size
+                slots = [_C.linear_wgrad_sq_slots(dev, B, o, _round_up(i, 8) + 1, self.eng) for i, o in dims]
+                if min(slots) < 1:
+                    raise RuntimeError("codae: wgrad_sqnorm: the tensor-core engine cannot tile every layer of this model")
+                offs = [0]
+                for c in slots:
+                    offs.append(offs[-1] + c)
+                b["sq_off"] = offs
+                b["sq_partials"] = torch.zeros(offs[-1], dtype=torch.float64, device=dev)
             self._bufs[B] = b
         return b
 
@@ -158,7 +174,12 @@ class FusedStep:
                 ready.record(main)                      # dL/d(out_l) has been produced (loss or dgrad(l+1))
                 side.wait_event(ready)
             with torch.cuda.stream(side):
-                _C.linear_wgrad(gl, acts[l], model.aug_view(self.gflat, l), None, B, o, _round_up(i, 8) + 1, eng); n += 1
+                if self.wgrad_sqnorm:
+                    sq = b["sq_partials"][b["sq_off"][l]:b["sq_off"][l + 1]]
+                    _C.linear_wgrad_sq(gl, acts[l], model.aug_view(self.gflat, l), B, o, _round_up(i, 8) + 1, eng, sq)
+                else:
+                    _C.linear_wgrad(gl, acts[l], model.aug_view(self.gflat, l), None, B, o, _round_up(i, 8) + 1, eng)
+                n += 1
                 wdone[l] = torch.cuda.Event()
                 wdone[l].record(side)
             if overlap_comm:
@@ -187,16 +208,21 @@ class FusedStep:
         elif self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
-        n += self._enqueue_update()
+        n += self._enqueue_update(b.get("sq_partials"))
         return n
 
-    def _enqueue_update(self):
+    def _enqueue_update(self, sq_partials=None):
         """Step counter + clip + Adam over the flat buffers (after the gradients are final)."""
         model, eng = self.model, self.eng
         n = 0
         _C.counter_add(self.step_dev, 1); n += 1
         pb = model.flat_bf16 if eng == _C.BF16 else None
-        if self.fused_clip_adam:
+        if sq_partials is not None:
+            # the weight-gradient launches of this step left sum(dW^2) per CTA: no norm pass, no grid barrier
+            _C.adam_step_partials(model.flat, self.gflat, self.m, self.v, pb, self.lr, self.betas[0], self.betas[1], self.eps,
+                                  self.wd, 0, self.max_norm if self.clip else -1.0, sq_partials, self.sqnorm, 1.0,
+                                  self.step_dev); n += 1
+        elif self.fused_clip_adam:
             # ||g||^2, clip scale and Adam in one cooperative launch (the second read of g comes from L2).  Also without
             # clipping (max_norm < 0 -> scale 1): inside the step it measured faster than the plain Adam kernel
             # (modanet: 0.305 vs 0.319 ms/step) and the gradient norm comes out as a monitor.

@@ -21,6 +21,10 @@ struct Tc05Gemm {
     const float* bias; int act;                  // bias[n] + activation (fwd)
     const void* mask_src; int64_t ldm;           // bf16 [M, ldm]: C *= (mask_src > 0) (dgrad)
     bool b_is_weight = false;                    // B holds layer weights: its tiles may be fetched ahead of the stream dependency
+    double* sq_partial = nullptr;                // f32 outputs: every CTA writes the sum of squares of what it stored into its slot
+    int sq_slots = 0;                            // must equal codae_tc05_gemm_ctas(ctx, g)
 };
 bool codae_tc05_supported(const codae_ctx* ctx, const Tc05Gemm& g);
 int codae_tc05_gemm(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s);
+// CTAs codae_tc05_gemm launches for this shape under the context's current options (0: shape not supported).
+int codae_tc05_gemm_ctas(const codae_ctx* ctx, const Tc05Gemm& g);

@@ -55,6 +55,7 @@ struct Params {
     int staged;                  // 1: epilogue through the shared-memory tile (required when gridDim.z > 1)
     int prefetch_b;              // 1: B holds weights no running predecessor writes: fetch its first tiles before the PDL wait
     int group_m;                 // persistent kernel: row-tiles per raster group
+    double* sq_partial;          // f32 outputs only: slot [linear CTA id] receives the sum of squares of what this CTA stored (or NULL)
     unsigned long long* trace;   // debugging: CTA (0,0,0) writes %globaltimer stamps of its phases here (or NULL)
 };
 
@@ -162,6 +163,24 @@ __device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
     }
 }
 
+// Sum of squares of the stored outputs (the weight-gradient norm of clip_grad_norm_, taken while the gradient tile is
+// still in registers): the four epilogue warps combine their per-thread sums with a fixed tree and thread 64 writes the
+// CTA's slot.  Called by all 128 epilogue threads (warps 2..5); named barrier 1.
+__device__ __forceinline__ void sq_partial_store(double* slot, double sq, double* red) {
+    const int lane = threadIdx.x & 31, w = (threadIdx.x >> 5) - 2;
+    sq = warp_sum(sq);
+    if (lane == 0) red[w] = sq;
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) *slot = (red[0] + red[1]) + (red[2] + red[3]);
+}
+template <int W>
+__device__ __forceinline__ float chunk_sq(const float (&f)[W], int col0, int n) {
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < W; ++j) if (col0 + j < n) s = fmaf(f[j], f[j], s);
+    return s;
+}
+
 // Shared-memory matrix descriptor (sm_100 format: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout SWIZZLE_128B=2 [61,64)).
 //   K-major tile  [rows][64 elems]: 8-row swizzle atoms 1024 B apart (SBO); LBO unused (=1).
@@ -252,6 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     uint64_t* tmem_full_bar = empty_bar + nstages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
     constexpr int kStagePitch = BN + 4;               // floats per row of the staged fp32 tile
+    __shared__ double sq_red[4];
+    double sq_acc = 0.0;                              // epilogue threads: sum of squares of the values this thread stored
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -368,6 +389,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 store_chunk<32>(p, row, col0, f);
+                if (p.sq_partial) sq_acc += (double)chunk_sq<32>(f, col0, p.N);
             } else {
                 // row pitch BN+4 floats: the 8 lanes of a 128-bit store phase hit 8 distinct 16-byte bank groups
                 float4* dst = reinterpret_cast<float4*>(stage_row + c * 32);
@@ -437,6 +459,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                         for (int j = 0; j < 4; ++j) if (col + j < p.N && !(__bfloat162float(mrow[j]) > 0.f)) f[j] = 0.f;
                     }
                 }
+                if (p.sq_partial) sq_acc += (double)chunk_sq<4>(f, col, p.N);
                 if (p.c_bf16) {
                     __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col;
                     if (full) {
@@ -463,6 +486,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         if (nsplit > 1) cluster_sync();                      // peers may still be reading this CTA's tile
         if (threadIdx.x == 64) trace_stamp(p, 9);                  // cluster barrier 2 passed
     }
+    if (p.sq_partial && warp >= 2)
+        sq_partial_store(p.sq_partial + ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x, sq_acc, sq_red);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -506,6 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
     uint64_t* tmem_full_bar = empty_bar + kS;          // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    __shared__ double sq_red[4];
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -597,6 +623,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
         // ===== epilogue warps: drain buffer i & 1 while the MMA warp fills the other one =====
         const int q = warp & 3;
         int it = 0;
+        double sq_acc = 0.0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_ph = (it >> 1) & 1;
@@ -624,8 +651,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 store_chunk<32>(p, row, col0, f);
+                if (p.sq_partial) sq_acc += (double)chunk_sq<32>(f, col0, p.N);
             }
         }
+        if (p.sq_partial) sq_partial_store(p.sq_partial + blockIdx.x, sq_acc, sq_red);
     }
     tc_fence_before();
     __syncthreads();
@@ -657,9 +686,49 @@ int make_map(codae_ctx* ctx, CUtensorMap* map, const void* base, long long rows,
     return CODAE_OK;
 }
 
+// Launch shape of one contraction, decided up front (also reported by codae_tc05_gemm_ctas).
+struct Plan {
+    int nsplit;        // cluster split-K factor (grid z)
+    bool staged;       // epilogue through the shared-memory tile
+    bool persistent;   // one CTA per SM walking tiles
+    int gx, gy;        // output tiles along N and M
+    int ctas;          // CTAs the launch will have (= sum-of-squares slots it writes)
+};
+template <int BN>
+Plan make_plan(const codae_ctx* ctx, const Tc05Gemm& g) {
+    Plan pl;
+    pl.gx = (g.N + BN - 1) / BN;
+    pl.gy = (g.M + BM - 1) / BM;
+    // split-K over a thread-block cluster (see the header comment): only when the tiles alone would leave most SMs
+    // idle and every split still gets at least 2 k-blocks.
+    const int tiles = pl.gx * pl.gy;
+    const int total_kb = (g.K + BK - 1) / BK;
+    int nsplit = 1;
+    if (ctx->splitk && 2 * tiles <= ctx->sm_count && total_kb >= 8) {
+        int want = ctx->sm_count / tiles;
+        if (want > total_kb / 2) want = total_kb / 2;
+        if (want > kMaxSplit) want = kMaxSplit;
+        if (want > 1) {
+            const int kb_per = (total_kb + want - 1) / want;
+            nsplit = (total_kb + kb_per - 1) / kb_per;               // no empty split
+        }
+    }
+    pl.nsplit = nsplit;
+    // staged (coalesced) epilogue: always for split-K; for fp32 outputs only while the grid is at most ~2 waves
+    // (measured: the direct epilogue is faster for the 4096-wide weight gradients, 247 vs 261 us)
+    pl.staged = nsplit > 1 || (g.c_dtype == CODAE_F32 && tiles <= 2 * ctx->sm_count);
+    pl.persistent = nsplit == 1 && !pl.staged && ctx->persistent && tiles > 2 * ctx->sm_count;
+    pl.ctas = pl.persistent ? ctx->sm_count : tiles * nsplit;
+    return pl;
+}
+
 template <int BN>
 int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     using C = Cfg<BN>;
+    const Plan pl = make_plan<BN>(ctx, g);
+    if (g.sq_partial && (g.c_dtype != CODAE_F32 || g.sq_slots != pl.ctas))
+        return codae_fail(ctx, CODAE_EINVAL, "codae_tc05_gemm: %d sum-of-squares slots passed, this launch writes %d (f32 outputs only)",
+                          g.sq_slots, pl.ctas);
     CUtensorMap ma, mb;
     int rc;
     // A(m,k): K-major storage [M rows, K cols]; MN-major storage [K rows, M cols]
@@ -675,27 +744,14 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_dtype == CODAE_BF16;
     p.bias = g.bias; p.act = g.act;
     p.mask_src = reinterpret_cast<const __nv_bfloat16*>(g.mask_src); p.ldm = g.ldm;
-    // split-K over a thread-block cluster (see the header comment): only when the tiles alone would leave most SMs
-    // idle and every split still gets at least 2 k-blocks.
-    const int tiles = ((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM);
+    p.sq_partial = g.sq_partial;
     const int total_kb = (g.K + BK - 1) / BK;
-    int nsplit = 1;
-    if (ctx->splitk && 2 * tiles <= ctx->sm_count && total_kb >= 8) {
-        int want = ctx->sm_count / tiles;
-        if (want > total_kb / 2) want = total_kb / 2;
-        if (want > kMaxSplit) want = kMaxSplit;
-        if (want > 1) {
-            const int kb_per = (total_kb + want - 1) / want;
-            nsplit = (total_kb + kb_per - 1) / kb_per;               // no empty split
-        }
-    }
-    // staged (coalesced) epilogue: always for split-K; for fp32 outputs only while the grid is at most ~2 waves
-    // (measured: the direct epilogue is faster for the 4096-wide weight gradients, 247 vs 261 us)
+    const int nsplit = pl.nsplit;
     p.trace = g_trace_buf;
-    p.staged = (nsplit > 1 || (g.c_dtype == CODAE_F32 && tiles <= 2 * ctx->sm_count)) ? 1 : 0;
+    p.staged = pl.staged ? 1 : 0;
     p.prefetch_b = (g.b_is_weight && ctx->pdl && ctx->weight_prefetch) ? 1 : 0;
     p.group_m = 16;
-    if (nsplit == 1 && !p.staged && ctx->persistent && tiles > 2 * ctx->sm_count) {
+    if (pl.persistent) {
         static bool pattr_set = false;
         if (!pattr_set) {
             cudaError_t e = cudaFuncSetAttribute(tc05_gemm_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
@@ -734,7 +790,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     const size_t smem_bytes = pipe_bytes + 1024 + 256;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, nsplit);
+    cfg.gridDim = dim3(pl.gx, pl.gy, nsplit);
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = s;
@@ -786,13 +842,30 @@ bool codae_tc05_supported(const codae_ctx* ctx, const Tc05Gemm& g) {
     return true;
 }
 
-int codae_tc05_gemm(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
-    if (!codae_tc05_supported(ctx, g)) return codae_fail(ctx, CODAE_EINVAL, "codae_tc05_gemm: unsupported shape/alignment");
-    // tile width: the widest tile that still yields at least one CTA per SM (small batches want many CTAs
-    // streaming the weights), 256-wide for large problems.
+// Tile width: the widest tile that still yields at least one CTA per SM (small batches want many CTAs streaming the
+// weights), 256-wide for large problems.
+static int pick_bn(const codae_ctx* ctx, const Tc05Gemm& g) {
     const long tiles_m = (g.M + BM - 1) / BM;
     const long t256 = tiles_m * ((g.N + 255) / 256), t128 = tiles_m * ((g.N + 127) / 128);
-    if (t256 >= ctx->sm_count && g.N >= 256) return launch<256>(ctx, g, s);
-    if (t128 >= ctx->sm_count && g.N >= 128) return launch<128>(ctx, g, s);
-    return launch<64>(ctx, g, s);
+    if (t256 >= ctx->sm_count && g.N >= 256) return 256;
+    if (t128 >= ctx->sm_count && g.N >= 128) return 128;
+    return 64;
+}
+
+int codae_tc05_gemm(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
+    if (!codae_tc05_supported(ctx, g)) return codae_fail(ctx, CODAE_EINVAL, "codae_tc05_gemm: unsupported shape/alignment");
+    switch (pick_bn(ctx, g)) {
+        case 256: return launch<256>(ctx, g, s);
+        case 128: return launch<128>(ctx, g, s);
+        default: return launch<64>(ctx, g, s);
+    }
+}
+
+int codae_tc05_gemm_ctas(const codae_ctx* ctx, const Tc05Gemm& g) {
+    if (!ctx || !ctx->encode_tiled || g.M < 1 || g.N < 32 || g.K < 1) return 0;
+    switch (pick_bn(ctx, g)) {
+        case 256: return make_plan<256>(ctx, g).ctas;
+        case 128: return make_plan<128>(ctx, g).ctas;
+        default: return make_plan<64>(ctx, g).ctas;
+    }
 }

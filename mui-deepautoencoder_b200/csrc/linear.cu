@@ -66,4 +66,22 @@ int codae_linear_wgrad(codae_ctx* ctx, const void* dY, int64_t lddy, const void*
     return rc;
 }
 
+int codae_linear_wgrad_sq_slots(const codae_ctx* ctx, int M, int N, int K, int dtype) {
+    if (!ctx || dtype != CODAE_BF16 || !tc_shape_ok(M, N, K)) return 0;
+    Tc05Gemm g{nullptr, 0, false, nullptr, 0, false, nullptr, 0, CODAE_F32, N, K, M, nullptr, CODAE_ACT_NONE, nullptr, 0};
+    return codae_tc05_gemm_ctas(ctx, g);
+}
+
+int codae_linear_wgrad_sq(codae_ctx* ctx, const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW, int64_t lddw,
+                          int M, int N, int K, int dtype, double* sq_partials, int n_slots, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && dY && X && dW && sq_partials, "codae_linear_wgrad_sq: NULL argument");
+    CODAE_REQUIRE(ctx, M >= 1 && N >= 1 && K >= 1 && lddy >= N && ldx >= K && lddw >= K, "codae_linear_wgrad_sq: bad shape M=%d N=%d K=%d", M, N, K);
+    CODAE_REQUIRE(ctx, dtype == CODAE_BF16, "codae_linear_wgrad_sq: tensor-core engine only (dtype %d)", dtype);
+    CODAE_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(sq_partials) & 7) == 0, "codae_linear_wgrad_sq: sq_partials must be 8-byte aligned");
+    Tc05Gemm g{dY, lddy, false, X, ldx, false, dW, lddw, CODAE_F32, N, K, M, nullptr, CODAE_ACT_NONE, nullptr, 0};
+    g.sq_partial = sq_partials;
+    g.sq_slots = n_slots;
+    return codae_tc05_gemm(ctx, g, as_stream(stream));
+}
+
 }  // extern "C"

@@ -133,6 +133,67 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
     }
 }
 
+// Adam with the clip scale derived from per-CTA sums of squares that the weight-gradient kernels left behind
+// (codae_linear_wgrad_sq): no norm pass over g at all.  Every CTA sums the (few thousand, L2-resident) partials in the
+// same fixed order, so all CTAs use the same scale and the result is bitwise reproducible.
+__global__ void __launch_bounds__(kThreads) adam_partials_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                                 float* __restrict__ m, float* __restrict__ v,
+                                                                 __nv_bfloat16* __restrict__ pb, int64_t n, AdamArgs a,
+                                                                 const double* __restrict__ partials, int n_partials,
+                                                                 float* __restrict__ sqnorm_out,
+                                                                 const int32_t* __restrict__ step_dev) {
+    __shared__ double scratch[32];
+    __shared__ float s_coef;
+    pdl_launch_dependents();
+    pdl_wait();
+    {
+        double t = 0.0;
+        for (int i = threadIdx.x; i < n_partials; i += blockDim.x) t += __ldcg(&partials[i]);
+        t = block_sum<double>(t, scratch);
+        if (threadIdx.x == 0) {
+            const float sq = (float)t;
+            if (blockIdx.x == 0) *sqnorm_out = sq;
+            const float total = __fmul_rn(sqrtf(sq), a.grad_scale);
+            s_coef = a.max_norm >= 0.f ? fminf(__fdiv_rn(a.max_norm, __fadd_rn(total, 1e-6f)), 1.0f) : 1.0f;
+        }
+        __syncthreads();
+    }
+    const float coef = s_coef;
+    if (step_dev) {
+        const double t = (double)(*step_dev);
+        a.bc2_sqrt = (float)sqrt(1.0 - pow(a.beta2_d, t));
+        a.neg_step = (float)(-(a.lr_d / (1.0 - pow(a.beta1_d, t))));
+    }
+    const int64_t n4 = n >> 2;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += stride) {
+        float4 pv = *reinterpret_cast<const float4*>(p + 4 * e);
+        const float4 gv = __ldcg(reinterpret_cast<const float4*>(g) + e);
+        float4 mv = *reinterpret_cast<const float4*>(m + 4 * e);
+        float4 vv = *reinterpret_cast<const float4*>(v + 4 * e);
+        adam_one(pv.x, gv.x, mv.x, vv.x, a, coef);
+        adam_one(pv.y, gv.y, mv.y, vv.y, a, coef);
+        adam_one(pv.z, gv.z, mv.z, vv.z, a, coef);
+        adam_one(pv.w, gv.w, mv.w, vv.w, a, coef);
+        *reinterpret_cast<float4*>(p + 4 * e) = pv;
+        *reinterpret_cast<float4*>(m + 4 * e) = mv;
+        *reinterpret_cast<float4*>(v + 4 * e) = vv;
+        if (pb) {
+            uint2 q;
+            q.x = pack_bf16x2(pv.x, pv.y);
+            q.y = pack_bf16x2(pv.z, pv.w);
+            *reinterpret_cast<uint2*>(pb + 4 * e) = q;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const int64_t i = (n4 << 2) + threadIdx.x;
+        float pv = p[i], mv = m[i], vv = v[i];
+        adam_one(pv, g[i], mv, vv, a, coef);
+        p[i] = pv; m[i] = mv; v[i] = vv;
+        if (pb) pb[i] = __float2bfloat16_rn(pv);
+    }
+}
+
 // clip_grad_norm_ + Adam in ONE cooperative launch: phase 1 reduces ||g||^2 (per-CTA partials, then every CTA sums the
 // partials in the same fixed order), a grid barrier, phase 2 applies the update.  g (4 B/param) is read twice, but the
 // second read is served by the 126 MB L2 for the shipped configs (94 MB of gradients), and one launch disappears.
@@ -235,6 +296,25 @@ __global__ void counter_add_kernel(int32_t* c, int delta) {
     *c += delta;
 }
 
+// scalar bookkeeping in double, exactly as torch/optim/adam.py does in Python floats
+inline AdamArgs make_adam_args(double lr, double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
+                               double grad_scale) {
+    AdamArgs a;
+    a.beta1_d = beta1; a.beta2_d = beta2; a.lr_d = lr;
+    const double bc1 = 1.0 - pow(beta1, (double)step);
+    const double bc2 = 1.0 - pow(beta2, (double)step);
+    a.w1 = (float)(1.0 - beta1);
+    a.beta2 = (float)beta2;
+    a.omb2 = (float)(1.0 - beta2);
+    a.bc2_sqrt = (float)sqrt(bc2);
+    a.neg_step = (float)(-(lr / bc1));
+    a.eps = (float)eps;
+    a.wd = (float)weight_decay;
+    a.grad_scale = (float)grad_scale;
+    a.max_norm = (float)max_norm;
+    return a;
+}
+
 inline int grid_for(const codae_ctx* ctx, int64_t n4, int per_thread) {
     int64_t blocks = (n4 + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
     const int64_t cap = (int64_t)ctx->sm_count * 8;
@@ -270,20 +350,7 @@ int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v
                          reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
                   "codae_adam_step: buffers must be 16-byte aligned");
     CODAE_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(p_bf16) & 15) == 0, "codae_adam_step: p_bf16 must be 16-byte aligned");
-    // scalar bookkeeping in double, exactly as torch/optim/adam.py does in Python floats
-    AdamArgs a;
-    a.beta1_d = beta1; a.beta2_d = beta2; a.lr_d = lr;
-    const double bc1 = 1.0 - pow(beta1, (double)step);
-    const double bc2 = 1.0 - pow(beta2, (double)step);
-    a.w1 = (float)(1.0 - beta1);
-    a.beta2 = (float)beta2;
-    a.omb2 = (float)(1.0 - beta2);
-    a.bc2_sqrt = (float)sqrt(bc2);
-    a.neg_step = (float)(-(lr / bc1));
-    a.eps = (float)eps;
-    a.wd = (float)weight_decay;
-    a.grad_scale = (float)grad_scale;
-    a.max_norm = (float)max_norm;
+    const AdamArgs a = make_adam_args(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale);
     if (n == 0) return CODAE_OK;
     // one resident wave: 4 CTAs per SM measured best for this access pattern (more CTAs per SM: 156 vs 138 us on 23.6 M
     // parameters; a grid of 8 per SM does not fit at once and leaves a partial second wave)
@@ -307,19 +374,7 @@ int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, flo
     if (ws_bytes < sizeof(NormWs))
         return codae_fail(ctx, CODAE_ENOMEM, "codae_clip_adam_step: workspace %zu < %zu bytes", ws_bytes, sizeof(NormWs));
     if (step < 1) step = 1;
-    AdamArgs a;
-    a.beta1_d = beta1; a.beta2_d = beta2; a.lr_d = lr;
-    const double bc1 = 1.0 - pow(beta1, (double)step);
-    const double bc2 = 1.0 - pow(beta2, (double)step);
-    a.w1 = (float)(1.0 - beta1);
-    a.beta2 = (float)beta2;
-    a.omb2 = (float)(1.0 - beta2);
-    a.bc2_sqrt = (float)sqrt(bc2);
-    a.neg_step = (float)(-(lr / bc1));
-    a.eps = (float)eps;
-    a.wd = (float)weight_decay;
-    a.grad_scale = (float)grad_scale;
-    a.max_norm = (float)max_norm;
+    const AdamArgs a = make_adam_args(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale);
     if (n == 0) return CODAE_OK;
     // cooperative launch: the grid must be co-resident
     static int max_blocks_per_sm = 0;
@@ -350,6 +405,31 @@ int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, flo
     }
     codae_mark_weights_written(ctx, as_stream(stream));
     return codae_check_launch(ctx, "clip_adam_kernel");
+}
+
+int codae_adam_step_partials(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr,
+                             double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
+                             const double* sq_partials, int n_partials, float* sqnorm_out, double grad_scale,
+                             const int32_t* step_dev, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && p && g && m && v && sq_partials && sqnorm_out && n >= 0 && n_partials >= 1 && (step >= 1 || step_dev),
+                  "codae_adam_step_partials: bad argument");
+    CODAE_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(p_bf16)) & 15) == 0 &&
+                            (reinterpret_cast<uintptr_t>(sq_partials) & 7) == 0,
+                  "codae_adam_step_partials: buffers must be 16-byte aligned (sq_partials: 8)");
+    if (step < 1) step = 1;
+    const AdamArgs a = make_adam_args(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale);
+    if (n == 0) return CODAE_OK;
+    int grid = grid_for(ctx, n >> 2, 2);
+    if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;       // one resident wave, as codae_adam_step
+    cudaError_t le = launch_pdl(ctx, adam_partials_kernel, dim3(grid), dim3(kThreads), 0, as_stream(stream), p, (const float*)g, m, v,
+                                reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a, sq_partials, n_partials, sqnorm_out, step_dev);
+    if (le != cudaSuccess) {
+        cudaGetLastError();
+        return codae_fail(ctx, CODAE_ECUDA, "adam_partials_kernel launch: %s", cudaGetErrorString(le));
+    }
+    codae_mark_weights_written(ctx, as_stream(stream));
+    return codae_check_launch(ctx, "adam_partials_kernel");
 }
 
 int codae_counter_add(codae_ctx* ctx, int32_t* counter, int delta, void* stream) {

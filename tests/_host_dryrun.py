@@ -10,7 +10,9 @@ class FakeLib:
         if name.endswith("workspace_bytes"):
             return lambda *a: 1 << 16
         if name == "codae_linear_engine":
-            return lambda c, dtype, M, N, K: 1 if (dtype == 1 and N >= 32 and K >= 32 and N % 8 == 0 and K % 8 == 0) else 0
+            return lambda c, dtype, M, N, K: 1 if (dtype == 1 and N >= 32 and K >= 32) else 0   # csrc/linear.cu: tc_shape_ok
+        if name == "codae_linear_wgrad_sq_slots":
+            return lambda c, M, N, K, dtype: 7 if dtype == 1 else 0
         def f(*a):
             exp = _C.SIGNATURES[name][1]
             assert len(a) == len(exp), (name, len(a), len(exp))
@@ -64,6 +66,16 @@ for dtype in ("fp32", "bf16"):
     fs.step(torch.arange(8)); fs.step(torch.arange(5)); print(dtype, "launches", fs.kernel_launches, fs.last_loss(8))
     fs.evaluate(torch.arange(4)); print(fs.read_monitors())
     st = (torch.rand(8, 96), torch.zeros(8, cor.nb_run, dtype=torch.int16)); fs.step(None, staged=st)
+    if dtype == "bf16":   # norm-free clipped step: one slot range per layer, Adam from the partials
+        fq = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, wgrad_sqnorm=True)
+        fq.step(torch.arange(8)); fq.step(torch.arange(5)); fq.step(torch.arange(0))
+        assert fq._bufs[8]["sq_partials"].numel() == 7 * len(m.dims) and fq.kernel_launches == 2
+        fq.step(torch.arange(8)); print("wgrad_sqnorm launches", fq.kernel_launches)
+    else:
+        try:
+            FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, wgrad_sqnorm=True); raise AssertionError("fp32 engine accepted wgrad_sqnorm")
+        except RuntimeError:
+            pass
     # legacy
     masks, fmask = cor.get_masks((1, 2, 3), 0)
     x = ds.data[[1, 2, 3]]
