@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--no-persistent", action="store_true", help="A/B: one tile per CTA for the large contractions")
     ap.add_argument("--wgrad-sqnorm", action="store_true",
                     help="A/B (1 GPU): weight-gradient kernels leave sum(dW^2) behind, Adam takes the clip scale from those partials")
+    ap.add_argument("--tma-store", action="store_true", help="A/B: single-pass f32 output tiles leave through TMA bulk stores")
     ap.add_argument("--catalog", type=int, default=10_000_000)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -231,6 +232,8 @@ def main():
         _C.set_option(dev, _C.OPT_SPLITK, 0)
     if args.no_persistent:
         _C.set_option(dev, _C.OPT_PERSISTENT, 0)
+    if args.tma_store:
+        _C.set_option(dev, _C.OPT_TMA_STORE, 1)
     pk = peaks()
     B, K, Wm = w["B"], args.steps, args.warmup
     if args.workload == "polyvore" and K > 50:

@@ -106,7 +106,7 @@ def ctx(device=None):
     return c
 
 
-OPT_SPLITK, OPT_PDL, OPT_PERSISTENT, OPT_WEIGHT_PREFETCH = 0, 1, 2, 3
+OPT_SPLITK, OPT_PDL, OPT_PERSISTENT, OPT_WEIGHT_PREFETCH, OPT_TMA_STORE = 0, 1, 2, 3, 4
 
 
 _options = {}
@@ -120,7 +120,7 @@ def set_option(device, option, value):
 
 
 def get_option_cached(device, option):
-    return _options.get((torch.device(device).index or 0, option), 1)
+    return _options.get((torch.device(device).index or 0, option), 0 if option == OPT_TMA_STORE else 1)
 
 
 def set_splitk(device, enabled):

@@ -16,6 +16,8 @@ Replaces, per step (script/train_dae_on_embedding.py:198-223; script/train_dae_o
 No host synchronisation happens inside a step; monitors stay on the device until read_monitors().
 The whole sequence can be captured once per batch size into a CUDA graph (use_graph=True).
 """
+import os
+
 import torch
 
 from codae import _C
@@ -32,7 +34,7 @@ class FusedStep:
 
     def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True,
-                 fused_clip_adam=True, wgrad_sqnorm=False):
+                 fused_clip_adam=True, wgrad_sqnorm=None):
         """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
         tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
         {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
@@ -82,6 +84,9 @@ class FusedStep:
             lin.bias.grad = model.bias_view(self.gflat, l)
         lay, total = model.layout()
         self._layer_span = [(lay[l][0], lay[l + 1][0] if l + 1 < len(lay) else total) for l in range(len(lay))]
+        if wgrad_sqnorm is None:
+            # default off until measured on the target; CODAE_WGRAD_SQNORM=1 turns it on wherever it applies
+            self.wgrad_sqnorm = os.environ.get("CODAE_WGRAD_SQNORM") == "1" and world_size == 1 and self.eng == _C.BF16
         if self.wgrad_sqnorm and (world_size > 1 or self.eng != _C.BF16):
             raise RuntimeError("codae: wgrad_sqnorm needs a single GPU (the norm of a data-parallel run is taken after the "
                                "all-reduce) and the tensor-core engine")

@@ -13,9 +13,9 @@ int codae_fail(codae_ctx* ctx, int code, const char* fmt, ...) {
     va_end(ap);
     if (ctx) {
         std::lock_guard<std::mutex> lk(ctx->mu);
-        strncpy(ctx->err, buf, sizeof(ctx->err) - 1);
+        snprintf(ctx->err, sizeof(ctx->err), "%s", buf);
     }
-    strncpy(g_codae_last_error, buf, sizeof(g_codae_last_error) - 1);
+    snprintf(g_codae_last_error, sizeof(g_codae_last_error), "%s", buf);
     return code;
 }
 
@@ -61,6 +61,7 @@ int codae_ctx_create(int device, codae_ctx** out) {
     c->pdl = 1;
     c->persistent = 1;
     c->weight_prefetch = 1;
+    c->tma_store = 0;
     c->weights_dirty = 0;
     c->dirty_stream = nullptr;
     void* fn = nullptr;
@@ -87,6 +88,7 @@ int codae_ctx_set_option(codae_ctx* ctx, int option, int value) {
     else if (option == CODAE_OPT_PDL) ctx->pdl = value ? 1 : 0;
     else if (option == CODAE_OPT_PERSISTENT) ctx->persistent = value ? 1 : 0;
     else if (option == CODAE_OPT_WEIGHT_PREFETCH) ctx->weight_prefetch = value ? 1 : 0;
+    else if (option == CODAE_OPT_TMA_STORE) ctx->tma_store = value ? 1 : 0;
     else return codae_fail(ctx, CODAE_EINVAL, "codae_ctx_set_option: unknown option %d", option);
     return CODAE_OK;
 }

@@ -55,6 +55,7 @@ struct Params {
     int staged;                  // 1: epilogue through the shared-memory tile (required when gridDim.z > 1)
     int prefetch_b;              // 1: B holds weights no running predecessor writes: fetch its first tiles before the PDL wait
     int group_m;                 // persistent kernel: row-tiles per raster group
+    int tma_store;               // 1: staged f32 tile leaves through cp.async.bulk.tensor stores (nsplit == 1, plain epilogue)
     double* sq_partial;          // f32 outputs only: slot [linear CTA id] receives the sum of squares of what this CTA stored (or NULL)
     unsigned long long* trace;   // debugging: CTA (0,0,0) writes %globaltimer stamps of its phases here (or NULL)
 };
@@ -104,6 +105,13 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
             smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// Bulk tensor store shared -> global (bulk async-group completion); out-of-range rows / columns of the box are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(map)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
@@ -261,7 +269,8 @@ __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, 
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
-                                                                const __grid_constant__ CUtensorMap tma_b, const Params p) {
+                                                                const __grid_constant__ CUtensorMap tma_b,
+                                                                const __grid_constant__ CUtensorMap tma_c, const Params p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -288,6 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+        if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_c)) : "memory");
         for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tmem_full_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -390,6 +400,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
                 store_chunk<32>(p, row, col0, f);
                 if (p.sq_partial) sq_acc += (double)chunk_sq<32>(f, col0, p.N);
+            } else if (p.tma_store) {
+                // box c = [128 rows][32 floats] at smem + c * 16 KB in the 128-byte-swizzle layout the store's tensor map
+                // names: 16-byte chunk j of row r sits at chunk j ^ (r & 7), so the 8 lanes of a store phase (8 consecutive
+                // rows) hit 8 distinct bank groups
+                uint8_t* brow = smem + c * 16384 + (q * 32 + lane) * 128;
+                const int sw = lane & 7;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4*>(brow + ((j ^ sw) << 4)) =
+                        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                    __uint_as_float(v[4 * j + 3]));
+                if (p.sq_partial && row_ok && col0 < p.N) {
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    sq_acc += (double)chunk_sq<32>(f, col0, p.N);
+                }
             } else {
                 // row pitch BN+4 floats: the 8 lanes of a 128-bit store phase hit 8 distinct 16-byte bank groups
                 float4* dst = reinterpret_cast<float4*>(stage_row + c * 32);
@@ -401,7 +428,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         }
     }
 
-    if (p.staged) {
+    if (p.staged && p.tma_store) {
+        // ===== epilogue, part 2 (bulk store): the tile leaves through the TMA unit, BN/32 boxes of 128 x 32 floats =====
+        if (warp >= 2) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> async proxy
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 64) {
+                trace_stamp(p, 6);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c)
+                    if (n0 + c * 32 < p.N) tma_store_2d(&tma_c, smem + c * 16384, n0 + c * 32, m0);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem is released at the barrier below
+                trace_stamp(p, 8);
+            }
+        }
+    } else if (p.staged) {
         // ===== epilogue, part 2 (staged): [cluster reduce +] fused epilogue + coalesced stores =====
         __syncwarp();
         if (threadIdx.x == 64) trace_stamp(p, 6);                  // tile staged in shared memory
@@ -694,6 +736,19 @@ struct Plan {
     int gx, gy;        // output tiles along N and M
     int ctas;          // CTAs the launch will have (= sum-of-squares slots it writes)
 };
+// 2-D f32 tensor map over the row-major output [rows, cols] with pitch ld (elements), box {32 floats, 128 rows}.
+int make_store_map(codae_ctx* ctx, CUtensorMap* map, void* base, long long rows, long long cols, long long ld) {
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    const cuuint32_t box[2] = {32, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
+        map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return codae_fail(ctx, CODAE_ECUDA, "cuTensorMapEncodeTiled (f32 store map) failed (CUresult %d)", (int)r);
+    return CODAE_OK;
+}
+
 template <int BN>
 Plan make_plan(const codae_ctx* ctx, const Tc05Gemm& g) {
     Plan pl;
@@ -749,6 +804,15 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     const int nsplit = pl.nsplit;
     p.trace = g_trace_buf;
     p.staged = pl.staged ? 1 : 0;
+    // bulk-store epilogue: plain f32 tiles of a single-pass launch (the weight gradients of the small-batch step)
+    p.tma_store = (ctx->tma_store && pl.staged && nsplit == 1 && g.c_dtype == CODAE_F32 && !g.bias && g.act == CODAE_ACT_NONE &&
+                   !g.mask_src && (g.ldc % 4) == 0) ? 1 : 0;
+    CUtensorMap mc;
+    memset(&mc, 0, sizeof(mc));
+    if (p.tma_store) {
+        rc = make_store_map(ctx, &mc, g.C, g.M, g.N, g.ldc);
+        if (rc) return rc;
+    }
     p.prefetch_b = (g.b_is_weight && ctx->pdl && ctx->weight_prefetch) ? 1 : 0;
     p.group_m = 16;
     if (pl.persistent) {
@@ -810,7 +874,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, tc05_gemm_kernel<BN>, ma, mb, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, tc05_gemm_kernel<BN>, ma, mb, mc, p);
     if (le != cudaSuccess) {
         cudaGetLastError();
         return codae_fail(ctx, CODAE_ECUDA, "tc05_gemm_kernel<%d> launch (grid %u x %u x %d, smem %zu): %s", BN, cfg.gridDim.x,

@@ -76,6 +76,40 @@ def test_wgrad_sq_equals_wgrad_and_sums_to_the_norm(C, B, o, i, persistent):
         C.set_option(DEV, C.OPT_PERSISTENT, 1)
 
 
+@pytest.mark.parametrize("B,o,i", [(128, 1536, 1536), (32, 1536, 1536), (640, 598, 1067), (128, 192, 328), (100, 832, 128)])
+def test_tma_store_epilogue_is_bit_identical(C, B, o, i):
+    """CODAE_OPT_TMA_STORE: the staged f32 tile leaves through cp.async.bulk.tensor stores (128-byte swizzle box) instead of
+    per-thread stores.  Same gradient bits, same partial sums, ragged edges clipped by the tensor map, padding untouched."""
+    torch.manual_seed(23)
+    bf = torch.bfloat16
+    K = _ru(i, 8) + 1
+    ld = _ru(K, 64)
+    dY = torch.randn(B, _ru(o, 8)).to(DEV, bf)
+    X = torch.zeros(B, ld, device=DEV, dtype=bf)
+    X[:, :i] = torch.randn(B, i).to(DEV, bf)
+    X[:, _ru(i, 8)] = 1
+    slots = C.linear_wgrad_sq_slots(DEV, B, o, K, C.BF16)
+    res = {}
+    for on in (0, 1):
+        C.set_option(DEV, C.OPT_TMA_STORE, on)
+        try:
+            dW = torch.full((o + 3, ld), 5.0, device=DEV)             # 3 guard rows below the matrix
+            part = torch.full((slots,), -1.0, dtype=torch.float64, device=DEV)
+            C.linear_wgrad_sq(dY[:, :o], X[:, :K], dW[:o, :K], B, o, K, C.BF16, part)
+            dW2 = torch.full((o + 3, ld), 5.0, device=DEV)
+            C.linear_wgrad(dY[:, :o], X[:, :K], dW2[:o, :K], None, B, o, K, C.BF16)
+            torch.cuda.synchronize()
+            res[on] = (dW, part, dW2)
+        finally:
+            C.set_option(DEV, C.OPT_TMA_STORE, 0)
+    assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][2], res[0][2]) and torch.equal(res[1][0], res[1][2])
+    s0, s1 = float(res[0][1].sum()), float(res[1][1].sum())          # threads own different elements on the two paths
+    assert float(res[1][1].min()) >= 0 and abs(s1 - s0) <= 1e-6 * s0
+    assert float((res[1][0][:, K:] - 5.0).abs().max()) == 0 and float((res[1][0][o:] - 5.0).abs().max()) == 0
+    want = dY[:, :o].double().cpu().t().mm(X[:, :K].double().cpu())
+    assert rel(res[1][0][:o, :K].cpu().numpy(), want.numpy()) < 1e-4
+
+
 @pytest.mark.parametrize("n,shadow", [(23_608_320 // 8 + 5, True), (4096, False)])
 def test_adam_step_partials_equals_clip_adam(C, n, shadow):
     """Given the same sum of squares, the partials kernel is the cooperative norm+Adam kernel (weights, moments, shadow)."""
