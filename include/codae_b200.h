@@ -67,6 +67,8 @@ int codae_ctx_sm_count(const codae_ctx* ctx);
 enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1, CODAE_OPT_PERSISTENT = 2, CODAE_OPT_WEIGHT_PREFETCH = 3,
                     CODAE_OPT_TMA_STORE = 4 };
 int codae_ctx_set_option(codae_ctx* ctx, int option, int value);
+/* Current value (0 / 1) of a tuning switch, CODAE_EINVAL for an unknown option. */
+int codae_ctx_get_option(const codae_ctx* ctx, int option);
 /* Which engine codae_linear_* will use for (dtype, M, N, K). */
 int codae_linear_engine(const codae_ctx* ctx, int dtype, int M, int N, int K);
 

@@ -31,6 +31,7 @@ SIGNATURES = {
     "codae_last_error": (_c.c_char_p, [_vp]),
     "codae_ctx_sm_count": (_i, [_vp]),
     "codae_ctx_set_option": (_i, [_vp, _i, _i]),
+    "codae_ctx_get_option": (_i, [_vp, _i]),
     "codae_linear_engine": (_i, [_vp, _i, _i, _i, _i]),
     "codae_mask_table_philox": (_i, [_vp, _u64, _i64, _i64, _i, _vp, _vp]),
     "codae_corrupt_fwd": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i64, _vp, _i64, _vp, _vp]),
@@ -109,18 +110,17 @@ def ctx(device=None):
 OPT_SPLITK, OPT_PDL, OPT_PERSISTENT, OPT_WEIGHT_PREFETCH, OPT_TMA_STORE = 0, 1, 2, 3, 4
 
 
-_options = {}
-
-
 def set_option(device, option, value):
-    """Tuning switches of the library (cluster split-K, programmatic dependent launch); both default on."""
+    """Tuning switches of the library (include/codae_b200.h: enum codae_option)."""
     c = ctx(device)
     check(lib().codae_ctx_set_option(c, option, 1 if value else 0), c)
-    _options[(torch.device(device).index or 0, option)] = 1 if value else 0
 
 
-def get_option_cached(device, option):
-    return _options.get((torch.device(device).index or 0, option), 0 if option == OPT_TMA_STORE else 1)
+def get_option(device, option):
+    v = lib().codae_ctx_get_option(ctx(device), option)
+    if v < 0:
+        raise RuntimeError("codae: unknown option %d" % option)
+    return v
 
 
 def set_splitk(device, enabled):

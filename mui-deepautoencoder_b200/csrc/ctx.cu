@@ -1,5 +1,6 @@
 // Context, error reporting and engine selection of libcodae_b200.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -61,7 +62,10 @@ int codae_ctx_create(int device, codae_ctx** out) {
     c->pdl = 1;
     c->persistent = 1;
     c->weight_prefetch = 1;
-    c->tma_store = 0;
+    {   // default off until measured; CODAE_TMA_STORE=0/1 overrides the default (A/B runs of whole test suites)
+        const char* e = getenv("CODAE_TMA_STORE");
+        c->tma_store = e ? (atoi(e) != 0) : 0;
+    }
     c->weights_dirty = 0;
     c->dirty_stream = nullptr;
     void* fn = nullptr;
@@ -91,6 +95,18 @@ int codae_ctx_set_option(codae_ctx* ctx, int option, int value) {
     else if (option == CODAE_OPT_TMA_STORE) ctx->tma_store = value ? 1 : 0;
     else return codae_fail(ctx, CODAE_EINVAL, "codae_ctx_set_option: unknown option %d", option);
     return CODAE_OK;
+}
+
+int codae_ctx_get_option(const codae_ctx* ctx, int option) {
+    if (!ctx) return CODAE_EINVAL;
+    switch (option) {
+        case CODAE_OPT_SPLITK: return ctx->splitk;
+        case CODAE_OPT_PDL: return ctx->pdl;
+        case CODAE_OPT_PERSISTENT: return ctx->persistent;
+        case CODAE_OPT_WEIGHT_PREFETCH: return ctx->weight_prefetch;
+        case CODAE_OPT_TMA_STORE: return ctx->tma_store;
+        default: return CODAE_EINVAL;
+    }
 }
 
 }  // extern "C"

@@ -430,15 +430,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
 
     if (p.staged && p.tma_store) {
         // ===== epilogue, part 2 (bulk store): the tile leaves through the TMA unit, BN/32 boxes of 128 x 32 floats =====
+        // The store's tensor map ends at the last whole 16-byte unit of a row (n4 columns): TMA clips a ragged row end at
+        // 16-byte granularity (measured: it zero-fills up to 3 floats past the last valid column), so the N & 3 tail
+        // columns -- the bias-gradient column of an augmented layer -- are stored by the threads and padding stays untouched.
         if (warp >= 2) {
+            const int n4 = p.N & ~3;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy smem writes -> async proxy
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (threadIdx.x == 64) {
                 trace_stamp(p, 6);
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c)
-                    if (n0 + c * 32 < p.N) tma_store_2d(&tma_c, smem + c * 16384, n0 + c * 32, m0);
+                    if (n0 + c * 32 < n4) tma_store_2d(&tma_c, smem + c * 16384, n0 + c * 32, m0);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            if (n4 < p.N && n4 >= n0 && n4 < n0 + BN) {
+                const int rl = threadIdx.x - 64, row = m0 + rl;
+                if (row < p.M) {
+                    const int c = (n4 - n0) >> 5, j = ((n4 - n0) & 31) >> 2;
+                    const float* src = reinterpret_cast<const float*>(smem + c * 16384 + rl * 128 + ((j ^ (rl & 7)) << 4));
+                    float* crow = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + n4;
+                    for (int e = 0; e < p.N - n4; ++e) crow[e] = src[e];
+                }
+            }
+            if (threadIdx.x == 64) {
                 asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // smem is released at the barrier below
                 trace_stamp(p, 8);
             }
@@ -810,7 +825,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     CUtensorMap mc;
     memset(&mc, 0, sizeof(mc));
     if (p.tma_store) {
-        rc = make_store_map(ctx, &mc, g.C, g.M, g.N, g.ldc);
+        rc = make_store_map(ctx, &mc, g.C, g.M, g.N & ~3, g.ldc);     // whole 16-byte units only; the kernel stores the tail
         if (rc) return rc;
     }
     p.prefetch_b = (g.b_is_weight && ctx->pdl && ctx->weight_prefetch) ? 1 : 0;

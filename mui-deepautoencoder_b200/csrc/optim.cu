@@ -4,6 +4,7 @@
 // explicit _rn intrinsics where ATen does not fuse) so that weights track the reference to fp32 rounding.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -422,8 +423,21 @@ int codae_adam_step_partials(codae_ctx* ctx, float* p, const float* g, float* m,
     if (n == 0) return CODAE_OK;
     int grid = grid_for(ctx, n >> 2, 2);
     if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;       // one resident wave, as codae_adam_step
-    cudaError_t le = launch_pdl(ctx, adam_partials_kernel, dim3(grid), dim3(kThreads), 0, as_stream(stream), p, (const float*)g, m, v,
-                                reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a, sq_partials, n_partials, sqnorm_out, step_dev);
+    // CODAE_ADAM_PARTIALS_PDL=0: full stream dependency instead of a programmatic one (A/B; read once)
+    static int use_pdl = -1;
+    if (use_pdl < 0) {
+        const char* e = getenv("CODAE_ADAM_PARTIALS_PDL");
+        use_pdl = e ? (atoi(e) != 0) : 1;
+    }
+    cudaError_t le;
+    if (use_pdl) {
+        le = launch_pdl(ctx, adam_partials_kernel, dim3(grid), dim3(kThreads), 0, as_stream(stream), p, (const float*)g, m, v,
+                        reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a, sq_partials, n_partials, sqnorm_out, step_dev);
+    } else {
+        adam_partials_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(p, (const float*)g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
+                                                                      n, a, sq_partials, n_partials, sqnorm_out, step_dev);
+        le = cudaSuccess;
+    }
     if (le != cudaSuccess) {
         cudaGetLastError();
         return codae_fail(ctx, CODAE_ECUDA, "adam_partials_kernel launch: %s", cudaGetErrorString(le));

@@ -90,6 +90,7 @@ def test_tma_store_epilogue_is_bit_identical(C, B, o, i):
     X[:, _ru(i, 8)] = 1
     slots = C.linear_wgrad_sq_slots(DEV, B, o, K, C.BF16)
     res = {}
+    saved = C.get_option(DEV, C.OPT_TMA_STORE)
     for on in (0, 1):
         C.set_option(DEV, C.OPT_TMA_STORE, on)
         try:
@@ -101,7 +102,7 @@ def test_tma_store_epilogue_is_bit_identical(C, B, o, i):
             torch.cuda.synchronize()
             res[on] = (dW, part, dW2)
         finally:
-            C.set_option(DEV, C.OPT_TMA_STORE, 0)
+            C.set_option(DEV, C.OPT_TMA_STORE, saved)
     assert torch.equal(res[1][0], res[0][0]) and torch.equal(res[1][2], res[0][2]) and torch.equal(res[1][0], res[1][2])
     s0, s1 = float(res[0][1].sum()), float(res[1][1].sum())          # threads own different elements on the two paths
     assert float(res[1][1].min()) >= 0 and abs(s1 - s0) <= 1e-6 * s0
