@@ -180,9 +180,9 @@ def main():
     ap.add_argument("--no-pdl", action="store_true", help="A/B: launch without programmatic dependent launch")
     ap.add_argument("--no-splitk", action="store_true", help="A/B: single-pass small-batch contractions")
     ap.add_argument("--no-persistent", action="store_true", help="A/B: one tile per CTA for the large contractions")
-    ap.add_argument("--wgrad-sqnorm", action="store_true",
-                    help="A/B (1 GPU): weight-gradient kernels leave sum(dW^2) behind, Adam takes the clip scale from those partials")
-    ap.add_argument("--tma-store", action="store_true", help="A/B: single-pass f32 output tiles leave through TMA bulk stores")
+    ap.add_argument("--no-wgrad-sqnorm", action="store_true",
+                    help="A/B (1 GPU): cooperative norm + Adam kernel instead of sum(dW^2) partials from the weight-gradient kernels")
+    ap.add_argument("--no-tma-store", action="store_true", help="A/B: per-thread stores instead of TMA bulk stores for single-pass f32 tiles")
     ap.add_argument("--catalog", type=int, default=10_000_000)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -232,8 +232,8 @@ def main():
         _C.set_option(dev, _C.OPT_SPLITK, 0)
     if args.no_persistent:
         _C.set_option(dev, _C.OPT_PERSISTENT, 0)
-    if args.tma_store:
-        _C.set_option(dev, _C.OPT_TMA_STORE, 1)
+    if args.no_tma_store:
+        _C.set_option(dev, _C.OPT_TMA_STORE, 0)
     pk = peaks()
     B, K, Wm = w["B"], args.steps, args.warmup
     if args.workload == "polyvore" and K > 50:
@@ -249,7 +249,7 @@ def main():
     model.to(dev)
     cor = Corrupter(w["N"], ds.arch, w["k_max"], dev, seed=w["seed"])
     fs = FusedStep(model, cor, data, lr=w["lr"], weight_decay=w["wd"], clip=w["clip"], world_size=world,
-                   use_graph=not args.no_graph, wgrad_sqnorm=args.wgrad_sqnorm and world == 1 and dtype == "bf16")
+                   use_graph=not args.no_graph, wgrad_sqnorm=False if args.no_wgrad_sqnorm else None)
     rng = np.random.RandomState(w["seed"] + rank)
     nb = Wm + K
     batches = torch.from_numpy(rng.randint(0, w["N"], size=(nb, B))).to(dev)

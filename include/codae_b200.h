@@ -47,7 +47,7 @@ int codae_ctx_create(int device, codae_ctx** out);
 int codae_ctx_destroy(codae_ctx* ctx);
 const char* codae_last_error(const codae_ctx* ctx); /* ctx may be NULL: last process-wide error */
 int codae_ctx_sm_count(const codae_ctx* ctx);
-/* Tuning switches, on by default unless noted (tests flip them to compare code paths):
+/* Tuning switches, all on by default (tests flip them to compare code paths):
  *   CODAE_OPT_SPLITK  contractions with too few output tiles to occupy the GPU (the small-batch layers of
  *                     embedding.yaml / modanet) spread their k-blocks over a thread-block cluster and reduce the partial
  *                     tiles through distributed shared memory, in rank order (bitwise reproducible);
@@ -61,9 +61,11 @@ int codae_ctx_sm_count(const codae_ctx* ctx);
  *                     weights (codae_adam_step, codae_clip_adam_step, codae_cast_bf16) makes the next launch on its stream
  *                     a full (non-programmatic) dependency.  A caller that writes the bf16 weight buffer with kernels of
  *                     its own must either switch this off or call codae_cast_bf16 / an optimizer entry point afterwards.
- *   CODAE_OPT_TMA_STORE  (default OFF) single-pass f32 output tiles of the tensor-core engine (the weight gradients of
- *                     the small-batch step) are staged in shared memory in the 128-byte-swizzle layout and leave through
- *                     cp.async.bulk.tensor stores instead of per-thread 128-bit stores.  Same values, bit for bit. */
+ *   CODAE_OPT_TMA_STORE  single-pass f32 output tiles of the tensor-core engine (the weight gradients of the small-batch
+ *                     step) are staged in shared memory in the 128-byte-swizzle layout and leave through
+ *                     cp.async.bulk.tensor stores instead of per-thread 128-bit stores (the N & 3 tail columns of a row
+ *                     are stored by the threads: TMA clips ragged row ends at 16-byte granularity).  Same values, bit for
+ *                     bit; measured 98.8 -> 64.2 us for the ten weight gradients of the embedding.yaml step. */
 enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1, CODAE_OPT_PERSISTENT = 2, CODAE_OPT_WEIGHT_PREFETCH = 3,
                     CODAE_OPT_TMA_STORE = 4 };
 int codae_ctx_set_option(codae_ctx* ctx, int option, int value);

@@ -21,7 +21,7 @@ struct codae_ctx {
     int persistent;      // 1: large contractions use the persistent, TMEM-double-buffered kernel (default on)
     int pdl;             // 1: training-step kernels are launched with programmatic dependent launch (default on)
     int weight_prefetch; // 1: fwd / dgrad GEMMs issue the TMA loads of their WEIGHT tiles before griddepcontrol.wait
-    int tma_store;       // 1: single-pass f32 output tiles leave through TMA bulk stores (default off until measured)
+    int tma_store;       // 1: single-pass f32 output tiles leave through TMA bulk stores (default on)
     int weights_dirty;   // a weight-writing kernel (Adam, clip+Adam, bf16 cast) was the last codae launch on dirty_stream
     cudaStream_t dirty_stream;
     std::mutex mu;

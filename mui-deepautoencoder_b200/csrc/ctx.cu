@@ -62,9 +62,10 @@ int codae_ctx_create(int device, codae_ctx** out) {
     c->pdl = 1;
     c->persistent = 1;
     c->weight_prefetch = 1;
-    {   // default off until measured; CODAE_TMA_STORE=0/1 overrides the default (A/B runs of whole test suites)
+    {   // on by default (embedding.yaml step 0.3775 -> 0.3446 ms, modanet 0.305 -> 0.284); CODAE_TMA_STORE=0 switches the
+        // default off for A/B runs of whole test suites
         const char* e = getenv("CODAE_TMA_STORE");
-        c->tma_store = e ? (atoi(e) != 0) : 0;
+        c->tma_store = e ? (atoi(e) != 0) : 1;
     }
     c->weights_dirty = 0;
     c->dirty_stream = nullptr;
