@@ -47,7 +47,7 @@ int codae_ctx_create(int device, codae_ctx** out);
 int codae_ctx_destroy(codae_ctx* ctx);
 const char* codae_last_error(const codae_ctx* ctx); /* ctx may be NULL: last process-wide error */
 int codae_ctx_sm_count(const codae_ctx* ctx);
-/* Tuning switches, all on by default (tests flip them to compare code paths):
+/* Tuning switches, on by default unless noted (tests flip them to compare code paths):
  *   CODAE_OPT_SPLITK  contractions with too few output tiles to occupy the GPU (the small-batch layers of
  *                     embedding.yaml / modanet) spread their k-blocks over a thread-block cluster and reduce the partial
  *                     tiles through distributed shared memory, in rank order (bitwise reproducible);
@@ -65,9 +65,12 @@ int codae_ctx_sm_count(const codae_ctx* ctx);
  *                     step) are staged in shared memory in the 128-byte-swizzle layout and leave through
  *                     cp.async.bulk.tensor stores instead of per-thread 128-bit stores (the N & 3 tail columns of a row
  *                     are stored by the threads: TMA clips ragged row ends at 16-byte granularity).  Same values, bit for
- *                     bit; measured 98.8 -> 64.2 us for the ten weight gradients of the embedding.yaml step. */
+ *                     bit; measured 98.8 -> 64.2 us for the ten weight gradients of the embedding.yaml step.
+ *   CODAE_OPT_TMA_STORE_PERSISTENT  (default OFF: written, not yet measured on a B200) the same for the persistent kernel
+ *                     of the large contractions: every epilogue warp stages 32 rows x 128 bytes per store in one of two
+ *                     boxes of its own and issues the bulk store itself (f32 and bf16 outputs, all fused epilogues). */
 enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1, CODAE_OPT_PERSISTENT = 2, CODAE_OPT_WEIGHT_PREFETCH = 3,
-                    CODAE_OPT_TMA_STORE = 4 };
+                    CODAE_OPT_TMA_STORE = 4, CODAE_OPT_TMA_STORE_PERSISTENT = 5 };
 int codae_ctx_set_option(codae_ctx* ctx, int option, int value);
 /* Current value (0 / 1) of a tuning switch, CODAE_EINVAL for an unknown option. */
 int codae_ctx_get_option(const codae_ctx* ctx, int option);

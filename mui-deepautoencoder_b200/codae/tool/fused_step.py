@@ -12,7 +12,10 @@ Replaces, per step (script/train_dae_on_embedding.py:198-223; script/train_dae_o
   clip_grad_norm_ + Adam   -> codae_clip_adam_step: one cooperative launch over the flat buffers (norm, grid barrier,
                               update); or codae_grad_sqnorm + codae_adam_step; or (wgrad_sqnorm=True, single GPU,
                               tensor-core engine) codae_linear_wgrad_sq + codae_adam_step_partials: the weight-gradient
-                              kernels leave sum(dW^2) behind and the optimizer never reads g for the norm
+                              kernels leave sum(dW^2) behind and the optimizer never reads g for the norm; or
+                              (layerwise_adam=True, no clipping, single GPU) codae_adam_step per layer on the weight-gradient
+                              stream as soon as that layer's wgrad and dgrad are done: the HBM-bound optimizer overlaps the
+                              latency-bound input-gradient chain (modanet_merge_top_bottom_shoe.yaml has no TRUNK_GRAD)
 No host synchronisation happens inside a step; monitors stay on the device until read_monitors().
 The whole sequence can be captured once per batch size into a CUDA graph (use_graph=True).
 """
@@ -34,7 +37,7 @@ class FusedStep:
 
     def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True,
-                 fused_clip_adam=True, wgrad_sqnorm=None):
+                 fused_clip_adam=True, wgrad_sqnorm=None, layerwise_adam=None):
         """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
         tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
         {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
@@ -88,6 +91,15 @@ class FusedStep:
             # on wherever it applies (embedding.yaml step: 0.3446 -> 0.3367 ms); CODAE_WGRAD_SQNORM=0 switches it off
             self.wgrad_sqnorm = (os.environ.get("CODAE_WGRAD_SQNORM", "1") != "0" and world_size == 1 and self.eng == _C.BF16
                                  and fused_clip_adam)
+        if layerwise_adam is None:
+            # opt-in until measured on the target: CODAE_LAYERWISE_ADAM=1 turns it on wherever it applies
+            layerwise_adam = os.environ.get("CODAE_LAYERWISE_ADAM") == "1" and not clip and world_size == 1 and self.eng == _C.BF16
+        if layerwise_adam and (clip or world_size > 1):
+            raise RuntimeError("codae: layerwise_adam needs clip=False (the clip scale depends on every layer's gradient) and a "
+                               "single GPU (the update follows the gradient all-reduce)")
+        self.layerwise_adam = bool(layerwise_adam)
+        if self.layerwise_adam:
+            self.wgrad_sqnorm = False          # no norm is needed at all
         if self.wgrad_sqnorm and (world_size > 1 or self.eng != _C.BF16):
             raise RuntimeError("codae: wgrad_sqnorm needs a single GPU (the norm of a data-parallel run is taken after the "
                                "all-reduce) and the tensor-core engine")
@@ -171,6 +183,10 @@ class FusedStep:
         sides = [self._wgrad_stream] if (eng == _C.BF16 and B <= 1024) else [main]
         wdone = [None] * L
         bucket_hi = None
+        layerwise = self.layerwise_adam
+        pb = model.flat_bf16 if eng == _C.BF16 else None
+        if layerwise:
+            _C.counter_add(self.step_dev, 1); n += 1    # before the first per-layer update reads it
         for l in range(L - 1, -1, -1):
             i, o = dims[l]
             gl = gbuf[l % 3][:, :_round_up(o, 8)]
@@ -206,6 +222,18 @@ class FusedStep:
                     main.wait_event(wdone[l + 2])       # dgrad(l) overwrites the buffer wgrad(l+2) was reading
                 gp = gbuf[(l - 1) % 3][:, :_round_up(i, 8)]
                 _C.linear_dgrad(gl, model.weight_view(wflat, l), acts[l] if model.relu[l - 1] else None, gp, B, o, i, eng); n += 1
+            if layerwise:
+                # layer l's weights may change once BOTH its weight gradient (side stream order) and dgrad(l), which reads
+                # them, are done: the update runs on the weight-gradient stream beside the rest of the input-gradient chain
+                if side is not main:
+                    dg_done = torch.cuda.Event()
+                    dg_done.record(main)
+                    side.wait_event(dg_done)
+                lo, hi = self._layer_span[l]
+                with torch.cuda.stream(side):
+                    _C.adam_step(model.flat[lo:hi], self.gflat[lo:hi], self.m[lo:hi], self.v[lo:hi],
+                                 None if pb is None else pb[lo:hi], self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0,
+                                 -1.0, None, 1.0, self.step_dev); n += 1
         for side in sides:
             if side is not main:
                 main.wait_stream(side)
@@ -214,7 +242,8 @@ class FusedStep:
         elif self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
-        n += self._enqueue_update(b.get("sq_partials"))
+        if not layerwise:
+            n += self._enqueue_update(b.get("sq_partials"))
         return n
 
     def _enqueue_update(self, sq_partials=None):

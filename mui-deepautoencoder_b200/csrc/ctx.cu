@@ -67,6 +67,10 @@ int codae_ctx_create(int device, codae_ctx** out) {
         const char* e = getenv("CODAE_TMA_STORE");
         c->tma_store = e ? (atoi(e) != 0) : 1;
     }
+    {
+        const char* e = getenv("CODAE_TMA_STORE_PERSISTENT");
+        c->tma_store_persistent = e ? (atoi(e) != 0) : 0;
+    }
     c->weights_dirty = 0;
     c->dirty_stream = nullptr;
     void* fn = nullptr;
@@ -94,6 +98,7 @@ int codae_ctx_set_option(codae_ctx* ctx, int option, int value) {
     else if (option == CODAE_OPT_PERSISTENT) ctx->persistent = value ? 1 : 0;
     else if (option == CODAE_OPT_WEIGHT_PREFETCH) ctx->weight_prefetch = value ? 1 : 0;
     else if (option == CODAE_OPT_TMA_STORE) ctx->tma_store = value ? 1 : 0;
+    else if (option == CODAE_OPT_TMA_STORE_PERSISTENT) ctx->tma_store_persistent = value ? 1 : 0;
     else return codae_fail(ctx, CODAE_EINVAL, "codae_ctx_set_option: unknown option %d", option);
     return CODAE_OK;
 }
@@ -106,6 +111,7 @@ int codae_ctx_get_option(const codae_ctx* ctx, int option) {
         case CODAE_OPT_PERSISTENT: return ctx->persistent;
         case CODAE_OPT_WEIGHT_PREFETCH: return ctx->weight_prefetch;
         case CODAE_OPT_TMA_STORE: return ctx->tma_store;
+        case CODAE_OPT_TMA_STORE_PERSISTENT: return ctx->tma_store_persistent;
         default: return CODAE_EINVAL;
     }
 }

@@ -40,6 +40,7 @@ constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
 constexpr uint32_t kATileBytes = BM * BK * 2;  // 16 KB
 constexpr int kMaxSplit = 8;     // portable cluster size limit
+constexpr uint32_t kPersistentStageBytes = 4 * 2 * 4096;   // persistent kernel, bulk-store epilogue: 4 warps x 2 boxes of 32 rows x 128 B
 
 struct Params {
     int M, N, K;
@@ -209,7 +210,7 @@ __device__ __forceinline__ uint32_t make_idesc(int n, bool a_kmajor, bool b_kmaj
 // Fused epilogue of one W-column chunk (W = 16 or 32) of one output row: bias + activation / ReLU mask of the
 // layer input, cast, 128-bit stores.
 template <int W>
-__device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, float (&f)[W]) {
+__device__ __forceinline__ void epilogue_chunk(const Params& p, int row, int col0, float (&f)[W]) {
     const bool full = col0 + W <= p.N;
     if (p.bias) {
 #pragma unroll
@@ -238,6 +239,11 @@ __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, 
                 if (col0 + j < p.N && !(__bfloat162float(mrow[j]) > 0.f)) f[j] = 0.f;
         }
     }
+}
+template <int W>
+__device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, float (&f)[W]) {
+    const bool full = col0 + W <= p.N;
+    epilogue_chunk<W>(p, row, col0, f);
     if (p.c_bf16) {
         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
         if (full) {
@@ -578,12 +584,15 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                            const __grid_constant__ CUtensorMap tma_b,
+                                                                           const __grid_constant__ CUtensorMap tma_c,
                                                                            const Params p) {
     using C = Cfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kS = C::kStages;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kS * C::kStageBytes);
+    // bulk-store epilogue: 2 x 4 KB staging boxes per epilogue warp between the ring and the barriers (only allocated then)
+    uint8_t* stage_base = smem + kS * C::kStageBytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(stage_base + (p.tma_store ? kPersistentStageBytes : 0));
     uint64_t* empty_bar = full_bar + kS;
     uint64_t* tmem_full_bar = empty_bar + kS;          // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
@@ -599,6 +608,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
+        if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_c)) : "memory");
         for (int s = 0; s < kS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -681,6 +691,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
         const int q = warp & 3;
         int it = 0;
         double sq_acc = 0.0;
+        // bulk-store epilogue (p.tma_store): every warp stages 32 rows x 128 B (32 floats, or 2 x 32 bf16) in one of its two
+        // 4 KB boxes (128-byte swizzle) and lane 0 issues a cp.async.bulk.tensor store; a box is rewritten after the store
+        // issued two units earlier has read it.  The store's tensor map ends at the last whole 16-byte unit of a row (TMA
+        // clips ragged row ends at that granularity); the tail columns are stored by the threads.
+        const bool tma_st = p.tma_store != 0;
+        const int tail_mask = p.c_bf16 ? 7 : 3;
+        const int n4 = p.N & ~tail_mask;
+        uint8_t* wbuf = stage_base + q * 8192;
+        int unit = 0;
         for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_ph = (it >> 1) & 1;
@@ -703,13 +722,70 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
                     if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                 }
                 const int col0 = n0 + c * 32;
-                if (!row_ok || col0 >= p.N) continue;
+                if (!tma_st) {
+                    if (!row_ok || col0 >= p.N) continue;
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    store_chunk<32>(p, row, col0, f);
+                    if (p.sq_partial) sq_acc += (double)chunk_sq<32>(f, col0, p.N);
+                    continue;
+                }
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                store_chunk<32>(p, row, col0, f);
-                if (p.sq_partial) sq_acc += (double)chunk_sq<32>(f, col0, p.N);
+                if (row_ok) {
+                    epilogue_chunk<32>(p, row, col0, f);
+                    if (p.sq_partial) sq_acc += (double)chunk_sq<32>(f, col0, p.N);
+                }
+                const bool opens = !p.c_bf16 || (c & 1) == 0;                        // first (or only) half of a box
+                const bool closes = !p.c_bf16 || (c & 1) == 1 || c == n_chunks - 1;
+                uint8_t* box = wbuf + (unit & 1) * 4096;
+                if (opens) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    __syncwarp();
+                }
+                uint8_t* brow = box + lane * 128;
+                const int sw = lane & 7;
+                if (p.c_bf16) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+                        o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+                        o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+                        o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+                        *reinterpret_cast<uint4*>(brow + ((((c & 1) * 4 + j) ^ sw) << 4)) = o;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(brow + ((j ^ sw) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                }
+                if (row_ok && n4 < p.N && n4 >= col0 && n4 < col0 + 32) {               // ragged tail of the row
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (col0 + j >= n4 && col0 + j < p.N) {
+                            if (p.c_bf16) reinterpret_cast<__nv_bfloat16*>(p.C)[(long long)row * p.ldc + col0 + j] = __float2bfloat16_rn(f[j]);
+                            else reinterpret_cast<float*>(p.C)[(long long)row * p.ldc + col0 + j] = f[j];
+                        }
+                    }
+                }
+                if (closes) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int cbase = p.c_bf16 ? (n0 + (c & ~1) * 32) : col0;
+                        if (cbase < n4 && m0 + q * 32 < p.M) tma_store_2d(&tma_c, box, cbase, m0 + q * 32);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++unit;
+                }
             }
+        }
+        if (tma_st) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // boxes are read before the CTA exits
+            __syncwarp();
         }
         if (p.sq_partial) sq_partial_store(p.sq_partial + blockIdx.x, sq_acc, sq_red);
     }
@@ -751,16 +827,20 @@ struct Plan {
     int gx, gy;        // output tiles along N and M
     int ctas;          // CTAs the launch will have (= sum-of-squares slots it writes)
 };
-// 2-D f32 tensor map over the row-major output [rows, cols] with pitch ld (elements), box {32 floats, 128 rows}.
-int make_store_map(codae_ctx* ctx, CUtensorMap* map, void* base, long long rows, long long cols, long long ld) {
+// 2-D tensor map over the row-major OUTPUT [rows, cols] with pitch ld (elements) for cp.async.bulk.tensor stores:
+// boxes of 128 bytes x box_rows rows, 128-byte swizzle (f32: 32 columns, bf16: 64 columns).
+int make_store_map(codae_ctx* ctx, CUtensorMap* map, void* base, int c_dtype, long long rows, long long cols, long long ld,
+                   int box_rows) {
+    const bool bf = c_dtype == CODAE_BF16;
     const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    const cuuint32_t box[2] = {32, (cuuint32_t)BM};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * (bf ? 2 : 4)};
+    const cuuint32_t box[2] = {(cuuint32_t)(bf ? 64 : 32), (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-        map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return codae_fail(ctx, CODAE_ECUDA, "cuTensorMapEncodeTiled (f32 store map) failed (CUresult %d)", (int)r);
+        map, bf ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides, box, estr,
+        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return codae_fail(ctx, CODAE_ECUDA, "cuTensorMapEncodeTiled (store map) failed (CUresult %d)", (int)r);
     return CODAE_OK;
 }
 
@@ -825,7 +905,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     CUtensorMap mc;
     memset(&mc, 0, sizeof(mc));
     if (p.tma_store) {
-        rc = make_store_map(ctx, &mc, g.C, g.M, g.N & ~3, g.ldc);     // whole 16-byte units only; the kernel stores the tail
+        rc = make_store_map(ctx, &mc, g.C, CODAE_F32, g.M, g.N & ~3, g.ldc, BM);     // whole 16-byte units only; the kernel stores the tail
         if (rc) return rc;
     }
     p.prefetch_b = (g.b_is_weight && ctx->pdl && ctx->weight_prefetch) ? 1 : 0;
@@ -833,9 +913,17 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     if (pl.persistent) {
         static bool pattr_set = false;
         if (!pattr_set) {
-            cudaError_t e = cudaFuncSetAttribute(tc05_gemm_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
-            if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaFuncSetAttribute(smem=%u): %s", C::kSmemBytes, cudaGetErrorString(e));
+            cudaError_t e = cudaFuncSetAttribute(tc05_gemm_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(C::kSmemBytes + kPersistentStageBytes));
+            if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaFuncSetAttribute(smem=%u): %s", C::kSmemBytes + kPersistentStageBytes, cudaGetErrorString(e));
             pattr_set = true;
+        }
+        // bulk-store epilogue of the persistent kernel (opt-in): needs a row of at least one whole 16-byte unit
+        const int unit = g.c_dtype == CODAE_BF16 ? 8 : 4;
+        p.tma_store = (ctx->tma_store_persistent && (g.N & ~(unit - 1)) > 0 && (g.ldc % unit) == 0) ? 1 : 0;
+        if (p.tma_store) {
+            rc = make_store_map(ctx, &mc, g.C, g.c_dtype, g.M, g.N & ~(unit - 1), g.ldc, 32);
+            if (rc) return rc;
         }
         // raster group: 16 row-tiles measured best on the 4096-wide step (8: 7.48, 16: 7.14, 32: 7.33, 64: 7.43 ms/step);
         // CODAE_GROUP_M overrides it for tuning runs (read once)
@@ -846,7 +934,8 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
         }
         p.group_m = env_group_m;
         p.stages = C::kStages;
-        cudaError_t le = launch_pdl(ctx, tc05_gemm_persistent_kernel<BN>, dim3(ctx->sm_count), dim3(kThreads), C::kSmemBytes, s, ma, mb, p);
+        cudaError_t le = launch_pdl(ctx, tc05_gemm_persistent_kernel<BN>, dim3(ctx->sm_count), dim3(kThreads),
+                                    C::kSmemBytes + (p.tma_store ? kPersistentStageBytes : 0), s, ma, mb, mc, p);
         if (le != cudaSuccess) {
             cudaGetLastError();
             return codae_fail(ctx, CODAE_ECUDA, "tc05_gemm_persistent_kernel<%d> launch: %s", BN, cudaGetErrorString(le));

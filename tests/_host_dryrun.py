@@ -71,6 +71,13 @@ for dtype in ("fp32", "bf16"):
         fq.step(torch.arange(8)); fq.step(torch.arange(5)); fq.step(torch.arange(0))
         assert fq._bufs[8]["sq_partials"].numel() == 7 * len(m.dims) and fq.kernel_launches == 2
         fq.step(torch.arange(8)); print("wgrad_sqnorm launches", fq.kernel_launches)
+        fl = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=False, layerwise_adam=True)      # per-layer updates beside the dgrad chain
+        fl.step(torch.arange(8)); print("layerwise launches", fl.kernel_launches)          # 1 + 8 + 1 + counter + 8 wgrad + 7 dgrad + 8 adam
+        assert fl.kernel_launches == 34 and not fl.wgrad_sqnorm
+        try:
+            FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, layerwise_adam=True); raise AssertionError("layerwise_adam accepted clipping")
+        except RuntimeError:
+            pass
     else:
         try:
             FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, wgrad_sqnorm=True); raise AssertionError("fp32 engine accepted wgrad_sqnorm")
