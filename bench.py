@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--no-wgrad-sqnorm", action="store_true",
                     help="A/B (1 GPU): cooperative norm + Adam kernel instead of sum(dW^2) partials from the weight-gradient kernels")
     ap.add_argument("--no-tma-store", action="store_true", help="A/B: per-thread stores instead of TMA bulk stores for single-pass f32 tiles")
+    ap.add_argument("--chain", action="store_true",
+                    help="A/B (B <= 128): forward pass and input-gradient chain as one persistent launch each (codae_linear_chain)")
     ap.add_argument("--catalog", type=int, default=10_000_000)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -249,7 +251,8 @@ def main():
     model.to(dev)
     cor = Corrupter(w["N"], ds.arch, w["k_max"], dev, seed=w["seed"])
     fs = FusedStep(model, cor, data, lr=w["lr"], weight_decay=w["wd"], clip=w["clip"], world_size=world,
-                   use_graph=not args.no_graph, wgrad_sqnorm=False if args.no_wgrad_sqnorm else None)
+                   use_graph=not args.no_graph, wgrad_sqnorm=False if args.no_wgrad_sqnorm else None,
+                   chain_forward=True if args.chain else None, chain_backward=True if (args.chain and world == 1) else None)
     rng = np.random.RandomState(w["seed"] + rank)
     nb = Wm + K
     batches = torch.from_numpy(rng.randint(0, w["N"], size=(nb, B))).to(dev)
@@ -450,7 +453,7 @@ def profile_step(fs, idx, B, world):
     model = fs.model
     dims = model.dims
     wrapped = ["corrupt_fwd", "linear_fwd", "mse_loss_fwd_bwd", "linear_wgrad", "linear_dgrad", "grad_sqnorm", "counter_add", "adam_step",
-               "clip_adam_step", "linear_wgrad_sq", "adam_step_partials"]
+               "clip_adam_step", "linear_wgrad_sq", "adam_step_partials", "linear_chain"]
     orig = {n: getattr(_C, n) for n in wrapped}
     calls = {n: [] for n in wrapped}
 

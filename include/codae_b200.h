@@ -176,6 +176,28 @@ int codae_linear_wgrad_sq_slots(const codae_ctx* ctx, int M, int N, int K, int d
 int codae_linear_wgrad_sq(codae_ctx* ctx, const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW,
                           int64_t lddw, int M, int N, int K, int dtype, double* sq_partials, int n_slots,
                           void* stream);
+/* A CHAIN of dependent Linear layers in one persistent launch (tensor-core engine, batches of at most 128 rows):
+ * the model(c_input) call of the training loop (train_dae_on_embedding.py:204; forward :137-185) or the input-gradient
+ * chain of loss.backward() as ONE kernel instead of one per layer.  Layer l computes
+ *     C_l[M, N] = epilogue( A_l[M, K] . B_l )      A_l bf16 [M, lda]; typically A_{l+1} = C_l
+ *   b_kmajor = 1: B_l = W[N, K] (pitch ldb), C = A . W^T        (forward; act = CODAE_ACT_RELU fuses the ReLU)
+ *   b_kmajor = 0: B_l = W[K, N] (pitch ldb), C = A . W          (input gradient; mask_src [M, ldm] bf16: C *= (mask > 0))
+ *   c_dtype: CODAE_BF16 (feeds the next layer) or CODAE_F32 (last layer).
+ * Same tiles, k order and rank-ordered split-K reduction as codae_linear_fwd / codae_linear_dgrad at these sizes.
+ * OPT-IN: written and compiled, not yet validated on a B200 (FusedStep(chain_forward=True) / CODAE_CHAIN=1).
+ * workspace >= codae_linear_chain_workspace_bytes(); it is zeroed with a memset node on `stream` before the launch. */
+#define CODAE_CHAIN_MAX_LAYERS 16
+typedef struct codae_chain_layer {
+    const void* A; int64_t lda;
+    const void* B; int64_t ldb; int b_kmajor;
+    void* C; int64_t ldc; int c_dtype;
+    int N, K;
+    int act;
+    const void* mask_src; int64_t ldm;
+} codae_chain_layer;
+size_t codae_linear_chain_workspace_bytes(const codae_ctx* ctx);
+int codae_linear_chain(codae_ctx* ctx, const codae_chain_layer* layers, int n_layers, int M, void* workspace,
+                       size_t ws_bytes, void* stream);
 /* f32 -> bf16 copy of n elements (weight shadow / activation cast). */
 int codae_cast_bf16(codae_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
 

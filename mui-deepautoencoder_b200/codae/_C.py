@@ -46,6 +46,8 @@ SIGNATURES = {
     "codae_linear_wgrad": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
     "codae_linear_wgrad_sq_slots": (_i, [_vp, _i, _i, _i, _i]),
     "codae_linear_wgrad_sq": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp]),
+    "codae_linear_chain_workspace_bytes": (_sz, [_vp]),
+    "codae_linear_chain": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp]),
     "codae_cast_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "codae_sqnorm_workspace_bytes": (_sz, [_vp]),
     "codae_grad_sqnorm": (_i, [_vp, _vp, _i64, _vp, _vp, _sz, _vp]),
@@ -61,6 +63,14 @@ SIGNATURES = {
     "codae_swap_error_topk": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _f, _vp, _i64, _i64, _i, _vp, _vp, _vp,
                                    _sz, _vp]),
 }
+
+class ChainLayer(ctypes.Structure):
+    """struct codae_chain_layer (include/codae_b200.h)."""
+    _fields_ = [("A", _vp), ("lda", _i64), ("B", _vp), ("ldb", _i64), ("b_kmajor", _i), ("C", _vp), ("ldc", _i64),
+                ("c_dtype", _i), ("N", _i), ("K", _i), ("act", _i), ("mask_src", _vp), ("ldm", _i64)]
+
+
+CHAIN_MAX_LAYERS = 16
 
 _lib = None
 _lock = threading.RLock()   # re-entrant: ctx() loads the library under the same lock
@@ -243,6 +253,24 @@ def linear_wgrad_sq(dY, X, dW, M, N, K, dtype, sq_partials):
     c = ctx(dY.device)
     check(lib().codae_linear_wgrad_sq(c, p(dY), dY.stride(0), p(X), X.stride(0), p(dW), dW.stride(0), M, N, K, dtype,
                                       p(sq_partials), sq_partials.numel(), stream()), c)
+
+
+def linear_chain_workspace(device):
+    c = ctx(device)
+    return torch.zeros(int(lib().codae_linear_chain_workspace_bytes(c)), dtype=torch.uint8, device=device)
+
+
+def chain_layer(A, B, b_kmajor, C, N, K, act=ACT_NONE, mask_src=None):
+    """One entry of a codae_linear_chain call: C[M, N] = epilogue(A[M, K] . B), see include/codae_b200.h."""
+    return ChainLayer(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), 1 if b_kmajor else 0, C.data_ptr(), C.stride(0), dt(C),
+                      N, K, act, None if mask_src is None else mask_src.data_ptr(), 0 if mask_src is None else mask_src.stride(0))
+
+
+def linear_chain(layers, M, ws):
+    """layers: list of ChainLayer (their tensors must stay alive until the stream reaches the launch)."""
+    c = ctx(ws.device)
+    arr = (ChainLayer * len(layers))(*layers)
+    check(lib().codae_linear_chain(c, ctypes.cast(arr, _vp), len(layers), M, p(ws), ws.numel(), stream()), c)
 
 
 def cast_bf16(src, dst):

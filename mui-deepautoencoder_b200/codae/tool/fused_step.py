@@ -37,7 +37,7 @@ class FusedStep:
 
     def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True,
-                 fused_clip_adam=True, wgrad_sqnorm=None, layerwise_adam=None):
+                 fused_clip_adam=True, wgrad_sqnorm=None, layerwise_adam=None, chain_forward=None, chain_backward=None):
         """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
         tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
         {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
@@ -91,6 +91,21 @@ class FusedStep:
             # on wherever it applies (embedding.yaml step: 0.3446 -> 0.3367 ms); CODAE_WGRAD_SQNORM=0 switches it off
             self.wgrad_sqnorm = (os.environ.get("CODAE_WGRAD_SQNORM", "1") != "0" and world_size == 1 and self.eng == _C.BF16
                                  and fused_clip_adam)
+        if chain_forward is None:
+            # opt-in, not yet validated on a B200: the whole forward pass as ONE persistent launch (codae_linear_chain)
+            chain_forward = os.environ.get("CODAE_CHAIN") == "1" and self.eng == _C.BF16 and mixed is None
+        if chain_forward and (self.eng != _C.BF16 or len(model.dims) > _C.CHAIN_MAX_LAYERS):
+            raise RuntimeError("codae: chain_forward needs the tensor-core engine and at most %d layers" % _C.CHAIN_MAX_LAYERS)
+        self.chain_forward = bool(chain_forward)
+        if chain_backward is None:
+            # same switch: the input-gradient chain as one launch, then all weight gradients side by side on three streams
+            chain_backward = (os.environ.get("CODAE_CHAIN") == "1" and self.eng == _C.BF16 and mixed is None and world_size == 1)
+        if chain_backward and (self.eng != _C.BF16 or len(model.dims) > _C.CHAIN_MAX_LAYERS or world_size > 1):
+            raise RuntimeError("codae: chain_backward needs the tensor-core engine, at most %d layers and a single GPU "
+                               "(the data-parallel schedule reduces finished layers while the backward pass runs)" % _C.CHAIN_MAX_LAYERS)
+        self.chain_backward = bool(chain_backward)
+        self.chain_ws = _C.linear_chain_workspace(dev) if (self.chain_forward or self.chain_backward) else None
+        self._wgrad_stream2 = torch.cuda.Stream(device=dev) if self.chain_backward else None
         if layerwise_adam is None:
             # opt-in until measured on the target: CODAE_LAYERWISE_ADAM=1 turns it on wherever it applies
             layerwise_adam = os.environ.get("CODAE_LAYERWISE_ADAM") == "1" and not clip and world_size == 1 and self.eng == _C.BF16
@@ -129,6 +144,9 @@ class FusedStep:
                      idx=torch.zeros(B, dtype=torch.int64, device=dev),
                      x=torch.zeros((B, wmax), dtype=torch.float32, device=dev) if self.mixed is not None else None,
                      mon=torch.zeros((B, len(self.mixed["arch"])), dtype=torch.float32, device=dev) if self.mixed is not None else None)
+            if self.chain_backward and B <= 128:
+                # the chain keeps every layer's dL/d(out_l) until the weight gradients have read it
+                b["gchain"] = [torch.zeros((B, wmax), dtype=adt, device=dev) for _ in dims]
             if self.wgrad_sqnorm:
                 # one slot per CTA of every weight-gradient launch of this batch size
                 slots = [_C.linear_wgrad_sq_slots(dev, B, o, _round_up(i, 8) + 1, self.eng) for i, o in dims]
@@ -151,13 +169,20 @@ class FusedStep:
         n = 0
         _C.corrupt_fwd(data, idx, B, table, run, bits, col_var, self.io, acts[0], b["x"], b["mask_id"]); n += 1
         wflat = model.flat_bf16 if eng == _C.BF16 else model.flat
-        for l, (i, o) in enumerate(dims):
-            _C.linear_fwd(acts[l], model.aug_view(wflat, l), None, acts[l + 1], B, o, _round_up(i, 8) + 1,
-                          _C.ACT_RELU if model.relu[l] else _C.ACT_NONE, eng); n += 1
+        if self.chain_forward and B <= 128:
+            # every layer of the forward pass in one persistent launch (batches that fit one 128-row tile)
+            _C.linear_chain([_C.chain_layer(acts[l], model.aug_view(wflat, l), True, acts[l + 1], o, _round_up(i, 8) + 1,
+                                            _C.ACT_RELU if model.relu[l] else _C.ACT_NONE) for l, (i, o) in enumerate(dims)],
+                            B, self.chain_ws); n += 1
+        else:
+            for l, (i, o) in enumerate(dims):
+                _C.linear_fwd(acts[l], model.aug_view(wflat, l), None, acts[l + 1], B, o, _round_up(i, 8) + 1,
+                              _C.ACT_RELU if model.relu[l] else _C.ACT_NONE, eng); n += 1
         y = acts[L]
         o_last = dims[L - 1][1]
         gbuf = [b["g0"], b["g1"], b["g2"]]            # dL/d(output of layer l) lives in gbuf[l % 3]
-        g = gbuf[(L - 1) % 3][:, :_round_up(o_last, 8)]
+        chain_bwd = train and self.chain_backward and B <= 128
+        g = (b["gchain"][L - 1] if chain_bwd else gbuf[(L - 1) % 3])[:, :_round_up(o_last, 8)]
         if self.mixed is None:
             _C.mse_loss_fwd_bwd(data, idx, y, b["mask_id"], bits, col_var, B, self.io, 2.0 / (global_batch * self.io),
                                 g if train else None, self.acc, self.loss_ws); n += 1
@@ -169,6 +194,8 @@ class FusedStep:
                              nmiss, self.corrupter.k_max, b["mon"], self.mixed_acc); n += 1
         if not train:
             return n
+        if chain_bwd:
+            return n + self._enqueue_chain_backward(B, b)
         # Backward.  The input-gradient chain dgrad(L-1) -> ... -> dgrad(1) is the critical path; every weight gradient
         # only needs dL/d(out_l) and the stored activation, so wgrad(l) runs on a second stream next to dgrad(l)
         # (at B=128 each of these kernels is a ~8 us latency chain that leaves most of the GPU idle).
@@ -245,6 +272,42 @@ class FusedStep:
         if not layerwise:
             n += self._enqueue_update(b.get("sq_partials"))
         return n
+
+    def _enqueue_chain_backward(self, B, b):
+        """Backward pass around codae_linear_chain: dgrad(L-1) .. dgrad(1) in ONE persistent launch (every dL/d(out_l) is kept),
+        then the L mutually independent weight gradients spread over three streams, then the update."""
+        model, dims, eng = self.model, self.model.dims, self.eng
+        L = len(dims)
+        acts, gch = b["acts"], b["gchain"]
+        wflat = model.flat_bf16
+        n = 0
+        if L > 1:
+            layers = []
+            for l in range(L - 1, 0, -1):
+                i, o = dims[l]
+                layers.append(_C.chain_layer(gch[l][:, :_round_up(o, 8)], model.weight_view(wflat, l), False,
+                                             gch[l - 1][:, :_round_up(i, 8)], i, o, _C.ACT_NONE,
+                                             acts[l] if model.relu[l - 1] else None))
+            _C.linear_chain(layers, B, self.chain_ws); n += 1
+        main = torch.cuda.current_stream()
+        streams = [main, self._wgrad_stream, self._wgrad_stream2]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for s in streams[1:]:
+            s.wait_event(ready)
+        for l in range(L - 1, -1, -1):
+            i, o = dims[l]
+            gl = gch[l][:, :_round_up(o, 8)]
+            with torch.cuda.stream(streams[l % 3]):
+                if self.wgrad_sqnorm:
+                    sq = b["sq_partials"][b["sq_off"][l]:b["sq_off"][l + 1]]
+                    _C.linear_wgrad_sq(gl, acts[l], model.aug_view(self.gflat, l), B, o, _round_up(i, 8) + 1, eng, sq)
+                else:
+                    _C.linear_wgrad(gl, acts[l], model.aug_view(self.gflat, l), None, B, o, _round_up(i, 8) + 1, eng)
+                n += 1
+        for s in streams[1:]:
+            main.wait_stream(s)
+        return n + self._enqueue_update(b.get("sq_partials"))
 
     def _enqueue_update(self, sq_partials=None):
         """Step counter + clip + Adam over the flat buffers (after the gradients are final)."""

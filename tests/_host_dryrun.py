@@ -74,6 +74,13 @@ for dtype in ("fp32", "bf16"):
         fl = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=False, layerwise_adam=True)      # per-layer updates beside the dgrad chain
         fl.step(torch.arange(8)); print("layerwise launches", fl.kernel_launches)          # 1 + 8 + 1 + counter + 8 wgrad + 7 dgrad + 8 adam
         assert fl.kernel_launches == 34 and not fl.wgrad_sqnorm
+        fc = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, chain_forward=True)          # forward pass as one chain launch
+        fc.step(torch.arange(8)); print("chain launches", fc.kernel_launches)               # 27 - 8 fwd + 1 chain
+        assert fc.kernel_launches == 20
+        fc.evaluate(torch.arange(4))
+        fb = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, chain_forward=True, chain_backward=True)
+        fb.step(torch.arange(8)); print("chain fwd+bwd launches", fb.kernel_launches)       # corrupt, chain, loss, chain, 8 wgrad, counter, adam
+        assert fb.kernel_launches == 14
         try:
             FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, layerwise_adam=True); raise AssertionError("layerwise_adam accepted clipping")
         except RuntimeError:
