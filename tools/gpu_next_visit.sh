@@ -10,6 +10,12 @@ echo "== polyvore default"; timeout -s KILL 120 $P > gpurun_out/nv_poly.json 2> 
 echo "== polyvore, persistent bulk store"; CODAE_TMA_STORE_PERSISTENT=1 timeout -s KILL 120 $P > gpurun_out/nv_poly_tma.json 2> gpurun_out/nv_poly_tma.err; pick gpurun_out/nv_poly_tma.json
 echo "== modanet default"; timeout -s KILL 90 $M > gpurun_out/nv_modanet.json 2> gpurun_out/nv_modanet.err; pick gpurun_out/nv_modanet.json
 echo "== modanet, layer-wise Adam"; CODAE_LAYERWISE_ADAM=1 timeout -s KILL 90 $M > gpurun_out/nv_modanet_lw.json 2> gpurun_out/nv_modanet_lw.err; pick gpurun_out/nv_modanet_lw.json
+echo "== experimental: chain kernel (never run on a GPU when it was written): probe, tests, A/B"
+timeout -s KILL 150 python tests/gpu_probe_chain.py > gpurun_out/nv_chain_probe.log 2>&1; echo "probe rc=$?"; tail -12 gpurun_out/nv_chain_probe.log
+CODAE_EXPERIMENTAL=1 timeout -s KILL 300 python -m pytest tests/test_gpu_experimental.py -q -m gpu -p no:cacheprovider > gpurun_out/nv_experimental.log 2>&1; echo "rc=$?"; tail -6 gpurun_out/nv_experimental.log
+E="python bench.py --steps 1000 --warmup 50 --no-cpu --no-fp32 --no-scoring"
+echo "== embedding default"; timeout -s KILL 90 $E > gpurun_out/nv_emb.json 2> gpurun_out/nv_emb.err; pick gpurun_out/nv_emb.json
+echo "== embedding --chain"; timeout -s KILL 90 $E --chain > gpurun_out/nv_emb_chain.json 2> gpurun_out/nv_emb_chain.err; echo "rc=$?"; pick gpurun_out/nv_emb_chain.json
 echo "== ncu launch list (default command, short)"
 CMD="python bench.py --steps 3 --warmup 3 --no-scoring --no-cpu --no-fp32 --no-graph"
 timeout -s KILL 200 $CMD > gpurun_out/plain.log 2>&1 && \
