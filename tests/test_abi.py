@@ -81,3 +81,21 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 s = open(os.path.join(d, f)).read()
                 assert "oracle" not in s.replace("# oracle", ""), os.path.join(d, f)
+
+
+def test_chain_layer_struct_layout_matches_header(tmp_path):
+    """codae._C.ChainLayer mirrors struct codae_chain_layer: same size and field offsets as the C compiler sees them."""
+    import ctypes
+    from codae import _C
+    fields = [f[0] for f in _C.ChainLayer._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "codae_b200.h"\nint main(void) {\n'
+                   '  printf("%zu", sizeof(codae_chain_layer));\n' +
+                   "".join('  printf(" %%zu", offsetof(codae_chain_layer, %s));\n' % f for f in fields) +
+                   '  printf(" %d\\n", CODAE_CHAIN_MAX_LAYERS);\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    want = [ctypes.sizeof(_C.ChainLayer)] + [getattr(_C.ChainLayer, f).offset for f in fields] + [_C.CHAIN_MAX_LAYERS]
+    assert got == want, (got, want)
