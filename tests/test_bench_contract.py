@@ -1,0 +1,45 @@
+"""CPU: bench.py's reference arm runs without a GPU and prints the contract's JSON line; the product arm refuses to run
+without a B200 instead of falling back."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+
+def run_bench(*args, timeout=300):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True, timeout=timeout,
+                          cwd=ROOT)
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = run_bench("--impl", "reference", "--steps", "2", "--warmup", "1")
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1                                            # ONE JSON line
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "train samples/s" and d["unit"] == "samples/s"
+    assert d["higher_is_better"] is True and d["steps"] == 2 and d["warmup"] == 1 and d["gpu_launches"] == 0
+    assert d["value"] > 0 and abs(d["value"] - 128 * 1e3 / d["ms_per_step"]) <= 1e-6 * d["value"]
+    assert d["config"]["workload"].startswith("embedding (config/embedding.yaml)") and d["config"]["params"] == 23608320
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "steps of B=128" in cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["data"] == "synthetic"
+
+
+def test_reference_arm_other_ranks_exit_silently():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_product_arm_refuses_to_run_without_a_gpu():
+    r = run_bench("--steps", "1", "--warmup", "0", timeout=120)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
