@@ -391,6 +391,26 @@ def main():
                    "roofline": {"bound": "hbm", "achieved": bytes_per / (k_ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                                 "frac": bytes_per / (k_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None,
                                 "kernel": "score_topk_kernel (+merge)", "peak_source": pk["src"]}}
+        # the same sweep over a bf16 copy of the catalog (1024 B / candidate instead of 2048): kernel alone, this rank's shard
+        try:
+            cat_bf = catalog.to(torch.bfloat16)
+            sc_bf = ComplementarityScorer(cat_bf, w["E"], metric="sqerr", k=10, row_offset=lo)
+            for _ in range(3):
+                sc_bf.topk_local(q)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                sc_bf.topk_local(q)
+            e1.record()
+            torch.cuda.synchronize()
+            kb_ms = e0.elapsed_time(e1) / reps
+            bytes_bf = n_local * w["E"] * 2
+            scoring["bf16_catalog"] = {"value": n_local / (kb_ms / 1e3), "unit": "scores/s per GPU", "ms_per_sweep": kb_ms,
+                                       "roofline": {"bound": "hbm", "achieved": bytes_bf / (kb_ms / 1e3) / 1e9, "peak": pk["hbm"],
+                                                    "unit": "GB/s", "frac": bytes_bf / (kb_ms / 1e3) / 1e9 / pk["hbm"]}}
+            del sc_bf, cat_bf
+        except Exception as ex:  # the fp32 line above is the contract; report, do not lose the run
+            scoring["bf16_catalog"] = {"error": repr(ex)[:200]}
         # swaps scored by FULL reconstruction (candidate substituted, whole outfit through the DAE): GEMM-bound variant
         n_sw = min(n_local, 1 << 20)
         sw = SwapScorer(model, catalog[:n_sw], w["E"], k=10, row_offset=lo, chunk=8192)
