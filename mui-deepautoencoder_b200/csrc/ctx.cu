@@ -29,6 +29,22 @@ int codae_check_launch(codae_ctx* ctx, const char* what) {
     return CODAE_OK;
 }
 
+namespace {
+__global__ void stamp_kernel(unsigned long long* slot) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    *slot = t;
+}
+}  // namespace
+
+// Debugging hook (exported, deliberately absent from include/codae_b200.h): a one-thread kernel on `stream` that writes
+// %globaltimer (ns) into *slot when the stream reaches it.  tools/step_timeline.py brackets every call of a training step
+// with these to print where the time of a (graph-captured) step goes, per stream.
+extern "C" int codae_debug_stamp(void* slot, void* stream) {
+    stamp_kernel<<<1, 1, 0, as_stream(stream)>>>(reinterpret_cast<unsigned long long*>(slot));
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : CODAE_ECUDA;
+}
+
 extern "C" {
 
 int codae_version(void) { return CODAE_VERSION; }
