@@ -17,11 +17,12 @@
 #include "common.cuh"
 #include "gemm.h"
 #include "tc05_ptx.cuh"
+#include "chain_geo.h"
 
 namespace {
 
 constexpr int kThreads = 192;
-constexpr int CBN = 64;                                           // output tile width
+constexpr int CBN = kChainBN;                                     // output tile width (chain_geo.h)
 constexpr int kStages = 7;
 constexpr uint32_t kBTileBytes = CBN * BK * 2;                    // 8 KB
 constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;       // 24 KB
@@ -47,20 +48,13 @@ struct ChainParams {
     int num_layers, M;
 };
 
-struct Geo { int tiles, total_kb, kb_begin, num_kb, nsplit; };
+// work decomposition (chain_geo.h: shared with the host-side unit test tests/test_chain_geometry.py)
 __device__ __forceinline__ Geo layer_geo(const ChainParams& P, int l, int S, int rank) {
-    Geo g;
-    g.tiles = (P.layer[l].N + CBN - 1) / CBN;
-    g.total_kb = (P.layer[l].K + BK - 1) / BK;
-    const int kb_per = (g.total_kb + S - 1) / S;
-    g.nsplit = (g.total_kb + kb_per - 1) / kb_per;                // ranks >= nsplit have no k-block of this layer
-    g.kb_begin = rank * kb_per;
-    g.num_kb = max(0, min(g.total_kb, g.kb_begin + kb_per) - g.kb_begin);
-    return g;
+    return chain_layer_geo(P.layer[l].N, P.layer[l].K, S, rank);
 }
 // first (layer, tile) at or after (l, t) that exists for this cluster
 __device__ __forceinline__ void normalize_item(const ChainParams& P, int cid, int& l, int& t) {
-    while (l < P.num_layers && t >= (P.layer[l].N + CBN - 1) / CBN) { ++l; t = cid; }
+    while (l < P.num_layers && t >= chain_tiles(P.layer[l].N)) { ++l; t = cid; }
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
