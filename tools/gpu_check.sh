@@ -31,7 +31,7 @@ echo "ncu rc=$?"
 echo "== ncu full capture of the hot kernels"
 CMD2="python bench.py --steps 2 --warmup 3 --no-cpu --no-fp32 --no-graph --catalog 2000000"
 timeout -s KILL 300 $CMD2 > gpurun_out/plain2.log 2>&1 && {
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"adam_kernel|sqnorm_kernel|corrupt_fwd|mse_loss" -s 9 -c 6 -o gpurun_out/prof_r1_elementwise $CMD2 > gpurun_out/ncu_full1.log 2>&1; echo "ncu elementwise rc=$?"
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"adam_kernel|adam_partials_kernel|sqnorm_kernel|corrupt_fwd|mse_loss" -s 9 -c 6 -o gpurun_out/prof_r1_elementwise $CMD2 > gpurun_out/ncu_full1.log 2>&1; echo "ncu elementwise rc=$?"
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"score_topk_kernel" -s 2 -c 2 -o gpurun_out/prof_r1_score $CMD2 > gpurun_out/ncu_full2.log 2>&1; echo "ncu score rc=$?"
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"tc05_gemm_kernel" -s 100 -c 8 -o gpurun_out/prof_r1_gemm_small $CMD2 > gpurun_out/ncu_full3.log 2>&1; echo "ncu gemm small rc=$?"
 }
@@ -39,6 +39,6 @@ CMD3="python bench.py --workload polyvore --steps 1 --warmup 3 --no-cpu --no-sco
 timeout -s KILL 300 $CMD3 > gpurun_out/plain3.log 2>&1 && \
 timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:"tc05_gemm" -s 96 -c 8 -o gpurun_out/prof_r1_gemm_large $CMD3 > gpurun_out/ncu_full4.log 2>&1
 echo "ncu gemm large rc=$?"
-timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:"corrupt_fwd|mse_loss|clip_adam_kernel" -s 6 -c 3 -o gpurun_out/prof_r1_elementwise_large $CMD3 > gpurun_out/ncu_full5.log 2>&1
+timeout -s KILL 400 ncu --set full --clock-control none --import-source on -k regex:"corrupt_fwd|mse_loss|clip_adam_kernel|adam_partials_kernel" -s 6 -c 3 -o gpurun_out/prof_r1_elementwise_large $CMD3 > gpurun_out/ncu_full5.log 2>&1
 echo "ncu elementwise large rc=$?"
 echo "== done"
