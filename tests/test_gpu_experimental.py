@@ -48,3 +48,33 @@ print("CHAIN STEP OK", out[False][0][0] == out[True][0][0])
 ''' % (backward, HERE, HERE, HERE)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "CHAIN STEP OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_persistent_bulk_store_ragged_bf16_columns():
+    """CODAE_OPT_TMA_STORE_PERSISTENT with bf16 outputs whose width is not a multiple of 64 / 8: odd chunk counts in the last
+    column tile (half-filled box) and a row tail stored by the threads.  (The even / f32 cases are in test_gpu_optin.py.)"""
+    code = r'''
+import os, sys
+sys.path.insert(0, os.path.join(%r, "..")); sys.path.insert(0, os.path.join(%r, "..", "mui-deepautoencoder_b200"))
+import torch
+from codae import _C as C
+DEV = torch.device("cuda", 0)
+torch.manual_seed(41)
+bf = torch.bfloat16
+for M, N, K in [(8192, 1067, 264), (8192, 1040, 136), (16384, 600, 72)]:
+    ldn = (N + 7) // 8 * 8 + 8
+    X = torch.randn(M, K).to(DEV, bf)
+    W = (torch.randn(N, K) / 8).to(DEV, bf)
+    res = {}
+    for on in (0, 1):
+        C.set_option(DEV, C.OPT_TMA_STORE_PERSISTENT, on)
+        Y = torch.full((M + 1, ldn), 3.0, device=DEV, dtype=bf)
+        C.linear_fwd(X, W, None, Y[:M, :N], M, N, K, C.ACT_RELU, C.BF16)
+        torch.cuda.synchronize()
+        res[on] = Y
+    C.set_option(DEV, C.OPT_TMA_STORE_PERSISTENT, 0)
+    assert torch.equal(res[0].view(torch.int16), res[1].view(torch.int16)), (M, N, K, int((res[0] != res[1]).sum()))
+print("RAGGED OK")
+''' % (HERE, HERE)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0 and "RAGGED OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
