@@ -16,6 +16,10 @@ Replaces, per step (script/train_dae_on_embedding.py:198-223; script/train_dae_o
                               (layerwise_adam=True, no clipping, single GPU) codae_adam_step per layer on the weight-gradient
                               stream as soon as that layer's wgrad and dgrad are done: the HBM-bound optimizer overlaps the
                               latency-bound input-gradient chain (modanet_merge_top_bottom_shoe.yaml has no TRUNK_GRAD)
+  [deferred_update=True]   -> the update of step s is issued at the START of step s+1, layer by layer on its own stream, and
+                              the forward GEMM of layer l only waits for layer l's update: the HBM-bound optimizer (124 us)
+                              hides the latency-bound forward chain (72 us) of the next step.  Same arithmetic, same results;
+                              weights are final after flush() (evaluate() flushes).  Opt-in, single GPU, needs wgrad_sqnorm.
 No host synchronisation happens inside a step; monitors stay on the device until read_monitors().
 The whole sequence can be captured once per batch size into a CUDA graph (use_graph=True).
 """
@@ -37,7 +41,7 @@ class FusedStep:
 
     def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True,
-                 fused_clip_adam=True, wgrad_sqnorm=None, layerwise_adam=None, chain_forward=None, chain_backward=None):
+                 fused_clip_adam=True, wgrad_sqnorm=None, layerwise_adam=None, chain_forward=None, chain_backward=None, deferred_update=None):
         """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
         tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
         {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
@@ -118,6 +122,15 @@ class FusedStep:
         if self.wgrad_sqnorm and (world_size > 1 or self.eng != _C.BF16):
             raise RuntimeError("codae: wgrad_sqnorm needs a single GPU (the norm of a data-parallel run is taken after the "
                                "all-reduce) and the tensor-core engine")
+        if deferred_update is None:
+            # opt-in until measured on the target: CODAE_DEFERRED_UPDATE=1 turns it on wherever it applies
+            deferred_update = os.environ.get("CODAE_DEFERRED_UPDATE") == "1" and self.wgrad_sqnorm and not self.layerwise_adam
+        if deferred_update and (not self.wgrad_sqnorm or self.layerwise_adam):
+            raise RuntimeError("codae: deferred_update needs the norm-free update (wgrad_sqnorm: single GPU, tensor-core engine) "
+                               "and excludes layerwise_adam")
+        self.deferred_update = bool(deferred_update)
+        self._pending = None                       # (B, sum-of-squares partials) of the step whose gradients await their update
+        self._update_stream = torch.cuda.Stream(device=dev) if self.deferred_update else None
         self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
         self._wgrad_stream = torch.cuda.Stream(device=dev)
         self._bufs = {}
@@ -161,14 +174,38 @@ class FusedStep:
         return b
 
     # ---- the kernel sequence ----------------------------------------------------------------------------
-    def _enqueue(self, B, b, run, global_batch, data, idx, table, train=True):
+    def _enqueue(self, B, b, run, global_batch, data, idx, table, train=True, pending=None):
         model, dims, eng = self.model, self.model.dims, self.eng
         L = len(dims)
         _, bits, col_var, nmiss = self.corrupter.device_tables()
         acts = b["acts"]
         n = 0
+        updated = None
+        if pending is not None:
+            # The previous step's update, layer by layer (first layer first) on the update stream; this step's corruption and
+            # forward GEMMs run beside it on the current stream, layer l waiting only for layer l's new weights.
+            main, upd = torch.cuda.current_stream(), self._update_stream
+            fork = torch.cuda.Event()
+            fork.record(main)
+            upd.wait_event(fork)                      # the gradients and their sum-of-squares partials are complete
+            pb = model.flat_bf16 if eng == _C.BF16 else None
+            updated = []
+            with torch.cuda.stream(upd):
+                _C.counter_add(self.step_dev, 1); n += 1
+                for l in range(L):
+                    lo, hi = self._layer_span[l]
+                    _C.adam_step_partials(model.flat[lo:hi], self.gflat[lo:hi], self.m[lo:hi], self.v[lo:hi],
+                                          None if pb is None else pb[lo:hi], self.lr, self.betas[0], self.betas[1], self.eps,
+                                          self.wd, 0, self.max_norm if self.clip else -1.0, pending, self.sqnorm, 1.0,
+                                          self.step_dev); n += 1
+                    ev = torch.cuda.Event()
+                    ev.record(upd)
+                    updated.append(ev)
         _C.corrupt_fwd(data, idx, B, table, run, bits, col_var, self.io, acts[0], b["x"], b["mask_id"]); n += 1
         wflat = model.flat_bf16 if eng == _C.BF16 else model.flat
+        if updated is not None and self.chain_forward and B <= 128:
+            torch.cuda.current_stream().wait_stream(self._update_stream)      # the chain launch reads every layer's weights
+            updated = None
         if self.chain_forward and B <= 128:
             # every layer of the forward pass in one persistent launch (batches that fit one 128-row tile)
             _C.linear_chain([_C.chain_layer(acts[l], model.aug_view(wflat, l), True, acts[l + 1], o, _round_up(i, 8) + 1,
@@ -176,8 +213,12 @@ class FusedStep:
                             B, self.chain_ws); n += 1
         else:
             for l, (i, o) in enumerate(dims):
+                if updated is not None:
+                    torch.cuda.current_stream().wait_event(updated[l])
                 _C.linear_fwd(acts[l], model.aug_view(wflat, l), None, acts[l + 1], B, o, _round_up(i, 8) + 1,
                               _C.ACT_RELU if model.relu[l] else _C.ACT_NONE, eng); n += 1
+            if updated is not None:
+                torch.cuda.current_stream().wait_stream(self._update_stream)  # join (every event above has fired by now)
         y = acts[L]
         o_last = dims[L - 1][1]
         gbuf = [b["g0"], b["g1"], b["g2"]]            # dL/d(output of layer l) lives in gbuf[l % 3]
@@ -269,7 +310,7 @@ class FusedStep:
         elif self.world_size > 1:
             import torch.distributed as dist
             dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
-        if not layerwise:
+        if not layerwise and not self.deferred_update:
             n += self._enqueue_update(b.get("sq_partials"))
         return n
 
@@ -307,7 +348,7 @@ class FusedStep:
                 n += 1
         for s in streams[1:]:
             main.wait_stream(s)
-        return n + self._enqueue_update(b.get("sq_partials"))
+        return n if self.deferred_update else n + self._enqueue_update(b.get("sq_partials"))
 
     def _enqueue_update(self, sq_partials=None):
         """Step counter + clip + Adam over the flat buffers (after the gradients are final)."""
@@ -360,6 +401,7 @@ class FusedStep:
         B = int(batch_idx.numel()) if staged is None else int(staged[0].shape[0])
         gb = B * self.world_size if global_batch is None else global_batch
         if B == 0:
+            self.flush()
             self.step_count += 1
             self._step_without_samples()
             return
@@ -371,14 +413,20 @@ class FusedStep:
             data, idx = self.data, b["idx"]
             idx.copy_(batch_idx, non_blocking=True)
         self.step_count += 1
-        key = (B, run, gb, None if staged is None else (staged[0].data_ptr(), staged[1].data_ptr()))
+        pending = None
+        if self.deferred_update:
+            if self._pending is not None and self._pending[0] != B:
+                self.flush()             # the partials buffer belongs to the other batch size: apply that update on its own
+            pending = None if self._pending is None else self._pending[1]
+            self._pending = (B, b["sq_partials"])
+        key = (B, run, gb, None if staged is None else (staged[0].data_ptr(), staged[1].data_ptr()), pending is not None)
         if not self.use_graph:
-            self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table)
+            self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table, pending=pending)
             return
         calls = self._calls.get(key, 0)
         self._calls[key] = calls + 1
         if calls == 0:            # first step of this shape runs eagerly (lazy attribute setup, warm caches)
-            self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table)
+            self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table, pending=pending)
             return
         gr = self._graphs.get(key)
         if gr is None:
@@ -387,13 +435,21 @@ class FusedStep:
             self._static = getattr(self, "_static", {})
             self._static[key] = (data, idx, table)
             with torch.cuda.graph(gr):
-                self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table)
+                self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table, pending=pending)
             self._graphs[key] = gr
         gr.replay()
+
+    def flush(self):
+        """deferred_update: apply the update that the last step() left pending (one launch over the flat buffers).  After it
+        the weights, moments and the bf16 shadow are those the reference has after optimizer.step().  No-op otherwise."""
+        if self._pending is not None:
+            self._enqueue_update(self._pending[1])
+            self._pending = None
 
     def evaluate(self, batch_idx, run=0):
         """Validation pass: corruption + forward + monitor sums only (train_dae_on_embedding.py:241-259),
         without building any autograd state.  Returns the reconstruction [B, io] (device, fp32)."""
+        self.flush()
         B = int(batch_idx.numel())
         b = self._buffers(B)
         b["idx"].copy_(batch_idx, non_blocking=True)

@@ -78,6 +78,14 @@ for dtype in ("fp32", "bf16"):
         fc.step(torch.arange(8)); print("chain launches", fc.kernel_launches)               # 27 - 8 fwd + 1 chain
         assert fc.kernel_launches == 20
         fc.evaluate(torch.arange(4))
+        fd = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, deferred_update=True)         # update pipelined into the next step
+        fd.step(torch.arange(8)); first = fd.kernel_launches                                 # nothing pending: no update launches
+        fd.step(torch.arange(8)); second = fd.kernel_launches                                # counter + 8 per-layer updates first
+        print("deferred launches", first, second)
+        assert first == 25 and second == 25 + 1 + 8 and fd._pending is not None
+        fd.step(torch.arange(5)); assert fd._pending[0] == 5                                 # other batch size: flushed, then pending again
+        fd.evaluate(torch.arange(4)); assert fd._pending is None
+        fd.flush()
         fb = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, chain_forward=True, chain_backward=True)
         fb.step(torch.arange(8)); print("chain fwd+bwd launches", fb.kernel_launches)       # corrupt, chain, loss, chain, 8 wgrad, counter, adam
         assert fb.kernel_launches == 14

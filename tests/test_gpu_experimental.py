@@ -78,3 +78,44 @@ print("RAGGED OK")
 ''' % (HERE, HERE)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
     assert r.returncode == 0 and "RAGGED OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_deferred_update_gives_the_same_weights(graph):
+    """FusedStep(deferred_update=True): the update of step s runs at the start of step s+1 (per layer, beside the forward pass).
+    Same kernels, same arithmetic: losses of every step and the weights after flush() equal the default schedule's bit for bit."""
+    code = r'''
+import os, sys
+GRAPH = %s
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "..")); sys.path.insert(0, os.path.join(%r, "..", "mui-deepautoencoder_b200"))
+import numpy as np, torch
+from conftest import GOLDEN
+from test_gpu_training import build_embedding, DEV
+from codae.tool import FusedStep
+g = np.load(os.path.join(GOLDEN, "emb_mid.npz"))
+B = int(g["B"])
+out = {}
+for deferred in (False, True):
+    ds, model, cor = build_embedding(g, dtype="bf16")
+    fs = FusedStep(model, cor, ds.data, lr=float(g["lr"]), weight_decay=float(g["wd"]), clip=True, use_graph=GRAPH,
+                   deferred_update=deferred)
+    losses = []
+    for rep in range(3):
+        s = 0
+        while "idx%%d" %% s in g:
+            fs.step(torch.from_numpy(g["idx%%d" %% s]).to(DEV), run=0)
+            losses.append(fs.last_loss(B))
+            s += 1
+    fs.flush()
+    torch.cuda.synchronize()
+    out[deferred] = (losses, model.flat.clone(), fs.m.clone(), fs.v.clone(), model.flat_bf16.clone(), int(fs.step_dev.item()))
+a, b = out[False], out[True]
+assert a[0] == b[0], (a[0], b[0])
+assert a[5] == b[5] == len(a[0])
+for x, y in zip(a[1:4], b[1:4]):
+    assert torch.equal(x, y)
+assert torch.equal(a[4].view(torch.int16), b[4].view(torch.int16))
+print("DEFERRED OK")
+''' % (graph, HERE, HERE, HERE)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0 and "DEFERRED OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -16,6 +16,7 @@ CODAE_EXPERIMENTAL=1 timeout -s KILL 300 python -m pytest tests/test_gpu_experim
 E="python bench.py --steps 1000 --warmup 50 --no-cpu --no-fp32 --no-scoring"
 echo "== embedding default"; timeout -s KILL 90 $E > gpurun_out/nv_emb.json 2> gpurun_out/nv_emb.err; pick gpurun_out/nv_emb.json
 echo "== embedding --chain"; timeout -s KILL 90 $E --chain > gpurun_out/nv_emb_chain.json 2> gpurun_out/nv_emb_chain.err; echo "rc=$?"; pick gpurun_out/nv_emb_chain.json
+echo "== embedding --deferred-update (update of step s beside the forward pass of step s+1)"; timeout -s KILL 90 $E --deferred-update > gpurun_out/nv_emb_deferred.json 2> gpurun_out/nv_emb_deferred.err; echo "rc=$?"; pick gpurun_out/nv_emb_deferred.json
 echo "== embedding --no-pdl"; timeout -s KILL 90 $E --no-pdl > gpurun_out/nv_emb_nopdl.json 2> gpurun_out/nv_emb_nopdl.err; pick gpurun_out/nv_emb_nopdl.json
 echo "== step timeline (stamp kernels around every call, per stream)"; timeout -s KILL 120 python tools/step_timeline.py > gpurun_out/nv_timeline.txt 2>&1; echo "rc=$?"; tail -40 gpurun_out/nv_timeline.txt
 echo "== ncu launch list (default command, short)"
