@@ -1,0 +1,287 @@
+# Data-race check of FusedStep's multi-stream schedules on the CPU (run by test_schedule_races.py in a subprocess: it
+# monkeypatches torch.cuda).  Every C-ABI call becomes a node with the byte intervals it reads and writes; fake streams and
+# events record exactly the ordering the real ones would impose (stream order, wait_event, wait_stream).  For every pair of
+# calls that touch overlapping bytes with at least one write, the earlier one must HAPPEN BEFORE the later one through
+# those edges -- otherwise the two kernels could run concurrently on the GPU and the schedule has a race.
+# Three consecutive steps are issued per scenario so that hazards across step boundaries are covered as well.
+import ctypes
+import os
+import sys
+
+_R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _R)
+sys.path.insert(0, os.path.join(_R, "mui-deepautoencoder_b200"))
+import torch  # noqa: E402
+
+torch.Tensor.is_cuda = property(lambda self: True)
+from codae import _C  # noqa: E402
+
+NODES = []          # dict(name, stream, reads, writes, preds)
+
+
+class FakeStream:
+    count = 0
+
+    def __init__(self, *a, **k):
+        self.last = None
+        FakeStream.count += 1
+        self.name = "s%d" % FakeStream.count
+        self.cuda_stream = FakeStream.count
+
+    def _node(self, name, reads=(), writes=(), extra=()):
+        preds = set(extra)
+        if self.last is not None:
+            preds.add(self.last)
+        NODES.append(dict(name=name, stream=self.name, reads=list(reads), writes=list(writes), preds=preds))
+        self.last = len(NODES) - 1
+        return self.last
+
+    def wait_event(self, e):
+        if e.node is not None:
+            self._node("wait_event", extra=[e.node])
+
+    def wait_stream(self, s):
+        if s.last is not None:
+            self._node("wait_stream", extra=[s.last])
+
+    def synchronize(self):
+        pass
+
+
+class FakeEvent:
+    def __init__(self, *a, **k):
+        self.node = None
+
+    def record(self, stream=None):
+        s = stream if stream is not None else CUR[-1]
+        self.node = s.last
+
+
+MAIN = FakeStream()
+CUR = [MAIN]
+
+
+class _Use:
+    def __init__(self, s):
+        self.s = s
+
+    def __enter__(self):
+        CUR.append(self.s)
+        return self.s
+
+    def __exit__(self, *a):
+        CUR.pop()
+        return False
+
+
+torch.cuda.Stream = FakeStream
+torch.cuda.Event = FakeEvent
+torch.cuda.current_stream = lambda *a, **k: CUR[-1]
+torch.cuda.stream = lambda s: _Use(s)
+torch.cuda.synchronize = lambda *a: None
+torch.cuda.current_device = lambda: 0
+
+
+def span(t):
+    """Byte interval [lo, hi) a (possibly strided) tensor view can touch."""
+    if t is None:
+        return None
+    es = t.element_size()
+    lo = t.untyped_storage().data_ptr() + t.storage_offset() * es
+    ext = 1
+    for n, st in zip(t.shape, t.stride()):
+        if n == 0:
+            return None
+        ext += (n - 1) * st
+    return (lo, lo + ext * es)
+
+
+def op(name, reads, writes):
+    CUR[-1]._node(name, [s for s in map(span, reads) if s], [s for s in map(span, writes) if s])
+
+
+# ---- the C ABI wrappers, as access declarations (argument order: codae/_C.py) ------------------------------------------
+def corrupt_fwd(data, batch_idx, B, mask_table, run, mask_bits, col_var, io, out_cx, out_x=None, out_mask_id=None):
+    op("corrupt_fwd", [data, batch_idx, mask_table, mask_bits, col_var], [out_cx, out_x, out_mask_id])
+
+
+def linear_fwd(X, W, bias, Y, M, N, K, act, dtype):
+    op("linear_fwd", [X[:M, :K], W[:N, :K], bias], [Y[:M, :N]])
+
+
+def linear_dgrad(dY, W, A_prev, dX, M, N, K, dtype):
+    op("linear_dgrad", [dY[:M, :N], W[:N, :K], None if A_prev is None else A_prev[:M, :K]], [dX[:M, :K]])
+
+
+def linear_wgrad(dY, X, dW, db, M, N, K, dtype):
+    op("linear_wgrad", [dY[:M, :N], X[:M, :K]], [dW[:N, :K], db])
+
+
+def linear_wgrad_sq(dY, X, dW, M, N, K, dtype, sq):
+    op("linear_wgrad_sq", [dY[:M, :N], X[:M, :K]], [dW[:N, :K], sq])
+
+
+def mse_loss_fwd_bwd(x, batch_idx, y, mask_id, mask_bits, col_var, B, io, grad_scale, dy, acc, ws):
+    op("mse_loss_fwd_bwd", [x, batch_idx, y, mask_id, acc], [dy, acc, ws])
+
+
+def counter_add(counter, delta):
+    op("counter_add", [counter], [counter])
+
+
+def grad_sqnorm(g, out, ws):
+    op("grad_sqnorm", [g], [out, ws])
+
+
+def adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm, grad_scale, step_dev=None):
+    op("adam_step", [pf, g, m, v, sqnorm, step_dev], [pf, m, v, p_bf16])
+
+
+def adam_step_partials(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sq_partials, sqnorm_out, grad_scale, step_dev=None):
+    op("adam_step_partials", [pf, g, m, v, sq_partials, step_dev], [pf, m, v, p_bf16, sqnorm_out])
+
+
+def clip_adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm_out, ws, grad_scale, step_dev=None):
+    op("clip_adam_step", [pf, g, m, v, step_dev], [pf, m, v, p_bf16, sqnorm_out, ws])
+
+
+def cast_bf16(src, dst):
+    op("cast_bf16", [src], [dst])
+
+
+def chain_layer(A, B, b_kmajor, C, N, K, act=0, mask_src=None):
+    return (A, B, b_kmajor, C, N, K, mask_src)
+
+
+def linear_chain(layers, M, ws):
+    reads, writes = [], [ws]
+    for A, B, bk, C, N, K, mask in layers:
+        reads += [A[:M, :K], B[:N, :K] if bk else B[:K, :N], None if mask is None else mask[:M, :N]]
+        writes.append(C[:M, :N])
+    # the kernel orders its own layers (grid barrier); towards the rest of the step it is ONE node
+    op("linear_chain", reads, writes)
+
+
+for _n in ("corrupt_fwd", "linear_fwd", "linear_dgrad", "linear_wgrad", "linear_wgrad_sq", "mse_loss_fwd_bwd", "counter_add",
+           "grad_sqnorm", "adam_step", "adam_step_partials", "clip_adam_step", "cast_bf16", "chain_layer", "linear_chain"):
+    setattr(_C, _n, globals()[_n])
+_C.linear_engine = lambda device, dtype, M, N, K: 1 if (dtype == 1 and N >= 32 and K >= 32) else 0
+_C.linear_wgrad_sq_slots = lambda device, M, N, K, dtype: 7 if dtype == 1 else 0
+_C.sqnorm_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
+_C.loss_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
+_C.linear_chain_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
+_C.ctx = lambda device=None: ctypes.c_void_p(1)
+
+import codae.model._flat_mlp as fm  # noqa: E402
+
+
+def _to(self, *a, **k):
+    self._flatten(torch.device("cpu"))
+    return self
+
+
+fm.FlatMLP.to = _to
+import codae.tool.data_tool as dtl  # noqa: E402
+
+dtl.Corrupter._cuda_device = lambda self: torch.device("cpu")
+_C.mask_table_philox = lambda seed, first, n, nb_run, device: torch.zeros((n, nb_run), dtype=torch.int16)
+
+import torch.distributed as dist  # noqa: E402
+
+
+def _all_reduce(t, op=None, group=None):
+    globals()["op"]("all_reduce", [t], [t])
+
+
+dist.all_reduce = _all_reduce
+
+from codae.dataset import ConcatenatedEmbeddingDataset  # noqa: E402
+from codae.model import EmbeddingDenoisingAutoencoder  # noqa: E402
+from codae.tool import Corrupter, FusedStep  # noqa: E402
+
+
+def overlap(a, b):
+    return a[0] < b[1] and b[0] < a[1]
+
+
+def check(tag):
+    n = len(NODES)
+    reach = [0] * n            # bitset of ancestors
+    for j in range(n):
+        r = 0
+        for i in NODES[j]["preds"]:
+            r |= reach[i] | (1 << i)
+        reach[j] = r
+    races = []
+    for j in range(n):
+        nj = NODES[j]
+        if not (nj["reads"] or nj["writes"]):
+            continue
+        for i in range(j):
+            ni = NODES[i]
+            if (reach[j] >> i) & 1:
+                continue
+            hit = any(overlap(w, x) for w in ni["writes"] for x in nj["reads"] + nj["writes"]) or \
+                any(overlap(r_, w) for r_ in ni["reads"] for w in nj["writes"])
+            if hit:
+                races.append((i, ni["name"], ni["stream"], j, nj["name"], nj["stream"]))
+    kernels = sum(1 for x in NODES if x["reads"] or x["writes"])
+    streams = len({x["stream"] for x in NODES})
+    print("%-34s %3d calls on %d streams, %d unordered conflicting pairs" % (tag, kernels, streams, len(races)))
+    for r in races[:8]:
+        print("   RACE: #%d %s (%s)  <->  #%d %s (%s)" % r)
+    return len(races)
+
+
+def scenario(tag, dtype="bf16", clip=True, world=1, steps=3, batches=(8, 8, 8), **kw):
+    del NODES[:]
+    MAIN.last = None
+    ds = ConcatenatedEmbeddingDataset.from_tensors([torch.rand(64, 32) for _ in range(3)])
+    m = EmbeddingDenoisingAutoencoder(96, 40, 32, 3, 3, False)
+    m.set_compute_dtype(dtype)
+    m.to(torch.device("cpu"))
+    cor = Corrupter(64, ds.arch, 2, torch.device("cpu"))
+    fs = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=clip, world_size=world, **kw)
+    for B in batches:
+        fs.step(torch.arange(B))
+    fs.evaluate(torch.arange(4))
+    fs.step(torch.arange(batches[0]))
+    fs.flush()
+    return check(tag)
+
+
+bad = 0
+bad += scenario("default (norm-free update)")
+bad += scenario("cooperative clip+Adam", wgrad_sqnorm=False)
+bad += scenario("separate norm + Adam kernels", wgrad_sqnorm=False, fused_clip_adam=False)
+bad += scenario("fp32 engine (one stream)", dtype="fp32")
+bad += scenario("un-clipped", clip=False)
+bad += scenario("layer-wise Adam", clip=False, layerwise_adam=True)
+bad += scenario("deferred update", deferred_update=True)
+bad += scenario("deferred update, ragged batch", deferred_update=True, batches=(8, 8, 5, 8))
+bad += scenario("chain forward", chain_forward=True)
+bad += scenario("chain forward + backward", chain_forward=True, chain_backward=True)
+bad += scenario("chain + deferred update", chain_forward=True, chain_backward=True, deferred_update=True)
+bad += scenario("data parallel, overlapped all-reduce", world=2)
+bad += scenario("data parallel, one all-reduce", world=2, overlap_allreduce=False)
+
+# the checker itself: a schedule with a known race must be flagged
+del NODES[:]
+MAIN.last = None
+side = FakeStream()
+a, b_ = torch.zeros(16), torch.zeros(16)
+op("writer", [], [a])
+with torch.cuda.stream(side):
+    op("reader without a wait", [a], [b_])
+assert check("self-test: missing wait_event") == 1
+del NODES[:]
+MAIN.last = None
+op("writer", [], [a])
+ev = FakeEvent()
+ev.record(MAIN)
+side.wait_event(ev)
+with torch.cuda.stream(side):
+    op("reader after wait_event", [a], [b_])
+assert check("self-test: with wait_event") == 0
+print("SCHEDULES OK" if bad == 0 else "SCHEDULE RACES: %d" % bad)
+sys.exit(0 if bad == 0 else 1)
