@@ -19,7 +19,8 @@ Replaces, per step (script/train_dae_on_embedding.py:198-223; script/train_dae_o
   [deferred_update=True]   -> the update of step s is issued at the START of step s+1, layer by layer on its own stream, and
                               the forward GEMM of layer l only waits for layer l's update: the HBM-bound optimizer (124 us)
                               hides the latency-bound forward chain (72 us) of the next step.  Same arithmetic, same results;
-                              weights are final after flush() (evaluate() flushes).  Opt-in, single GPU, needs wgrad_sqnorm.
+                              weights are final after flush() (evaluate() flushes).  Opt-in.  Without the per-CTA partials
+                              (data parallel, fp32 engine) the prologue takes the norm with codae_grad_sqnorm first.
 No host synchronisation happens inside a step; monitors stay on the device until read_monitors().
 The whole sequence can be captured once per batch size into a CUDA graph (use_graph=True).
 """
@@ -124,12 +125,11 @@ class FusedStep:
                                "all-reduce) and the tensor-core engine")
         if deferred_update is None:
             # opt-in until measured on the target: CODAE_DEFERRED_UPDATE=1 turns it on wherever it applies
-            deferred_update = os.environ.get("CODAE_DEFERRED_UPDATE") == "1" and self.wgrad_sqnorm and not self.layerwise_adam
-        if deferred_update and (not self.wgrad_sqnorm or self.layerwise_adam):
-            raise RuntimeError("codae: deferred_update needs the norm-free update (wgrad_sqnorm: single GPU, tensor-core engine) "
-                               "and excludes layerwise_adam")
+            deferred_update = os.environ.get("CODAE_DEFERRED_UPDATE") == "1" and not self.layerwise_adam and mixed is None
+        if deferred_update and self.layerwise_adam:
+            raise RuntimeError("codae: deferred_update excludes layerwise_adam (both schedule the per-layer updates)")
         self.deferred_update = bool(deferred_update)
-        self._pending = None                       # (B, sum-of-squares partials) of the step whose gradients await their update
+        self._pending = None                       # (B, sum-of-squares partials | None) of the step whose gradients await their update
         self._update_stream = torch.cuda.Stream(device=dev) if self.deferred_update else None
         self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
         self._wgrad_stream = torch.cuda.Stream(device=dev)
@@ -192,12 +192,18 @@ class FusedStep:
             updated = []
             with torch.cuda.stream(upd):
                 _C.counter_add(self.step_dev, 1); n += 1
+                partials = pending[1]
+                if partials is None and self.clip:          # no per-CTA partials (data parallel / fp32 engine): one norm pass
+                    _C.grad_sqnorm(self.gflat, self.sqnorm, self.norm_ws); n += 1
                 for l in range(L):
                     lo, hi = self._layer_span[l]
-                    _C.adam_step_partials(model.flat[lo:hi], self.gflat[lo:hi], self.m[lo:hi], self.v[lo:hi],
-                                          None if pb is None else pb[lo:hi], self.lr, self.betas[0], self.betas[1], self.eps,
-                                          self.wd, 0, self.max_norm if self.clip else -1.0, pending, self.sqnorm, 1.0,
-                                          self.step_dev); n += 1
+                    args = (model.flat[lo:hi], self.gflat[lo:hi], self.m[lo:hi], self.v[lo:hi], None if pb is None else pb[lo:hi],
+                            self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, self.max_norm if self.clip else -1.0)
+                    if partials is not None:
+                        _C.adam_step_partials(*args, partials, self.sqnorm, 1.0, self.step_dev)
+                    else:
+                        _C.adam_step(*args, self.sqnorm if self.clip else None, 1.0, self.step_dev)
+                    n += 1
                     ev = torch.cuda.Event()
                     ev.record(upd)
                     updated.append(ev)
@@ -417,8 +423,8 @@ class FusedStep:
         if self.deferred_update:
             if self._pending is not None and self._pending[0] != B:
                 self.flush()             # the partials buffer belongs to the other batch size: apply that update on its own
-            pending = None if self._pending is None else self._pending[1]
-            self._pending = (B, b["sq_partials"])
+            pending = self._pending
+            self._pending = (B, b.get("sq_partials"))
         key = (B, run, gb, None if staged is None else (staged[0].data_ptr(), staged[1].data_ptr()), pending is not None)
         if not self.use_graph:
             self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table, pending=pending)
@@ -443,7 +449,7 @@ class FusedStep:
         """deferred_update: apply the update that the last step() left pending (one launch over the flat buffers).  After it
         the weights, moments and the bf16 shadow are those the reference has after optimizer.step().  No-op otherwise."""
         if self._pending is not None:
-            self._enqueue_update(self._pending[1])
+            self._enqueue_update(self._pending[1])       # partials, or None -> the cooperative / two-kernel norm + update
             self._pending = None
 
     def evaluate(self, batch_idx, run=0):

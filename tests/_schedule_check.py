@@ -259,6 +259,10 @@ bad += scenario("un-clipped", clip=False)
 bad += scenario("layer-wise Adam", clip=False, layerwise_adam=True)
 bad += scenario("deferred update", deferred_update=True)
 bad += scenario("deferred update, ragged batch", deferred_update=True, batches=(8, 8, 5, 8))
+bad += scenario("deferred update, norm pass (no partials)", deferred_update=True, wgrad_sqnorm=False)
+bad += scenario("deferred update, fp32 engine", dtype="fp32", deferred_update=True)
+bad += scenario("deferred update, un-clipped", clip=False, deferred_update=True)
+bad += scenario("deferred update, data parallel", world=2, deferred_update=True)
 bad += scenario("chain forward", chain_forward=True)
 bad += scenario("chain forward + backward", chain_forward=True, chain_backward=True)
 bad += scenario("chain + deferred update", chain_forward=True, chain_backward=True, deferred_update=True)
