@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--chain", action="store_true",
                     help="A/B (B <= 128): forward pass and input-gradient chain as one persistent launch each (codae_linear_chain)")
     ap.add_argument("--deferred-update", action="store_true",
-                    help="A/B (1 GPU): the update of step s runs per layer at the start of step s+1, beside its forward pass")
+                    help="A/B: the update of step s runs per layer at the start of step s+1, beside its forward pass")
     ap.add_argument("--catalog", type=int, default=10_000_000)
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
@@ -255,7 +255,7 @@ def main():
     fs = FusedStep(model, cor, data, lr=w["lr"], weight_decay=w["wd"], clip=w["clip"], world_size=world,
                    use_graph=not args.no_graph, wgrad_sqnorm=False if args.no_wgrad_sqnorm else None,
                    chain_forward=True if args.chain else None, chain_backward=True if (args.chain and world == 1) else None,
-                   deferred_update=True if (args.deferred_update and world == 1) else None)
+                   deferred_update=True if args.deferred_update else None)
     rng = np.random.RandomState(w["seed"] + rank)
     nb = Wm + K
     batches = torch.from_numpy(rng.randint(0, w["N"], size=(nb, B))).to(dev)
