@@ -26,7 +26,7 @@ from codae.tool import Corrupter, FusedStep
 from codae.tool.inference import ComplementarityScorer, shard_rows
 
 
-def build(dtype, ws, graph, overlap=True):
+def build(dtype, ws, graph, overlap=True, deferred=False):
     torch.manual_seed(3)
     S, E, N = 3, 128, 1024
     cats = [torch.randn(N, E).abs() for _ in range(S)]
@@ -36,7 +36,8 @@ def build(dtype, ws, graph, overlap=True):
     m.to(dev)
     ds.to(dev)
     cor = Corrupter(N, ds.arch, 1, dev, seed=77)
-    fs = FusedStep(m, cor, ds.data, lr=1e-3, weight_decay=1e-4, clip=True, world_size=ws, use_graph=graph, overlap_allreduce=overlap)
+    fs = FusedStep(m, cor, ds.data, lr=1e-3, weight_decay=1e-4, clip=True, world_size=ws, use_graph=graph, overlap_allreduce=overlap,
+                   deferred_update=deferred)
     return ds, m, cor, fs
 
 
@@ -75,6 +76,25 @@ for dtype, graph, tol in [("fp32", False, 1e-5), ("bf16", False, 1e-2), ("bf16",
           print("DP %s graph=%s overlap=%s: tables_equal=%s replicas_bitwise_equal=%s |w_dp - w_1|/|w| = %.2e (tol %.0e) -> %s"
                 % (dtype, graph, overlap, same_table, replicas_equal, err, tol, "OK" if good else "FAIL"), flush=True)
       del fs, fs1
+
+# deferred update under data parallelism (opt-in schedule): same weights as the immediate update, bit for bit, on every rank
+if os.environ.get("CODAE_EXPERIMENTAL") == "1":
+    for graph in (False, True):
+        rng = np.random.RandomState(6)
+        batches = [rng.permutation(1024)[:64 * world] for _ in range(5)]
+        res = {}
+        for deferred in (False, True):
+            ds, m, cor, fs = build("bf16", world, graph, True, deferred)
+            for gidx in batches:
+                fs.step(torch.as_tensor(gidx[rank::world], dtype=torch.int64, device=dev), global_batch=len(gidx))
+            fs.flush()
+            torch.cuda.synchronize()
+            res[deferred] = flat(m)
+            del fs
+        good = torch.equal(res[False], res[True])
+        ok &= good
+        if rank == 0:
+            print("DP deferred update graph=%s: weights bitwise equal to the immediate update: %s" % (graph, "OK" if good else "FAIL"), flush=True)
 
 # sharded catalog
 torch.manual_seed(9)
