@@ -77,7 +77,8 @@ for dtype, graph, tol in [("fp32", False, 1e-5), ("bf16", False, 1e-2), ("bf16",
                 % (dtype, graph, overlap, same_table, replicas_equal, err, tol, "OK" if good else "FAIL"), flush=True)
       del fs, fs1
 
-# deferred update under data parallelism (opt-in schedule): same weights as the immediate update, bit for bit, on every rank
+# deferred update under data parallelism (opt-in schedule): same weights as the immediate update up to the summation order of
+# the norm (cooperative kernel there, codae_grad_sqnorm here: the clip scale may differ by an fp32 ulp)
 if os.environ.get("CODAE_EXPERIMENTAL") == "1":
     for graph in (False, True):
         rng = np.random.RandomState(6)
@@ -91,10 +92,11 @@ if os.environ.get("CODAE_EXPERIMENTAL") == "1":
             torch.cuda.synchronize()
             res[deferred] = flat(m)
             del fs
-        good = torch.equal(res[False], res[True])
+        err = float((res[False] - res[True]).abs().max() / res[False].abs().max())
+        good = err < 1e-4
         ok &= good
         if rank == 0:
-            print("DP deferred update graph=%s: weights bitwise equal to the immediate update: %s" % (graph, "OK" if good else "FAIL"), flush=True)
+            print("DP deferred update graph=%s: |w_deferred - w_immediate|/|w| = %.2e -> %s" % (graph, err, "OK" if good else "FAIL"), flush=True)
 
 # sharded catalog
 torch.manual_seed(9)
