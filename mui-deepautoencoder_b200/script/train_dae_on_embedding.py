@@ -124,6 +124,7 @@ if __name__ == "__main__":
             log.info("VALIDATION PARTIAL ERROR = %7f" % pvl)
             log.info("VALIDATION RANKING ERROR = %7f" % book["rl"][-1])
 
+    trainer.flush()        # a deferred update (CODAE_DEFERRED_UPDATE=1) is applied before the weights are read; no-op otherwise
     if rank == 0:
         log.info("TRAINING HAS ENDED.")
         d = os.path.join(args.output_path, get_date() + "_train_" + config["DATASET"]["NAME"])
