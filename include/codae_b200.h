@@ -72,6 +72,11 @@ int codae_ctx_sm_count(const codae_ctx* ctx);
 enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1, CODAE_OPT_PERSISTENT = 2, CODAE_OPT_WEIGHT_PREFETCH = 3,
                     CODAE_OPT_TMA_STORE = 4, CODAE_OPT_TMA_STORE_PERSISTENT = 5 };
 int codae_ctx_set_option(codae_ctx* ctx, int option, int value);
+/* Tells the library that `stream` has just been made to wait (event / stream wait) for work on ANOTHER stream that writes
+ * layer weights -- e.g. an optimizer launch on a side stream.  The next launch on `stream` is then issued with a full stream
+ * dependency instead of a programmatic one, so that its weight-tile prefetch (CODAE_OPT_WEIGHT_PREFETCH) cannot run ahead of
+ * that wait.  Weight writers on the SAME stream are tracked by the library itself. */
+int codae_weights_written(codae_ctx* ctx, void* stream);
 /* Current value (0 / 1) of a tuning switch, CODAE_EINVAL for an unknown option. */
 int codae_ctx_get_option(const codae_ctx* ctx, int option);
 /* Which engine codae_linear_* will use for (dtype, M, N, K). */

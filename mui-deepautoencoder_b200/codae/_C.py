@@ -32,6 +32,7 @@ SIGNATURES = {
     "codae_ctx_sm_count": (_i, [_vp]),
     "codae_ctx_set_option": (_i, [_vp, _i, _i]),
     "codae_ctx_get_option": (_i, [_vp, _i]),
+    "codae_weights_written": (_i, [_vp, _vp]),
     "codae_linear_engine": (_i, [_vp, _i, _i, _i, _i]),
     "codae_mask_table_philox": (_i, [_vp, _u64, _i64, _i64, _i, _vp, _vp]),
     "codae_corrupt_fwd": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i64, _vp, _i64, _vp, _vp]),
@@ -124,6 +125,12 @@ def set_option(device, option, value):
     """Tuning switches of the library (include/codae_b200.h: enum codae_option)."""
     c = ctx(device)
     check(lib().codae_ctx_set_option(c, option, 1 if value else 0), c)
+
+
+def weights_written(device):
+    """The current stream now waits for a weight writer on another stream: its next launch gets a full dependency."""
+    c = ctx(device)
+    check(lib().codae_weights_written(c, stream()), c)
 
 
 def get_option(device, option):

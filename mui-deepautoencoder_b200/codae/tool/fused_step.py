@@ -211,6 +211,7 @@ class FusedStep:
         wflat = model.flat_bf16 if eng == _C.BF16 else model.flat
         if updated is not None and self.chain_forward and B <= 128:
             torch.cuda.current_stream().wait_stream(self._update_stream)      # the chain launch reads every layer's weights
+            _C.weights_written(self.dev)
             updated = None
         if self.chain_forward and B <= 128:
             # every layer of the forward pass in one persistent launch (batches that fit one 128-row tile)
@@ -221,6 +222,7 @@ class FusedStep:
             for l, (i, o) in enumerate(dims):
                 if updated is not None:
                     torch.cuda.current_stream().wait_event(updated[l])
+                    _C.weights_written(self.dev)        # full dependency: no weight-tile prefetch ahead of that wait
                 _C.linear_fwd(acts[l], model.aug_view(wflat, l), None, acts[l + 1], B, o, _round_up(i, 8) + 1,
                               _C.ACT_RELU if model.relu[l] else _C.ACT_NONE, eng); n += 1
             if updated is not None:
@@ -311,6 +313,8 @@ class FusedStep:
         for side in sides:
             if side is not main:
                 main.wait_stream(side)
+        if layerwise and sides[0] is not main:
+            _C.weights_written(self.dev)       # the per-layer updates ran on the side stream: full dependency for the next launch
         if overlap_comm:
             main.wait_stream(self._comm_stream)
         elif self.world_size > 1:

@@ -119,6 +119,12 @@ int codae_ctx_set_option(codae_ctx* ctx, int option, int value) {
     return CODAE_OK;
 }
 
+int codae_weights_written(codae_ctx* ctx, void* stream) {
+    if (!ctx) return codae_fail(nullptr, CODAE_EINVAL, "codae_weights_written: ctx is NULL");
+    codae_mark_weights_written(ctx, as_stream(stream));
+    return CODAE_OK;
+}
+
 int codae_ctx_get_option(const codae_ctx* ctx, int option) {
     if (!ctx) return CODAE_EINVAL;
     switch (option) {

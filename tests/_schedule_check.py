@@ -171,6 +171,7 @@ _C.sqnorm_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
 _C.loss_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
 _C.linear_chain_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
 _C.ctx = lambda device=None: ctypes.c_void_p(1)
+_C.weights_written = lambda device: None
 
 import codae.model._flat_mlp as fm  # noqa: E402
 
