@@ -4,6 +4,10 @@
 # calls that touch overlapping bytes with at least one write, the earlier one must HAPPEN BEFORE the later one through
 # those edges -- otherwise the two kernels could run concurrently on the GPU and the schedule has a race.
 # Three consecutive steps are issued per scenario so that hazards across step boundaries are covered as well.
+# Programmatic dependent launch is modelled too: codae_linear_fwd / codae_linear_dgrad request their WEIGHT tiles before
+# griddepcontrol.wait, i.e. as early as the previous kernel of their stream STARTS (event / stream waits issued in between are
+# conservatively assumed not to hold that prefetch back) -- unless the launch was made a full dependency by the library's
+# weights-written bookkeeping (csrc/common.cuh: codae_mark_weights_written / codae_pdl_allowed), which is replayed here.
 import ctypes
 import os
 import sys
@@ -24,6 +28,7 @@ class FakeStream:
 
     def __init__(self, *a, **k):
         self.last = None
+        self.last_kernel = None
         FakeStream.count += 1
         self.name = "s%d" % FakeStream.count
         self.cuda_stream = FakeStream.count
@@ -96,57 +101,87 @@ def span(t):
     return (lo, lo + ext * es)
 
 
-def op(name, reads, writes):
-    CUR[-1]._node(name, [s for s in map(span, reads) if s], [s for s in map(span, writes) if s])
+DIRTY = [False, None]        # codae_ctx::weights_dirty, dirty_stream
+USE_MARKS = [True]           # False: ignore explicit codae_weights_written calls (mutation test)
+
+
+def mark_written(stream=None):
+    DIRTY[0], DIRTY[1] = True, (stream or CUR[-1])
+
+
+def pdl_allowed():
+    if DIRTY[0] and DIRTY[1] is CUR[-1]:
+        DIRTY[0] = False
+        return False
+    return True
+
+
+def op(name, reads, writes, pdl=False, prefetch=None, writes_weights=False):
+    """pdl: the entry point launches through launch_pdl / the programmatic attribute (consumes the dirty flag);
+    prefetch: weight operand requested ahead of griddepcontrol.wait when the launch is a programmatic dependent."""
+    st = CUR[-1]
+    programmatic = pdl_allowed() if pdl else False
+    extra = []
+    if programmatic and prefetch is not None and st.last_kernel is not None:
+        # may begin as soon as the previous KERNEL of this stream begins: ordered only after that kernel's own predecessors;
+        # it is over when the kernel that consumes the tiles is over (the kernel node depends on it)
+        NODES.append(dict(name=name + ":weight-prefetch", stream=st.name, reads=[span(prefetch)], writes=[],
+                          preds=set(NODES[st.last_kernel]["preds"])))
+        extra = [len(NODES) - 1]
+    st._node(name, [s for s in map(span, reads) if s], [s for s in map(span, writes) if s], extra)
+    st.last_kernel = st.last
+    if writes_weights:
+        mark_written(st)
 
 
 # ---- the C ABI wrappers, as access declarations (argument order: codae/_C.py) ------------------------------------------
 def corrupt_fwd(data, batch_idx, B, mask_table, run, mask_bits, col_var, io, out_cx, out_x=None, out_mask_id=None):
-    op("corrupt_fwd", [data, batch_idx, mask_table, mask_bits, col_var], [out_cx, out_x, out_mask_id])
+    op("corrupt_fwd", [data, batch_idx, mask_table, mask_bits, col_var], [out_cx, out_x, out_mask_id], pdl=True)
 
 
 def linear_fwd(X, W, bias, Y, M, N, K, act, dtype):
-    op("linear_fwd", [X[:M, :K], W[:N, :K], bias], [Y[:M, :N]])
+    op("linear_fwd", [X[:M, :K], W[:N, :K], bias], [Y[:M, :N]], pdl=True, prefetch=W[:N, :K] if dtype == 1 else None)
 
 
 def linear_dgrad(dY, W, A_prev, dX, M, N, K, dtype):
-    op("linear_dgrad", [dY[:M, :N], W[:N, :K], None if A_prev is None else A_prev[:M, :K]], [dX[:M, :K]])
+    op("linear_dgrad", [dY[:M, :N], W[:N, :K], None if A_prev is None else A_prev[:M, :K]], [dX[:M, :K]], pdl=True,
+       prefetch=W[:N, :K] if dtype == 1 else None)
 
 
 def linear_wgrad(dY, X, dW, db, M, N, K, dtype):
-    op("linear_wgrad", [dY[:M, :N], X[:M, :K]], [dW[:N, :K], db])
+    op("linear_wgrad", [dY[:M, :N], X[:M, :K]], [dW[:N, :K], db], pdl=True)
 
 
 def linear_wgrad_sq(dY, X, dW, M, N, K, dtype, sq):
-    op("linear_wgrad_sq", [dY[:M, :N], X[:M, :K]], [dW[:N, :K], sq])
+    op("linear_wgrad_sq", [dY[:M, :N], X[:M, :K]], [dW[:N, :K], sq], pdl=True)
 
 
 def mse_loss_fwd_bwd(x, batch_idx, y, mask_id, mask_bits, col_var, B, io, grad_scale, dy, acc, ws):
-    op("mse_loss_fwd_bwd", [x, batch_idx, y, mask_id, acc], [dy, acc, ws])
+    op("mse_loss_fwd_bwd", [x, batch_idx, y, mask_id, acc], [dy, acc, ws], pdl=True)
 
 
 def counter_add(counter, delta):
-    op("counter_add", [counter], [counter])
+    op("counter_add", [counter], [counter], pdl=True)
 
 
 def grad_sqnorm(g, out, ws):
-    op("grad_sqnorm", [g], [out, ws])
+    op("grad_sqnorm", [g], [out, ws], pdl=True)
 
 
 def adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm, grad_scale, step_dev=None):
-    op("adam_step", [pf, g, m, v, sqnorm, step_dev], [pf, m, v, p_bf16])
+    op("adam_step", [pf, g, m, v, sqnorm, step_dev], [pf, m, v, p_bf16], writes_weights=True)
 
 
 def adam_step_partials(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sq_partials, sqnorm_out, grad_scale, step_dev=None):
-    op("adam_step_partials", [pf, g, m, v, sq_partials, step_dev], [pf, m, v, p_bf16, sqnorm_out])
+    op("adam_step_partials", [pf, g, m, v, sq_partials, step_dev], [pf, m, v, p_bf16, sqnorm_out], writes_weights=True)
 
 
 def clip_adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm_out, ws, grad_scale, step_dev=None):
-    op("clip_adam_step", [pf, g, m, v, step_dev], [pf, m, v, p_bf16, sqnorm_out, ws])
+    op("clip_adam_step", [pf, g, m, v, step_dev], [pf, m, v, p_bf16, sqnorm_out, ws], writes_weights=True)
 
 
 def cast_bf16(src, dst):
-    op("cast_bf16", [src], [dst])
+    op("cast_bf16", [src], [dst], writes_weights=True)
 
 
 def chain_layer(A, B, b_kmajor, C, N, K, act=0, mask_src=None):
@@ -171,7 +206,7 @@ _C.sqnorm_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
 _C.loss_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
 _C.linear_chain_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
 _C.ctx = lambda device=None: ctypes.c_void_p(1)
-_C.weights_written = lambda device: None
+_C.weights_written = lambda device: mark_written() if USE_MARKS[0] else None
 
 import codae.model._flat_mlp as fm  # noqa: E402
 
@@ -236,7 +271,8 @@ def check(tag):
 
 def scenario(tag, dtype="bf16", clip=True, world=1, steps=3, batches=(8, 8, 8), **kw):
     del NODES[:]
-    MAIN.last = None
+    MAIN.last = MAIN.last_kernel = None
+    DIRTY[0], DIRTY[1] = False, None
     ds = ConcatenatedEmbeddingDataset.from_tensors([torch.rand(64, 32) for _ in range(3)])
     m = EmbeddingDenoisingAutoencoder(96, 40, 32, 3, 3, False)
     m.set_compute_dtype(dtype)
@@ -270,9 +306,15 @@ bad += scenario("chain + deferred update", chain_forward=True, chain_backward=Tr
 bad += scenario("data parallel, overlapped all-reduce", world=2)
 bad += scenario("data parallel, one all-reduce", world=2, overlap_allreduce=False)
 
+# mutation: without the explicit codae_weights_written marks the deferred schedule lets a weight-tile prefetch overtake the
+# per-layer update it waits for -- the checker must see that
+USE_MARKS[0] = False
+assert scenario("mutation: deferred update without marks", deferred_update=True) > 0
+USE_MARKS[0] = True
+
 # the checker itself: a schedule with a known race must be flagged
 del NODES[:]
-MAIN.last = None
+MAIN.last = MAIN.last_kernel = None
 side = FakeStream()
 a, b_ = torch.zeros(16), torch.zeros(16)
 op("writer", [], [a])
@@ -280,7 +322,7 @@ with torch.cuda.stream(side):
     op("reader without a wait", [a], [b_])
 assert check("self-test: missing wait_event") == 1
 del NODES[:]
-MAIN.last = None
+MAIN.last = MAIN.last_kernel = None
 op("writer", [], [a])
 ev = FakeEvent()
 ev.record(MAIN)
