@@ -101,7 +101,9 @@ def span(t):
     return (lo, lo + ext * es)
 
 
+META = {}                    # extra attributes for the next node (critical-path estimate only)
 DIRTY = [False, None]        # codae_ctx::weights_dirty, dirty_stream
+WHOLE = [0]                  # number of parameters of the current model (a whole-buffer update vs a per-layer one)
 USE_MARKS = [True]           # False: ignore explicit codae_weights_written calls (mutation test)
 
 
@@ -129,6 +131,8 @@ def op(name, reads, writes, pdl=False, prefetch=None, writes_weights=False):
                           preds=set(NODES[st.last_kernel]["preds"])))
         extra = [len(NODES) - 1]
     st._node(name, [s for s in map(span, reads) if s], [s for s in map(span, writes) if s], extra)
+    NODES[st.last].update(META)
+    META.clear()
     st.last_kernel = st.last
     if writes_weights:
         mark_written(st)
@@ -169,14 +173,17 @@ def grad_sqnorm(g, out, ws):
 
 
 def adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm, grad_scale, step_dev=None):
+    META["whole"] = pf.numel() == WHOLE[0]
     op("adam_step", [pf, g, m, v, sqnorm, step_dev], [pf, m, v, p_bf16], writes_weights=True)
 
 
 def adam_step_partials(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sq_partials, sqnorm_out, grad_scale, step_dev=None):
+    META["whole"] = pf.numel() == WHOLE[0]
     op("adam_step_partials", [pf, g, m, v, sq_partials, step_dev], [pf, m, v, p_bf16, sqnorm_out], writes_weights=True)
 
 
 def clip_adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm_out, ws, grad_scale, step_dev=None):
+    META["whole"] = pf.numel() == WHOLE[0]
     op("clip_adam_step", [pf, g, m, v, step_dev], [pf, m, v, p_bf16, sqnorm_out, ws], writes_weights=True)
 
 
@@ -194,6 +201,7 @@ def linear_chain(layers, M, ws):
         reads += [A[:M, :K], B[:N, :K] if bk else B[:K, :N], None if mask is None else mask[:M, :N]]
         writes.append(C[:M, :N])
     # the kernel orders its own layers (grid barrier); towards the rest of the step it is ONE node
+    META["layers"] = len(layers)
     op("linear_chain", reads, writes)
 
 
@@ -269,18 +277,54 @@ def check(tag):
     return len(races)
 
 
+# Optional: critical path of ONE steady-state step through the recorded DAG, with the per-launch durations measured on a B200
+# for the embedding.yaml shapes (profiles/r01_bench_embedding_bf16_final.json; per-layer optimizer launches = 1/10 of the
+# one-launch kernel + 1.5 us).  No resource contention, no launch gaps: a lower bound that ranks schedules, not a prediction.
+DUR = {"corrupt_fwd": 2.8, "linear_fwd": 7.2, "linear_dgrad": 7.5, "linear_wgrad": 6.4, "linear_wgrad_sq": 6.9,
+       "mse_loss_fwd_bwd": 5.7, "counter_add": 1.0, "grad_sqnorm": 20.0, "all_reduce": 80.0, "linear_chain": 3.5}
+FULL_UPDATE = {"adam_step": 110.0, "adam_step_partials": 124.0, "clip_adam_step": 138.0}
+
+
+def critical_path(n_layers, first, last):
+    """Longest path (us) through nodes [first, last) given that everything before `first` is done at time 0."""
+    end = {}
+    for j in range(first, last):
+        nd = NODES[j]
+        name = nd["name"].split(":")[0]
+        if nd["name"].endswith(":weight-prefetch") or not (nd["reads"] or nd["writes"]):
+            d = 0.0
+        elif name in FULL_UPDATE:
+            whole = sum(b - a for a, b in nd["writes"][:1]) > 0 and nd.get("whole", False)
+            d = FULL_UPDATE[name] if nd.get("whole") else FULL_UPDATE[name] / n_layers + 1.5
+        elif name == "linear_chain":
+            d = DUR["linear_chain"] * nd.get("layers", n_layers)
+        else:
+            d = DUR.get(name, 1.0)
+        start = max([end.get(i, 0.0) for i in nd["preds"] if i >= first] + [0.0])
+        end[j] = start + d
+    return max(end.values()) if end else 0.0
+
+
 def scenario(tag, dtype="bf16", clip=True, world=1, steps=3, batches=(8, 8, 8), **kw):
     del NODES[:]
     MAIN.last = MAIN.last_kernel = None
     DIRTY[0], DIRTY[1] = False, None
     ds = ConcatenatedEmbeddingDataset.from_tensors([torch.rand(64, 32) for _ in range(3)])
-    m = EmbeddingDenoisingAutoencoder(96, 40, 32, 3, 3, False)
+    m = EmbeddingDenoisingAutoencoder(96, 96, 32, 4, 4, False)       # 10 Linear layers, like config/embedding.yaml
     m.set_compute_dtype(dtype)
     m.to(torch.device("cpu"))
     cor = Corrupter(64, ds.arch, 2, torch.device("cpu"))
     fs = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=clip, world_size=world, **kw)
+    WHOLE[0] = m.flat.numel()
+    marks = []
     for B in batches:
+        marks.append(len(NODES))
         fs.step(torch.arange(B))
+    marks.append(len(NODES))
+    if os.environ.get("CODAE_SCHEDULE_ESTIMATE") == "1" and len(set(batches)) == 1:
+        # steady state: the last of the identical steps, everything issued before it taken as complete
+        print("%-34s critical path of a steady-state step: %6.1f us (no contention, no launch gaps)"
+              % (tag, critical_path(len(m.dims), marks[-2], marks[-1])))
     fs.evaluate(torch.arange(4))
     fs.step(torch.arange(batches[0]))
     fs.flush()
