@@ -347,6 +347,7 @@ bad += scenario("deferred update, data parallel", world=2, deferred_update=True)
 bad += scenario("chain forward", chain_forward=True)
 bad += scenario("chain forward + backward", chain_forward=True, chain_backward=True)
 bad += scenario("chain + deferred update", chain_forward=True, chain_backward=True, deferred_update=True)
+bad += scenario("chain backward + deferred update", chain_backward=True, deferred_update=True)
 bad += scenario("data parallel, overlapped all-reduce", world=2)
 bad += scenario("data parallel, one all-reduce", world=2, overlap_allreduce=False)
 
