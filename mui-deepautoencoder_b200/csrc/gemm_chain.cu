@@ -364,30 +364,64 @@ int codae_linear_chain(codae_ctx* ctx, const codae_chain_layer* layers, int n_la
         if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "codae_linear_chain: cudaFuncSetAttribute(smem=%u): %s", kSmemBytes, cudaGetErrorString(e));
         attr_set = true;
     }
-    // S CTAs per cluster split the k-blocks of a tile; C clusters share the tiles of a layer.  The whole grid must be resident.
-    int S = ctx->sm_count / t_max;
-    if (S > kMaxCluster) S = kMaxCluster;
-    if (S < 1) S = 1;
+    // S CTAs per cluster split the k-blocks of a tile; C clusters share the tiles of a layer.  The whole grid must be resident
+    // (it spins on the layer counters), and clusters are placed inside one GPC (16 / 18 / 20 SMs on this part), so the number
+    // of co-resident clusters depends on S: take the largest S that (a) leaves no rank without k-blocks in every layer and
+    // (b) still hosts one cluster per tile of the widest layer; failing (b), the S with the most resident CTAs.
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = kSmemBytes;
     cfg.stream = as_stream(stream);
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = S;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cfg.gridDim = dim3(S * t_max);
-    int max_clusters = 0;
-    cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, tc05_chain_kernel, &cfg);
-    if (oe != cudaSuccess || max_clusters < 1) {
-        cudaGetLastError();
-        return codae_fail(ctx, CODAE_ECUDA, "codae_linear_chain: no resident cluster of %d CTAs with %u bytes of shared memory (%s)", S,
-                          kSmemBytes, oe == cudaSuccess ? "occupancy 0" : cudaGetErrorString(oe));
+    int S0 = ctx->sm_count / t_max;
+    if (S0 > kMaxCluster) S0 = kMaxCluster;
+    if (S0 < 1) S0 = 1;
+    int S = 0, C = 0, best_S = 0, best_C = 0;
+    // the decision only depends on the layer shapes: remember the last one (occupancy queries are host work per call, and
+    // the first call of a shape happens outside CUDA-graph capture)
+    constexpr int kCache = 4;                            // forward and input-gradient chains of a step alternate
+    static int cache_key[kCache][2 * kMaxLayers + 1], cache_S[kCache] = {0}, cache_C[kCache] = {0}, cache_next = 0;
+    int key[2 * kMaxLayers + 1] = {0};
+    key[0] = n_layers;
+    for (int l = 0; l < n_layers; ++l) { key[1 + 2 * l] = layers[l].N; key[2 + 2 * l] = layers[l].K; }
+    for (int e = 0; e < kCache; ++e)
+        if (cache_S[e] > 0 && memcmp(key, cache_key[e], sizeof(key)) == 0) { S = cache_S[e]; C = cache_C[e]; }
+    for (int s_try = S0; s_try >= 1 && S == 0; --s_try) {
+        int need = 1;
+        for (int l = 0; l < n_layers; ++l) {
+            const int ns = chain_layer_geo(layers[l].N, layers[l].K, s_try, 0).nsplit;
+            if (ns > need) need = ns;
+        }
+        if (need < s_try) continue;                      // a smaller cluster gives the same split without idle ranks
+        attr[0].val.clusterDim.x = s_try;
+        cfg.gridDim = dim3(s_try * t_max);
+        int max_clusters = 0;
+        cudaError_t oe = cudaOccupancyMaxActiveClusters(&max_clusters, tc05_chain_kernel, &cfg);
+        if (oe != cudaSuccess) {
+            cudaGetLastError();
+            continue;
+        }
+        const int c_try = t_max < max_clusters ? t_max : max_clusters;
+        if (c_try * s_try > best_C * best_S) { best_S = s_try; best_C = c_try; }
+        if (c_try == t_max) break;
     }
-    const int C = t_max < max_clusters ? t_max : max_clusters;
+    if (S == 0) {
+        S = best_S; C = best_C;
+        if (S > 0) {
+            memcpy(cache_key[cache_next], key, sizeof(key));
+            cache_S[cache_next] = S;
+            cache_C[cache_next] = C;
+            cache_next = (cache_next + 1) % kCache;
+        }
+    }
+    if (S < 1 || C < 1)
+        return codae_fail(ctx, CODAE_ECUDA, "codae_linear_chain: no resident cluster with %u bytes of shared memory per CTA", kSmemBytes);
+    attr[0].val.clusterDim.x = S;
     cfg.gridDim = dim3(S * C);
     cudaError_t me = cudaMemsetAsync(workspace, 0, kMaxLayers * sizeof(unsigned int), as_stream(stream));
     if (me != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "codae_linear_chain: cudaMemsetAsync: %s", cudaGetErrorString(me));
