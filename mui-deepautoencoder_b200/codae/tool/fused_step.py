@@ -129,6 +129,7 @@ class FusedStep:
         if deferred_update and self.layerwise_adam:
             raise RuntimeError("codae: deferred_update excludes layerwise_adam (both schedule the per-layer updates)")
         self.deferred_update = bool(deferred_update)
+        self.deferred_chunk = max(1, int(os.environ.get("CODAE_DEFERRED_CHUNK", "1")))     # tuning knob: layers per update launch
         self._pending = None                       # (B, sum-of-squares partials | None) of the step whose gradients await their update
         self._update_stream = torch.cuda.Stream(device=dev) if self.deferred_update else None
         self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
@@ -195,8 +196,10 @@ class FusedStep:
                 partials = pending[1]
                 if partials is None and self.clip:          # no per-CTA partials (data parallel / fp32 engine): one norm pass
                     _C.grad_sqnorm(self.gflat, self.sqnorm, self.norm_ws); n += 1
-                for l in range(L):
-                    lo, hi = self._layer_span[l]
+                chunk = self.deferred_chunk                  # layers per update launch (1: finest pipelining with the forward pass)
+                for l0 in range(0, L, chunk):
+                    l1 = min(L, l0 + chunk)
+                    lo, hi = self._layer_span[l0][0], self._layer_span[l1 - 1][1]
                     args = (model.flat[lo:hi], self.gflat[lo:hi], self.m[lo:hi], self.v[lo:hi], None if pb is None else pb[lo:hi],
                             self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, self.max_norm if self.clip else -1.0)
                     if partials is not None:
@@ -206,7 +209,7 @@ class FusedStep:
                     n += 1
                     ev = torch.cuda.Event()
                     ev.record(upd)
-                    updated.append(ev)
+                    updated.extend([ev] * (l1 - l0))
         _C.corrupt_fwd(data, idx, B, table, run, bits, col_var, self.io, acts[0], b["x"], b["mask_id"]); n += 1
         wflat = model.flat_bf16 if eng == _C.BF16 else model.flat
         if updated is not None and self.chain_forward and B <= 128:
