@@ -305,7 +305,7 @@ def critical_path(n_layers, first, last):
     return max(end.values()) if end else 0.0
 
 
-def scenario(tag, dtype="bf16", clip=True, world=1, steps=3, batches=(8, 8, 8), **kw):
+def scenario(tag, dtype="bf16", clip=True, world=1, steps=3, batches=(8, 8, 8), expect=None, **kw):
     del NODES[:]
     MAIN.last = MAIN.last_kernel = None
     DIRTY[0], DIRTY[1] = False, None
@@ -321,6 +321,14 @@ def scenario(tag, dtype="bf16", clip=True, world=1, steps=3, batches=(8, 8, 8), 
         marks.append(len(NODES))
         fs.step(torch.arange(B))
     marks.append(len(NODES))
+    if expect is not None:
+        # the launches of one steady-state step, per stream in issue order (guards the default schedule against accidental edits)
+        got = {}
+        for nd in NODES[marks[-2]:marks[-1]]:
+            if (nd["reads"] or nd["writes"]) and not nd["name"].endswith(":weight-prefetch"):
+                got.setdefault(nd["stream"], []).append(nd["name"])
+        seqs = sorted(got.values(), key=len, reverse=True)
+        assert seqs == expect, (tag, seqs)
     if os.environ.get("CODAE_SCHEDULE_ESTIMATE") == "1" and len(set(batches)) == 1:
         # steady state: the last of the identical steps, everything issued before it taken as complete
         print("%-34s critical path of a steady-state step: %6.1f us (no contention, no launch gaps)"
@@ -332,8 +340,10 @@ def scenario(tag, dtype="bf16", clip=True, world=1, steps=3, batches=(8, 8, 8), 
 
 
 bad = 0
-bad += scenario("default (norm-free update)")
-bad += scenario("cooperative clip+Adam", wgrad_sqnorm=False)
+MAIN_DEFAULT = ["corrupt_fwd"] + ["linear_fwd"] * 10 + ["mse_loss_fwd_bwd"] + ["linear_dgrad"] * 9
+bad += scenario("default (norm-free update)", expect=[MAIN_DEFAULT + ["counter_add", "adam_step_partials"], ["linear_wgrad_sq"] * 10])
+bad += scenario("cooperative clip+Adam", wgrad_sqnorm=False,
+                expect=[MAIN_DEFAULT + ["counter_add", "clip_adam_step"], ["linear_wgrad"] * 10])
 bad += scenario("separate norm + Adam kernels", wgrad_sqnorm=False, fused_clip_adam=False)
 bad += scenario("fp32 engine (one stream)", dtype="fp32")
 bad += scenario("un-clipped", clip=False)
@@ -348,7 +358,8 @@ bad += scenario("chain forward", chain_forward=True)
 bad += scenario("chain forward + backward", chain_forward=True, chain_backward=True)
 bad += scenario("chain + deferred update", chain_forward=True, chain_backward=True, deferred_update=True)
 bad += scenario("chain backward + deferred update", chain_backward=True, deferred_update=True)
-bad += scenario("data parallel, overlapped all-reduce", world=2)
+bad += scenario("data parallel, overlapped all-reduce", world=2,
+                expect=[MAIN_DEFAULT + ["counter_add", "clip_adam_step"], ["linear_wgrad"] * 10, ["all_reduce"]])
 bad += scenario("data parallel, one all-reduce", world=2, overlap_allreduce=False)
 
 # mutation: without the explicit codae_weights_written marks the deferred schedule lets a weight-tile prefetch overtake the
