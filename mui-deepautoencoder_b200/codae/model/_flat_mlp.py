@@ -142,7 +142,19 @@ class FlatMLP(torch.nn.Module):
             self.flat_bf16 = torch.empty(self.flat.numel(), dtype=torch.bfloat16, device=self.flat.device)
         _C.cast_bf16(self.flat, self.flat_bf16)
 
+    def sync_weights(self):
+        """A trainer that defers its optimizer update (FusedStep(deferred_update=True)) registers its flush() here; every entry
+        point of the model that reads the weights applies the pending update first.  No-op otherwise."""
+        hook = getattr(self, "_flush_hook", None)
+        if hook is not None:
+            hook()
+
+    def state_dict(self, *args, **kwargs):
+        self.sync_weights()
+        return super().state_dict(*args, **kwargs)
+
     def _require_cuda(self):
+        self.sync_weights()
         if self.flat is None:
             raise RuntimeError("codae: the model must be moved to a CUDA device (model.to(device)); "
                                "the B200 path has no CPU fallback")

@@ -131,6 +131,8 @@ class FusedStep:
         self.deferred_update = bool(deferred_update)
         self.deferred_chunk = max(1, int(os.environ.get("CODAE_DEFERRED_CHUNK", "1")))     # tuning knob: layers per update launch
         self._pending = None                       # (B, sum-of-squares partials | None) of the step whose gradients await their update
+        if self.deferred_update:
+            model._flush_hook = self.flush         # state_dict() / forward() / encode() / decode() of the model flush first
         self._update_stream = torch.cuda.Stream(device=dev) if self.deferred_update else None
         self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
         self._wgrad_stream = torch.cuda.Stream(device=dev)

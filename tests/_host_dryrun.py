@@ -85,7 +85,11 @@ for dtype in ("fp32", "bf16"):
         assert first == 25 and second == 25 + 1 + 8 and fd._pending is not None
         fd.step(torch.arange(5)); assert fd._pending[0] == 5                                 # other batch size: flushed, then pending again
         fd.evaluate(torch.arange(4)); assert fd._pending is None
+        fd.step(torch.arange(8)); assert fd._pending is not None
+        m.state_dict(); assert fd._pending is None                                           # reading the weights flushes
+        fd.step(torch.arange(8)); m(ds.data[:3]); assert fd._pending is None                 # so does the legacy forward pass
         fd.flush()
+        m._flush_hook = None
         fb = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, chain_forward=True, chain_backward=True)
         fb.step(torch.arange(8)); print("chain fwd+bwd launches", fb.kernel_launches)       # corrupt, chain, loss, chain, 8 wgrad, counter, adam
         assert fb.kernel_launches == 14
