@@ -203,6 +203,23 @@ typedef struct codae_chain_layer {
 size_t codae_linear_chain_workspace_bytes(const codae_ctx* ctx);
 int codae_linear_chain(codae_ctx* ctx, const codae_chain_layer* layers, int n_layers, int M, void* workspace,
                        size_t ws_bytes, void* stream);
+/* Tabular widths (abalone: Linear layers of at most 11 x 11): the WHOLE network in one launch, exact fp32 FMA arithmetic.
+ * Replaces the per-layer codae_linear_fwd / codae_linear_dgrad / codae_linear_wgrad launches of
+ * MixedVariableDenoisingAutoencoder.forward (codae/model/mixed_variable_denoising_autoencoder.py:133-181) and of
+ * loss.backward() (script/train_dae_on_abalone.py:219).  Parameters and gradients use the augmented flat layout (layer l:
+ * W'[out, ld] at w_off, bias in column bcol; activations [B, ld_act] carry the constant-1 column):
+ *   fwd: acts[l+1][r, o] = act_l(sum_{k <= bcol} acts[l][r, k] W'_l[o, k])                      acts: L+1 device pointers (host array)
+ *   bwd: dW'_l[o, k] = sum_r g_l[r, o] acts[l][r, k] ;  g_{l-1}[r, k] = (sum_o g_l[r, o] W'_l[o, k]) * (acts[l][r, k] > 0 if ReLU
+ *        follows layer l-1), with g_l in g3[l % 3] ([B, ld_g] f32; g3[(L-1) % 3] holds dL/dy on entry)
+ * OPT-IN, not yet run on a B200 (FusedStep(tiny_mlp=True)); the arithmetic (csrc/tiny_mlp.h) is unit-tested on the CPU. */
+typedef struct codae_tiny_layer {
+    int64_t w_off;
+    int32_t ld, bcol, in, out, relu;
+} codae_tiny_layer;
+int codae_tiny_mlp_fwd(codae_ctx* ctx, const codae_tiny_layer* layers, int n_layers, const float* flat, float* const* acts,
+                       int64_t ld_act, int B, void* stream);
+int codae_tiny_mlp_bwd(codae_ctx* ctx, const codae_tiny_layer* layers, int n_layers, const float* flat, float* gflat,
+                       float* const* acts, int64_t ld_act, float* const* g3, int64_t ld_g, int B, void* stream);
 /* f32 -> bf16 copy of n elements (weight shadow / activation cast). */
 int codae_cast_bf16(codae_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
 

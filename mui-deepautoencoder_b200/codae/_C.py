@@ -49,6 +49,8 @@ SIGNATURES = {
     "codae_linear_wgrad_sq": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp]),
     "codae_linear_chain_workspace_bytes": (_sz, [_vp]),
     "codae_linear_chain": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp]),
+    "codae_tiny_mlp_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _i, _vp]),
+    "codae_tiny_mlp_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp]),
     "codae_cast_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "codae_sqnorm_workspace_bytes": (_sz, [_vp]),
     "codae_grad_sqnorm": (_i, [_vp, _vp, _i64, _vp, _vp, _sz, _vp]),
@@ -72,6 +74,15 @@ class ChainLayer(ctypes.Structure):
 
 
 CHAIN_MAX_LAYERS = 16
+
+
+class TinyLayer(ctypes.Structure):
+    """struct codae_tiny_layer (include/codae_b200.h)."""
+    _fields_ = [("w_off", _i64), ("ld", _c.c_int32), ("bcol", _c.c_int32), ("in_", _c.c_int32), ("out", _c.c_int32),
+                ("relu", _c.c_int32)]
+
+
+TINY_MAX_LAYERS = 8
 
 _lib = None
 _lock = threading.RLock()   # re-entrant: ctx() loads the library under the same lock
@@ -278,6 +289,27 @@ def linear_chain(layers, M, ws):
     c = ctx(ws.device)
     arr = (ChainLayer * len(layers))(*layers)
     check(lib().codae_linear_chain(c, ctypes.cast(arr, _vp), len(layers), M, p(ws), ws.numel(), stream()), c)
+
+
+def _ptr_array(tensors):
+    return ctypes.cast((_vp * len(tensors))(*[t.data_ptr() for t in tensors]), _vp)
+
+
+def tiny_mlp_fwd(layers, flat, acts, B):
+    """layers: list of TinyLayer; acts: L+1 fp32 activation buffers with ONE common pitch (constant-1 columns set)."""
+    c = ctx(flat.device)
+    assert len({a.stride(0) for a in acts}) == 1 and all(a.dtype == torch.float32 for a in acts)
+    arr = (TinyLayer * len(layers))(*layers)
+    check(lib().codae_tiny_mlp_fwd(c, ctypes.cast(arr, _vp), len(layers), p(flat), _ptr_array(acts), acts[0].stride(0), B, stream()), c)
+
+
+def tiny_mlp_bwd(layers, flat, gflat, acts, g3, B):
+    """g3: the three rotating fp32 gradient buffers (dL/d(out_l) in g3[l % 3]; g3[(L-1) % 3] holds dL/dy)."""
+    c = ctx(flat.device)
+    assert len({a.stride(0) for a in acts}) == 1 and len({g.stride(0) for g in g3}) == 1 and len(g3) == 3
+    arr = (TinyLayer * len(layers))(*layers)
+    check(lib().codae_tiny_mlp_bwd(c, ctypes.cast(arr, _vp), len(layers), p(flat), p(gflat), _ptr_array(acts), acts[0].stride(0),
+                                   _ptr_array(g3), g3[0].stride(0), B, stream()), c)
 
 
 def cast_bf16(src, dst):

@@ -42,7 +42,8 @@ class FusedStep:
 
     def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True,
-                 fused_clip_adam=True, wgrad_sqnorm=None, layerwise_adam=None, chain_forward=None, chain_backward=None, deferred_update=None):
+                 fused_clip_adam=True, wgrad_sqnorm=None, layerwise_adam=None, chain_forward=None, chain_backward=None, deferred_update=None,
+                 tiny_mlp=None):
         """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
         tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
         {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
@@ -96,6 +97,17 @@ class FusedStep:
             # on wherever it applies (embedding.yaml step: 0.3446 -> 0.3367 ms); CODAE_WGRAD_SQNORM=0 switches it off
             self.wgrad_sqnorm = (os.environ.get("CODAE_WGRAD_SQNORM", "1") != "0" and world_size == 1 and self.eng == _C.BF16
                                  and fused_clip_adam)
+        lay = model.layout()[0]
+        tiny_ok = (self.eng == _C.F32 and world_size == 1 and len(model.dims) <= _C.TINY_MAX_LAYERS
+                   and max(max(i, o) for i, o in model.dims) <= 64)
+        if tiny_mlp is None:
+            # opt-in, not yet run on a B200: tabular widths as ONE forward and ONE backward launch (codae_tiny_mlp_fwd / _bwd)
+            tiny_mlp = os.environ.get("CODAE_TINY_MLP") == "1" and tiny_ok
+        if tiny_mlp and not tiny_ok:
+            raise RuntimeError("codae: tiny_mlp needs the fp32 engine, a single GPU, at most %d layers of width <= 64" % _C.TINY_MAX_LAYERS)
+        self.tiny_mlp = bool(tiny_mlp)
+        self._tiny_layers = [_C.TinyLayer(lay[l][0], lay[l][1], lay[l][2], i, o, 1 if model.relu[l] else 0)
+                             for l, (i, o) in enumerate(model.dims)] if self.tiny_mlp else None
         if chain_forward is None:
             # opt-in, not yet validated on a B200: the whole forward pass as ONE persistent launch (codae_linear_chain)
             chain_forward = os.environ.get("CODAE_CHAIN") == "1" and self.eng == _C.BF16 and mixed is None
@@ -218,7 +230,15 @@ class FusedStep:
             torch.cuda.current_stream().wait_stream(self._update_stream)      # the chain launch reads every layer's weights
             _C.weights_written(self.dev)
             updated = None
-        if self.chain_forward and B <= 128:
+        tiny = self.tiny_mlp and len({a.stride(0) for a in acts}) == 1
+        if tiny and updated is not None:
+            torch.cuda.current_stream().wait_stream(self._update_stream)      # one launch reads every layer's weights
+            _C.weights_written(self.dev)
+            updated = None
+        if tiny:
+            # tabular widths: every layer of the forward pass in one launch (rows are independent: one CTA per 32 rows)
+            _C.tiny_mlp_fwd(self._tiny_layers, model.flat, acts, B); n += 1
+        elif self.chain_forward and B <= 128:
             # every layer of the forward pass in one persistent launch (batches that fit one 128-row tile)
             _C.linear_chain([_C.chain_layer(acts[l], model.aug_view(wflat, l), True, acts[l + 1], o, _round_up(i, 8) + 1,
                                             _C.ACT_RELU if model.relu[l] else _C.ACT_NONE) for l, (i, o) in enumerate(dims)],
@@ -250,6 +270,12 @@ class FusedStep:
             return n
         if chain_bwd:
             return n + self._enqueue_chain_backward(B, b)
+        if tiny:
+            # every weight gradient and the input-gradient chain in one single-CTA launch, then the update
+            _C.tiny_mlp_bwd(self._tiny_layers, model.flat, self.gflat, acts, gbuf, B); n += 1
+            if not self.deferred_update:
+                n += self._enqueue_update(b.get("sq_partials"))
+            return n
         # Backward.  The input-gradient chain dgrad(L-1) -> ... -> dgrad(1) is the critical path; every weight gradient
         # only needs dL/d(out_l) and the stored activation, so wgrad(l) runs on a second stream next to dgrad(l)
         # (at B=128 each of these kernels is a ~8 us latency chain that leaves most of the GPU idle).

@@ -118,6 +118,11 @@ arch = [dict(name="Sex", size=3, type="classification", position=0)] + [dict(nam
 ds = MixedVariableDataset.from_arch(arch, torch.rand(100, 11))
 m = MixedVariableDenoisingAutoencoder(arch, 11, 4, dev, 2, 2, False); m.to(dev)
 cor = Corrupter(100, arch, 3, dev)
+ft = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, tiny_mlp=True,
+               mixed=dict(arch=arch, weight=[0.4] + [1] * 8, norm_scale=torch.rand(8), norm_min=torch.rand(8), norm_first=3))
+ft.step(torch.arange(16), run=5); print("tiny mlp launches", ft.kernel_launches)      # corrupt, fwd, loss, monitor, bwd, counter, clip+Adam
+assert ft.kernel_launches == 7
+ft.evaluate(torch.arange(7), run=2)
 fs = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, mixed=dict(arch=arch, weight=[0.4] + [1] * 8, norm_scale=torch.rand(8), norm_min=torch.rand(8), norm_first=3))
 fs.step(torch.arange(16), run=5); fs.evaluate(torch.arange(7), run=2); print({k: (v.shape if hasattr(v, "shape") else v) for k, v in fs.read_monitors().items()})
 crit = CombinedCriterion(arch, 3, dev, torch.tensor([0, 0, 0] + [1] * 8), weight=[0.4] + [1] * 8, reduction="mean")

@@ -84,18 +84,23 @@ def test_product_never_imports_oracle():
 
 
 def test_chain_layer_struct_layout_matches_header(tmp_path):
-    """codae._C.ChainLayer mirrors struct codae_chain_layer: same size and field offsets as the C compiler sees them."""
+    """codae._C.ChainLayer / TinyLayer mirror struct codae_chain_layer / codae_tiny_layer: same size and field offsets as the C
+    compiler sees them."""
     import ctypes
     from codae import _C
     fields = [f[0] for f in _C.ChainLayer._fields_]
+    tfields = [f[0] for f in _C.TinyLayer._fields_]
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "codae_b200.h"\nint main(void) {\n'
                    '  printf("%zu", sizeof(codae_chain_layer));\n' +
                    "".join('  printf(" %%zu", offsetof(codae_chain_layer, %s));\n' % f for f in fields) +
-                   '  printf(" %d\\n", CODAE_CHAIN_MAX_LAYERS);\n  return 0;\n}\n')
+                   '  printf(" %d", CODAE_CHAIN_MAX_LAYERS);\n  printf(" %zu", sizeof(codae_tiny_layer));\n' +
+                   "".join('  printf(" %%zu", offsetof(codae_tiny_layer, %s));\n' % f.rstrip("_") for f in tfields) +
+                   '  printf("\\n");\n  return 0;\n}\n')
     exe = tmp_path / "layout"
     r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
-    want = [ctypes.sizeof(_C.ChainLayer)] + [getattr(_C.ChainLayer, f).offset for f in fields] + [_C.CHAIN_MAX_LAYERS]
+    want = ([ctypes.sizeof(_C.ChainLayer)] + [getattr(_C.ChainLayer, f).offset for f in fields] + [_C.CHAIN_MAX_LAYERS] +
+            [ctypes.sizeof(_C.TinyLayer)] + [getattr(_C.TinyLayer, f).offset for f in tfields])
     assert got == want, (got, want)

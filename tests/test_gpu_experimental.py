@@ -119,3 +119,42 @@ print("DEFERRED OK")
 ''' % (graph, HERE, HERE, HERE)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
     assert r.returncode == 0 and "DEFERRED OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("name", ["abalone_k1", "abalone_k3"])
+def test_tiny_mlp_abalone_matches_reference(name):
+    """FusedStep(tiny_mlp=True): the abalone model's forward and backward passes as one launch each (codae_tiny_mlp_fwd / _bwd)
+    against the golden vectors of the reference (same checks as test_abalone_fused_and_legacy's fused path)."""
+    code = r'''
+import os, sys
+sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, "..")); sys.path.insert(0, os.path.join(%r, "..", "mui-deepautoencoder_b200"))
+import numpy as np, torch
+from conftest import GOLDEN
+from test_gpu_training import load_params, flat_grads, flat_params, rel, DEV
+from oracle.gen_golden import abalone_arch
+from codae.dataset import MixedVariableDataset
+from codae.model import MixedVariableDenoisingAutoencoder
+from codae.tool import Corrupter, FusedStep
+g = np.load(os.path.join(GOLDEN, %r + ".npz"))
+arch = abalone_arch()
+k_max, B = int(g["k_max"]), int(g["B"])
+ds = MixedVariableDataset.from_arch(arch, torch.from_numpy(g["data"]))
+m = MixedVariableDenoisingAutoencoder(arch, 11, int(g["z"]), DEV, 2, 2, bool(g["steep"]))
+load_params(m, g["init"], g["shapes"])
+m.to(DEV); ds.to(DEV)
+cor = Corrupter(ds.nb_observation, arch, k_max, DEV)
+cor.mask_to_use = torch.from_numpy(g["mask_to_use"])
+fs = FusedStep(m, cor, ds.data, lr=float(g["lr"]), weight_decay=float(g["wd"]), clip=True, tiny_mlp=True,
+               mixed=dict(arch=arch, weight=list(g["weight"]), norm_scale=torch.from_numpy(g["norm_scale"]),
+                          norm_min=torch.from_numpy(g["norm_min"]), norm_first=3))
+assert fs.tiny_mlp
+for s in range(3):
+    fs.step(torch.from_numpy(g["idx%%d" %% s]).to(DEV), run=int(g["run%%d" %% s]))
+    assert abs(fs.last_loss(B) - float(g["loss%%d" %% s])) <= 1e-5 * float(g["loss%%d" %% s])
+    assert rel(flat_grads(m), g["grads%%d" %% s]) < 1e-5
+    assert rel(flat_params(m), g["post%%d" %% s]) < 1e-5
+assert fs.kernel_launches == 7
+print("TINY OK")
+''' % (HERE, HERE, HERE, name)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+    assert r.returncode == 0 and "TINY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
