@@ -1,8 +1,14 @@
 """bench.py -- CODAE hot path on B200: train samples/s (headline) + candidate scores/s, with roofline and CPU baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload embedding|modanet|polyvore] [--dtype fp32|bf16]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload polyvore|embedding|modanet] [--dtype fp32|bf16]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU, NCCL)
-  python bench.py --impl reference ...   the reference's CPU implementation of the same step (oracle port), host cores
+  python bench.py --impl reference ...   the reference's own CPU implementation of the same step on the host cores (the
+                                          unmodified reference classes from baseline/_ref; the oracle port if that is absent)
+
+Default workload: the polyvore-shaped multi-slot step (BASELINE.json configs[3]: 10 x Linear(4096, 4096), B = 8192 per GPU,
+bf16 tensor-core engine) -- the largest single-GPU training configuration and the one the tensor-pipe bar is written for.
+The shipped small-batch configs (embedding.yaml at fp32 AND bf16, the modanet yaml at bf16) and the 10 M-row scoring sweep
+are measured in the same run and reported as secondary blocks of the same JSON line (`secondary`, `scoring`).
 
 A "step" is one pass of the training-step hot path over one batch of synthetic embeddings of the config's shape
 (corrupt -> encoder/decoder GEMMs -> loss -> backward GEMMs -> [all-reduce] -> clip -> Adam).  `value` is the
@@ -34,7 +40,7 @@ WORKLOADS = {
     "modanet": dict(yaml="config/modanet_merge_top_bottom_shoe.yaml", S=3, E=512, z=1536, nin=3, nout=3, B=32, k_max=1,
                     lr=1e-4, wd=1e-2, clip=False, dtype="bf16", N=131072, seed=50493213),
     "polyvore": dict(yaml="config/polyvore_multislot.yaml", S=8, E=512, z=4096, nin=4, nout=4, B=8192, k_max=2, lr=1e-4,
-                     wd=1e-2, clip=True, dtype="bf16", N=262144, seed=50493213),
+                     wd=1e-2, clip=True, dtype="bf16", N=1048576, seed=50493213, cpu_B=2048),
 }
 
 
@@ -115,133 +121,84 @@ def synthetic_rows(N, io, seed, device):
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port of the reference's step on the host cores
+# reference arm / cpu_baseline: the reference's own classes (baseline/_ref) or, without them, the oracle port, on the host cores
 # ----------------------------------------------------------------------------------------------------------------
 def cpu_reference(w, steps, warmup, seed=0):
-    from oracle import codae_oracle as O
-    torch.manual_seed(seed)
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    io, B = w["S"] * w["E"], w["B"]
+    """One CPU step = the reference's loop body over a bounded sample of the workload: cpu_B rows (the config's batch for the
+    small-batch configs, 2048 rows of the 8192-row polyvore batch).  kind "reference": the unmodified reference classes
+    (baseline/live_reference.py); kind "port": oracle/codae_oracle.py."""
+    io, B = w["S"] * w["E"], w.get("cpu_B", w["B"])
     dims = layer_dims(w)
-    relu = [True] * len(dims)
-    relu[w["nin"]] = False
-    relu[-1] = False
-    W = [torch.empty(o, i).uniform_(-1, 1) * (6.0 / (i + o)) ** 0.5 for i, o in dims]
-    b = [torch.zeros(o) for _, o in dims]
-    dae = O.OracleDAE(W, b, relu, w["lr"], w["wd"], w["clip"])
     n = max(4 * B, 1024)
     data = synthetic_rows(n, io, seed, "cpu")
-    arch = [dict(size=w["E"], position=p) for p in range(0, io, w["E"])]
-    bm, nmiss, _ = O.binary_masks(arch, w["k_max"])
-    import random
-    random.seed(seed)
-    tbl = O.mask_table_compat(n, bm.shape[0])
-    rng = np.random.RandomState(seed)
-    t0 = None
-    for s in range(warmup + steps):
-        if s == warmup:
-            t0 = time.perf_counter()
-        idx = rng.randint(0, n, size=B).tolist()
-        _, fmask = O.get_masks(bm, nmiss, tbl, idx, 0, w["k_max"])       # the reference's per-sample Python loop
-        dae.step_embedding(data[idx], fmask)
-    dt = time.perf_counter() - t0
-    return dict(value=B * steps / dt, unit="samples/s", cores=cores, kind="port",
-                sample="%d steps of B=%d (%s layer sizes) with the oracle port of the reference step on %d host threads"
-                       % (steps, B, "x".join(str(o) for _, o in dims[:2]) + "...", cores), ms_per_step=1e3 * dt / steps)
+    shape = "%d x Linear(%d, %d)" % (len(dims), dims[0][0], dims[0][1])
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import live_reference as LR
+    if LR.available() and os.environ.get("CODAE_CPU_ARM", "reference") != "port":
+        r = LR.train_steps(w, data, B, steps, warmup, seed)
+        dt, cores, kind = r["seconds"], r["cores"], "reference"
+        what = "the unmodified reference classes (baseline/_ref) driven by the reference's loop body"
+    else:
+        from oracle import codae_oracle as O
+        torch.manual_seed(seed)
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        relu = [True] * len(dims)
+        relu[w["nin"]] = False
+        relu[-1] = False
+        W = [torch.empty(o, i).uniform_(-1, 1) * (6.0 / (i + o)) ** 0.5 for i, o in dims]
+        b = [torch.zeros(o) for _, o in dims]
+        dae = O.OracleDAE(W, b, relu, w["lr"], w["wd"], w["clip"])
+        arch = [dict(size=w["E"], position=p) for p in range(0, io, w["E"])]
+        bm, nmiss, _ = O.binary_masks(arch, w["k_max"])
+        import random
+        random.seed(seed)
+        tbl = O.mask_table_compat(n, bm.shape[0])
+        rng = np.random.RandomState(seed)
+        t0 = None
+        for s in range(warmup + steps):
+            if s == warmup:
+                t0 = time.perf_counter()
+            idx = rng.randint(0, n, size=B).tolist()
+            _, fmask = O.get_masks(bm, nmiss, tbl, idx, 0, w["k_max"])       # the reference's per-sample Python loop
+            dae.step_embedding(data[idx], fmask)
+        dt, kind = time.perf_counter() - t0, "port"
+        what = "the oracle port of the reference step"
+    return dict(value=B * steps / dt, unit="samples/s", cores=cores, kind=kind,
+                sample="%d steps of %d rows%s (%s) with %s on %d host threads"
+                       % (steps, B, "" if B == w["B"] else " (of the %d-row batch)" % w["B"], shape, what, cores),
+                ms_per_step=1e3 * dt / steps)
 
 
 def cpu_scoring(E, rows=1_000_000):
-    from oracle import codae_oracle as O  # noqa: F401
-    cat = torch.rand(rows, E)
-    q = torch.rand(1, E)
-    t0 = time.perf_counter()
-    reps = 3
-    for _ in range(reps):
-        s = torch.nn.functional.cosine_similarity(cat, q)     # the reference's op (metering.py:67-69)
-        torch.topk(s, 10)
-    return rows * reps / (time.perf_counter() - t0)
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import live_reference as LR
+    r = LR.scoring_sweeps(E, rows)            # the reference's op (metering.py:67-69) is a torch call: same code either way
+    return r["scores"] / r["seconds"]
+
+
+def workload_config(name, w, dims, world):
+    io = w["S"] * w["E"]
+    P = sum(i * o + o for i, o in dims)
+    big = "larger than the 126 MB L2"
+    return {"workload": "%s (%s): %d x Linear, io=%d, B=%d/GPU, k_max=%d, N=%d" % (name, w["yaml"], len(dims), io, w["B"], w["k_max"], w["N"]),
+            "params": P, "l2_policy": "no flush: every step streams weights + Adam state (%.0f MB), activations and random dataset "
+                                      "rows, %s" % (32.0 * P / 1e6, big),
+            "parallelism": "dp%d" % world}
 
 
 # ----------------------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
-    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", type=str, default="embedding", choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", type=str, default=None, choices=["fp32", "bf16"])
-    ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--no-scoring", action="store_true")
-    ap.add_argument("--no-prefetch", action="store_true", help="weight tiles are not requested ahead of the PDL wait")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-fp32", action="store_true")
-    ap.add_argument("--no-pdl", action="store_true", help="A/B: launch without programmatic dependent launch")
-    ap.add_argument("--no-splitk", action="store_true", help="A/B: single-pass small-batch contractions")
-    ap.add_argument("--no-persistent", action="store_true", help="A/B: one tile per CTA for the large contractions")
-    ap.add_argument("--no-wgrad-sqnorm", action="store_true",
-                    help="A/B (1 GPU): cooperative norm + Adam kernel instead of sum(dW^2) partials from the weight-gradient kernels")
-    ap.add_argument("--no-tma-store", action="store_true", help="A/B: per-thread stores instead of TMA bulk stores for single-pass f32 tiles")
-    ap.add_argument("--chain", action="store_true",
-                    help="A/B (B <= 128): forward pass and input-gradient chain as one persistent launch each (codae_linear_chain)")
-    ap.add_argument("--deferred-update", action="store_true",
-                    help="A/B: the update of step s runs per layer at the start of step s+1, beside its forward pass")
-    ap.add_argument("--catalog", type=int, default=10_000_000)
-    args = ap.parse_args()
-    w = dict(WORKLOADS[args.workload])
-    dtype = args.dtype or w["dtype"]
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    io = w["S"] * w["E"]
-    dims = layer_dims(w)
-    Wsum = sum(i * o for i, o in dims)
-    P = Wsum + sum(o for _, o in dims)
-    config = {"workload": "%s (%s): %d x Linear, io=%d, B=%d/GPU, k_max=%d" % (args.workload, w["yaml"], len(dims), io, w["B"], w["k_max"]),
-              "params": P, "l2_policy": "no flush: every step streams weights + Adam state (%.0f MB) and random dataset rows, "
-                                        "larger than the 126 MB L2" % (32.0 * P / 1e6),
-              "parallelism": "dp%d" % world}
-
-    if args.impl == "reference":
-        if rank != 0:
-            return
-        steps = min(args.steps, 200 if args.workload != "polyvore" else 2)
-        r = cpu_reference(w, steps, min(args.warmup, 3))
-        print(json.dumps({"impl": "reference", "metric": "train samples/s", "value": r["value"], "unit": "samples/s",
-                          "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": r["ms_per_step"],
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": config, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                          "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}))
-        return
-
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a B200; the product has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+def train_block(name, dtype, K, Wm, args, env, e2e=True):
+    """One training workload on this rank's GPU: device-timed `value`, end-to-end `e2e`, per-kernel rooflines."""
     import torch.distributed as dist
-    if world > 1:
-        dist.init_process_group(backend="nccl", device_id=dev)
     from codae import _C
     from codae.dataset import ConcatenatedEmbeddingDataset
     from codae.model import EmbeddingDenoisingAutoencoder
     from codae.tool import Corrupter, FusedStep
-    from codae.tool.inference import ComplementarityScorer, SwapScorer, shard_rows
-
-    if args.no_pdl:
-        _C.set_option(dev, _C.OPT_PDL, 0)
-    if args.no_prefetch:
-        _C.set_option(dev, _C.OPT_WEIGHT_PREFETCH, 0)
-    if args.no_splitk:
-        _C.set_option(dev, _C.OPT_SPLITK, 0)
-    if args.no_persistent:
-        _C.set_option(dev, _C.OPT_PERSISTENT, 0)
-    if args.no_tma_store:
-        _C.set_option(dev, _C.OPT_TMA_STORE, 0)
-    pk = peaks()
-    B, K, Wm = w["B"], args.steps, args.warmup
-    if args.workload == "polyvore" and K > 50:
-        K = 50                      # 7 ms steps: 50 are plenty and keep the run short
+    rank, world, dev, local = env["rank"], env["world"], env["dev"], env["local"]
+    w = dict(WORKLOADS[name])
+    io, B = w["S"] * w["E"], w["B"]
+    dims = layer_dims(w)
     torch.manual_seed(w["seed"])
     data = synthetic_rows(w["N"], io, w["seed"], dev)
     ds = ConcatenatedEmbeddingDataset.__new__(ConcatenatedEmbeddingDataset)
@@ -254,11 +211,9 @@ def main():
     cor = Corrupter(w["N"], ds.arch, w["k_max"], dev, seed=w["seed"])
     fs = FusedStep(model, cor, data, lr=w["lr"], weight_decay=w["wd"], clip=w["clip"], world_size=world,
                    use_graph=not args.no_graph, wgrad_sqnorm=False if args.no_wgrad_sqnorm else None,
-                   chain_forward=True if args.chain else None, chain_backward=True if (args.chain and world == 1) else None,
-                   deferred_update=True if args.deferred_update else None)
+                   dp_mode=args.dp_mode)
     rng = np.random.RandomState(w["seed"] + rank)
-    nb = Wm + K
-    batches = torch.from_numpy(rng.randint(0, w["N"], size=(nb, B))).to(dev)
+    batches = torch.from_numpy(rng.randint(0, w["N"], size=(Wm + K, B))).to(dev)
 
     def barrier():
         if world > 1:
@@ -268,14 +223,12 @@ def main():
     # ---- device-resident timing: `value` ---------------------------------------------------------------------
     for s in range(Wm):
         fs.step(batches[s], global_batch=B * world)
-    fs.flush()                                   # deferred_update: nothing pending when the clock starts ...
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for s in range(Wm, Wm + K):
         fs.step(batches[s], global_batch=B * world)
-    fs.flush()                                   # ... and the K-th update is inside the timed region (no-op otherwise)
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -285,97 +238,107 @@ def main():
     clocks = sampler.stop() if sampler else None
     launches = K * fs.kernel_launches
     loss_last = fs.last_loss(B)
+    out = {"metric": "train samples/s", "value": world * B * K / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": K,
+           "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32" if fs_dtype(dtype, model) == "fp32" else "bf16", "data": "synthetic",
+           "config": workload_config(name, w, dims, world), "engine": engine_name(model), "dp_mode": fs.dp_mode,
+           "loss_last_step": loss_last, "clocks": clocks, "gpu_launches": launches, "cuda_graph": not args.no_graph}
 
     # ---- end-to-end through the public API with host buffers: `e2e` -------------------------------------------------
-    table = cor.device_tables()[0]
-    host_rows = torch.empty((4, B, io), dtype=torch.float32).pin_memory()
-    host_tab = torch.empty((4, B, table.shape[1]), dtype=torch.int16).pin_memory()
-    for j in range(4):
-        host_rows[j].copy_(data[batches[j]].cpu())
-        host_tab[j].copy_(table[batches[j]].cpu())
-    # two staging buffers: the host->device copy of step s+1 (copy stream) overlaps the kernels of step s; every step's
-    # copy and every step's loss read-back are inside the timed region
-    st_rows = [torch.empty((B, io), dtype=torch.float32, device=dev) for _ in range(2)]
-    st_tab = [torch.empty((B, table.shape[1]), dtype=torch.int16, device=dev) for _ in range(2)]
-    loss_host = torch.zeros(4, dtype=torch.float64).pin_memory()
-    Ke = max(10, K // 2)
-    copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    if e2e:
+        table = cor.device_tables()[0]
+        host_rows = torch.empty((4, B, io), dtype=torch.float32).pin_memory()
+        host_tab = torch.empty((4, B, table.shape[1]), dtype=torch.int16).pin_memory()
+        for j in range(4):
+            host_rows[j].copy_(data[batches[j]].cpu())
+            host_tab[j].copy_(table[batches[j]].cpu())
+        # two staging buffers: the host->device copy of step s+1 (copy stream) overlaps the kernels of step s; every step's
+        # copy and every step's loss read-back are inside the timed region
+        st_rows = [torch.empty((B, io), dtype=torch.float32, device=dev) for _ in range(2)]
+        st_tab = [torch.empty((B, table.shape[1]), dtype=torch.int16, device=dev) for _ in range(2)]
+        loss_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+        Ke = max(10, K // 2)
+        copy_stream = torch.cuda.Stream(device=dev)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
-    def stage(s):
-        j = s % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[j])          # the step that last used this buffer has finished
-            st_rows[j].copy_(host_rows[s % 4], non_blocking=True)
-            st_tab[j].copy_(host_tab[s % 4], non_blocking=True)
-            copied[j].record(copy_stream)
-
-    def e2e_loop(n):
-        main = torch.cuda.current_stream()
-        for j in range(2):
-            consumed[j].record(main)
-        stage(0)
-        last = 0.0
-        for s in range(n):
+        def stage(s):
             j = s % 2
-            if s + 1 < n:
-                stage(s + 1)
-            main.wait_event(copied[j])
-            fs.step(None, global_batch=B * world, staged=(st_rows[j], st_tab[j]))
-            consumed[j].record(main)
-            loss_host.copy_(fs.acc, non_blocking=True)
-            main.synchronize()                           # the user sees this step's loss before issuing the next step
-            last = float(loss_host[3]) / (B * io)
-        fs.flush()                                       # deferred_update: the last update belongs to the timed region
-        main.synchronize()
-        return last
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[j])          # the step that last used this buffer has finished
+                st_rows[j].copy_(host_rows[s % 4], non_blocking=True)
+                st_tab[j].copy_(host_tab[s % 4], non_blocking=True)
+                copied[j].record(copy_stream)
 
-    e2e_loop(6)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_loop(Ke)
-    barrier()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * Ke / (float(e2e_ms.item()) / 1e3)
+        def e2e_loop(n):
+            main = torch.cuda.current_stream()
+            for j in range(2):
+                consumed[j].record(main)
+            stage(0)
+            last = 0.0
+            for s in range(n):
+                j = s % 2
+                if s + 1 < n:
+                    stage(s + 1)
+                main.wait_event(copied[j])
+                fs.step(None, global_batch=B * world, staged=(st_rows[j], st_tab[j]))
+                consumed[j].record(main)
+                loss_host.copy_(fs.acc, non_blocking=True)
+                main.synchronize()                           # the user sees this step's loss before issuing the next step
+                last = float(loss_host[3]) / (B * io)
+            main.synchronize()
+            return last
 
-    # ---- the same step on the exact-fp32 engine (reference precision, 1e-5 parity), short run ---------------------------------
-    fp32_mode = None
-    if dtype == "bf16" and args.workload != "polyvore" and not args.no_fp32:
-        m32 = EmbeddingDenoisingAutoencoder(io, w["z"], w["E"], w["nin"], w["nout"], False)
-        m32.to(dev)
-        f32 = FusedStep(m32, cor, data, lr=w["lr"], weight_decay=w["wd"], clip=w["clip"], world_size=world, use_graph=not args.no_graph)
-        for s in range(4):
-            f32.step(batches[s], global_batch=B * world)
+        e2e_loop(6)
         barrier()
-        e0.record()
-        for s in range(20):
-            f32.step(batches[s], global_batch=B * world)
-        e1.record()
+        t0 = time.perf_counter()
+        e2e_loop(Ke)
         barrier()
-        fp32_mode = {"ms_per_step": e0.elapsed_time(e1) / 20, "value": world * B * 20 / (e0.elapsed_time(e1) / 1e3), "unit": "samples/s",
-                     "engine": "exact-fp32 FFMA GEMMs (parity 1e-5 vs the reference)"}
-        del f32, m32
+        e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
+        if world > 1:
+            dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+        out["e2e"] = {"value": world * B * Ke / (float(e2e_ms.item()) / 1e3), "unit": "samples/s",
+                      "h2d_bytes_per_step": B * io * 4 + B * table.shape[1] * 2, "d2h_bytes_per_step": 32, "steps": Ke,
+                      "api": "codae.tool.FusedStep.step(staged=(rows, mask_table_rows))"}
+        del host_rows, host_tab, st_rows, st_tab
 
     # ---- per-kernel durations inside a real step (CUDA events on the launch stream) -> roofline ----------------------
-    prof = profile_step(fs, batches[0], B, world)      # every rank: the steps inside contain the all-reduce
+    prof = profile_step(fs, batches[0], B, world, name)      # every rank: the steps inside contain the collective
+    out.update({"roofline": prof["roofline"], "rooflines": prof["rooflines"], "kernels": prof["kernels"], "step_floor": prof["floor"]})
+    # whole step against its floor: tensor-bound configs -> GEMM flops at the sustained bf16 peak (+ the HBM-bound kernels at
+    # the HBM peak); small-batch configs -> the HBM floor of SURVEY section 8(d)
+    fl = prof["floor"]
+    out["step_vs_floor"] = {"floor_ms": fl["ms"], "bound": fl["bound"], "frac": fl["ms"] / (ms / K)}
+    del fs, model, cor, data, ds, batches
+    torch.cuda.empty_cache()
+    return out, w
 
-    # ---- scoring: candidate scores/s over a sharded synthetic catalog ---------------------------------------------------
+
+def scoring_block(args, env, E, seed, model_for_swaps=None):
+    import torch.distributed as dist
+    from codae.tool.inference import ComplementarityScorer, shard_rows
+    rank, world, dev = env["rank"], env["world"], env["dev"]
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    lo, n_local = shard_rows(args.catalog, world, rank)
+    g = torch.Generator(device=dev).manual_seed(seed + 17)
+    catalog = torch.rand((n_local, E), generator=g, device=dev)
+    q = torch.rand((1, E), generator=g, device=dev)
+    reps = 10
     scoring = None
-    if not args.no_scoring:
-        del data, fs
-        torch.cuda.empty_cache()
-        lo, n_local = shard_rows(args.catalog, world, rank)
-        g = torch.Generator(device=dev).manual_seed(w["seed"] + 17)
-        catalog = torch.rand((n_local, w["E"]), generator=g, device=dev)
-        q = torch.rand((1, w["E"]), generator=g, device=dev)
-        sc = ComplementarityScorer(catalog, w["E"], metric="sqerr", k=10, row_offset=lo)
+    for tag, cat in (("f32", catalog), ("bf16", None)):
+        if cat is None:
+            cat = catalog.to(torch.bfloat16)
+        sc = ComplementarityScorer(cat, E, metric="sqerr", k=10, row_offset=lo)
         for _ in range(3):
             sc.topk(q)
         barrier()
-        reps = 10
         e0.record()
         for _ in range(reps):
             sc.topk(q)
@@ -392,77 +355,184 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / reps
-        bytes_per = n_local * w["E"] * 4
-        scoring = {"metric": "candidate-outfit scores/s", "value": args.catalog / (sweep_ms / 1e3), "unit": "scores/s",
-                   "catalog_rows": args.catalog, "E": w["E"], "dtype": "f32", "k": 10, "ms_per_sweep": sweep_ms, "scaling": "strong",
-                   "roofline": {"bound": "hbm", "achieved": bytes_per / (k_ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                                "frac": bytes_per / (k_ms / 1e3) / 1e9 / pk["hbm"], "traffic": None,
-                                "kernel": "score_topk_kernel (+merge)", "peak_source": pk["src"]}}
-        # the same sweep over a bf16 copy of the catalog (1024 B / candidate instead of 2048): kernel alone, this rank's shard
-        try:
-            cat_bf = catalog.to(torch.bfloat16)
-            sc_bf = ComplementarityScorer(cat_bf, w["E"], metric="sqerr", k=10, row_offset=lo)
-            for _ in range(3):
-                sc_bf.topk_local(q)
-            torch.cuda.synchronize()
-            e0.record()
-            for _ in range(reps):
-                sc_bf.topk_local(q)
-            e1.record()
-            torch.cuda.synchronize()
-            kb_ms = e0.elapsed_time(e1) / reps
-            bytes_bf = n_local * w["E"] * 2
-            scoring["bf16_catalog"] = {"value": n_local / (kb_ms / 1e3), "unit": "scores/s per GPU", "ms_per_sweep": kb_ms,
-                                       "roofline": {"bound": "hbm", "achieved": bytes_bf / (kb_ms / 1e3) / 1e9, "peak": pk["hbm"],
-                                                    "unit": "GB/s", "frac": bytes_bf / (kb_ms / 1e3) / 1e9 / pk["hbm"]}}
-            del sc_bf, cat_bf
-        except Exception as ex:  # the fp32 line above is the contract; report, do not lose the run
-            scoring["bf16_catalog"] = {"error": repr(ex)[:200]}
-        # swaps scored by FULL reconstruction (candidate substituted, whole outfit through the DAE): GEMM-bound variant
-        n_sw = min(n_local, 1 << 20)
-        sw = SwapScorer(model, catalog[:n_sw], w["E"], k=10, row_offset=lo, chunk=8192)
-        outfit = torch.rand(io, generator=g, device=dev)
-        for _ in range(2):
-            sw.topk(outfit, 1)
-        barrier()
-        e0.record()
-        for _ in range(3):
-            sw.topk(outfit, 1)
-        e1.record()
-        barrier()
-        sms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(sms, op=dist.ReduceOp.MAX)
-        sw_ms = float(sms.item()) / 3
-        sw_flops = 2.0 * sum(i * o for i, o in model.dims) * n_sw
-        scoring["swap_reconstruction"] = {"metric": "candidate swaps/s (full DAE reconstruction per swap)",
-                                          "value": world * n_sw / (sw_ms / 1e3), "unit": "swaps/s", "swaps_per_rank": n_sw,
-                                          "chunk": 8192, "ms": sw_ms, "engine": fs_dtype(dtype, model),
-                                          "tflops": sw_flops / (sw_ms / 1e3) / 1e12}
-        if rank == 0 and not args.no_cpu:
-            scoring["cpu_baseline"] = {"value": cpu_scoring(w["E"]), "unit": "scores/s", "cores": os.cpu_count(), "kind": "port",
-                                       "sample": "3 x cosine_similarity + topk over 1M x %d rows (the reference's op)" % w["E"]}
+        bytes_per = n_local * E * cat.element_size()
+        blk = {"metric": "candidate-outfit scores/s", "value": args.catalog / (sweep_ms / 1e3), "unit": "scores/s",
+               "catalog_rows": args.catalog, "E": E, "dtype": tag, "k": 10, "ms_per_sweep": sweep_ms, "scaling": "strong",
+               "kernel_ms": k_ms,
+               "roofline": {"bound": "hbm", "achieved": bytes_per / (k_ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                            "frac": bytes_per / (k_ms / 1e3) / 1e9 / pk["hbm"], "traffic": measured_traffic("scoring_" + tag),
+                            "kernel": "score_topk_kernel", "peak_source": pk["src"],
+                            "algorithmic_per_launch": bytes_per}}
+        if scoring is None:
+            scoring = blk
+        else:
+            scoring["bf16_catalog"] = blk
+        del sc
+    del catalog
+    torch.cuda.empty_cache()
+    return scoring
 
+
+def swap_block(args, env, seed):
+    """Swaps scored by FULL reconstruction (candidate substituted, whole outfit through the DAE): the GEMM-bound reading of
+    "scores candidate item swaps by reconstruction error", on the embedding.yaml model."""
+    import torch.distributed as dist
+    from codae.model import EmbeddingDenoisingAutoencoder
+    from codae.tool.inference import SwapScorer, shard_rows
+    rank, world, dev = env["rank"], env["world"], env["dev"]
+    w = WORKLOADS["embedding"]
+    io = w["S"] * w["E"]
+    model = EmbeddingDenoisingAutoencoder(io, w["z"], w["E"], w["nin"], w["nout"], False)
+    model.set_compute_dtype("bf16")
+    model.to(dev)
+    lo, n_local = shard_rows(args.catalog, world, rank)
+    n_sw = min(n_local, 1 << 20)
+    g = torch.Generator(device=dev).manual_seed(seed + 19)
+    catalog = torch.rand((n_sw, w["E"]), generator=g, device=dev)
+    sw = SwapScorer(model, catalog, w["E"], k=10, row_offset=lo, chunk=8192)
+    outfit = torch.rand(io, generator=g, device=dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(2):
+        sw.topk(outfit, 1)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(3):
+        sw.topk(outfit, 1)
+    e1.record()
+    torch.cuda.synchronize()
+    sms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+    sw_ms = float(sms.item()) / 3
+    sw_flops = 2.0 * sum(i * o for i, o in model.dims) * n_sw
+    return {"metric": "candidate swaps/s (full DAE reconstruction per swap)", "value": world * n_sw / (sw_ms / 1e3),
+            "unit": "swaps/s", "swaps_per_rank": n_sw, "chunk": 8192, "ms": sw_ms, "engine": "bf16",
+            "tflops": sw_flops / (sw_ms / 1e3) / 1e12}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", type=str, default="polyvore", choices=sorted(WORKLOADS))
+    ap.add_argument("--dtype", type=str, default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-scoring", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the small-batch configs reported beside the primary workload")
+    ap.add_argument("--no-prefetch", action="store_true", help="weight tiles are not requested ahead of the PDL wait")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="A/B: launch without programmatic dependent launch")
+    ap.add_argument("--no-splitk", action="store_true", help="A/B: single-pass small-batch contractions")
+    ap.add_argument("--no-persistent", action="store_true", help="A/B: one tile per CTA for the large contractions")
+    ap.add_argument("--no-wgrad-sqnorm", action="store_true",
+                    help="A/B (1 GPU): cooperative norm + Adam kernel instead of sum(dW^2) partials from the weight-gradient kernels")
+    ap.add_argument("--no-tma-store", action="store_true", help="A/B: per-thread stores instead of TMA bulk stores (both GEMM kernels)")
+    ap.add_argument("--dp-mode", type=str, default=None, choices=["peer", "nccl"],
+                    help="data parallel: fused peer-memory reduce-scatter + sharded Adam + all-gather kernel (default) or NCCL all-reduce")
+    ap.add_argument("--catalog", type=int, default=10_000_000)
+    args = ap.parse_args()
+    w0 = dict(WORKLOADS[args.workload])
+    big = args.workload == "polyvore"
+    K = args.steps if args.steps is not None else (30 if big else 2000)
+    Wm = args.warmup if args.warmup is not None else (5 if big else 50)
+    if Wm < 3 and args.impl == "ours":
+        Wm = 3                          # timing rules: at least 3 warm-up steps on the GPU arm
+    dtype = args.dtype or w0["dtype"]
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference(w0, K, Wm)
+        print(json.dumps({"impl": "reference", "metric": "train samples/s", "value": r["value"], "unit": "samples/s",
+                          "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": r["ms_per_step"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": workload_config(args.workload, w0, layer_dims(w0), world),
+                          "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                          "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a B200; the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    from codae import _C
+    if args.no_pdl:
+        _C.set_option(dev, _C.OPT_PDL, 0)
+    if args.no_prefetch:
+        _C.set_option(dev, _C.OPT_WEIGHT_PREFETCH, 0)
+    if args.no_splitk:
+        _C.set_option(dev, _C.OPT_SPLITK, 0)
+    if args.no_persistent:
+        _C.set_option(dev, _C.OPT_PERSISTENT, 0)
+    if args.no_tma_store:
+        _C.set_option(dev, _C.OPT_TMA_STORE, 0)
+        _C.set_option(dev, _C.OPT_TMA_STORE_PERSISTENT, 0)
+    env = dict(rank=rank, world=world, dev=dev, local=local)
+
+    out, w = train_block(args.workload, dtype, K, Wm, args, env, e2e=True)
+    # ---- the shipped small-batch configs, each at its stated precision and in the other mode (same run, same box) -------
+    if not args.no_secondary and args.workload == "polyvore" and args.dtype is None:
+        sec = {}
+        for tag, name, dt_ in (("embedding.yaml fp32 (reference precision)", "embedding", "fp32"),
+                               ("embedding.yaml bf16", "embedding", "bf16"),
+                               ("modanet_merge_top_bottom_shoe.yaml bf16", "modanet", "bf16")):
+            try:
+                blk, _ = train_block(name, dt_, 500, 30, args, env, e2e=True)
+                keep = ("value", "unit", "ms_per_step", "dtype", "engine", "config", "e2e", "roofline", "step_vs_floor", "kernels",
+                        "gpu_launches", "steps", "warmup", "loss_last_step", "dp_mode")
+                sec[tag] = {k: blk[k] for k in keep if k in blk}
+            except Exception as ex:      # the primary line is the contract: report, do not lose the run
+                sec[tag] = {"error": repr(ex)[:300]}
+        out["secondary"] = sec
+    if not args.no_scoring:
+        out["scoring"] = scoring_block(args, env, w["E"], w["seed"])
+        try:
+            out["scoring"]["swap_reconstruction"] = swap_block(args, env, w["seed"])
+        except Exception as ex:
+            out["scoring"]["swap_reconstruction"] = {"error": repr(ex)[:300]}
+        if rank == 0 and not args.no_cpu:
+            out["scoring"]["cpu_baseline"] = {"value": cpu_scoring(w["E"]), "unit": "scores/s", "cores": os.cpu_count(), "kind": "reference",
+                                              "sample": "3 x cosine_similarity + topk over 1M x %d rows (the reference's op, metering.py:67-69)" % w["E"]}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    out = {"metric": "train samples/s", "value": world * B * K / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": K,
-           "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32" if fs_dtype(dtype, model) == "fp32" else "bf16", "data": "synthetic", "config": config,
-           "loss_last_step": loss_last, "clocks": clocks,
-           "e2e": {"value": e2e_val, "unit": "samples/s", "h2d_bytes_per_step": B * io * 4 + B * table.shape[1] * 2,
-                   "d2h_bytes_per_step": 32, "steps": Ke, "api": "codae.tool.FusedStep.step(staged=(rows, mask_table_rows))"},
-           "gpu_launches": launches, "cuda_graph": not args.no_graph,
-           "roofline": prof["roofline"] if prof else None, "rooflines": prof["rooflines"] if prof else None,
-           "kernels": prof["kernels"] if prof else None,
-           "step_floor": prof["floor"] if prof else None, "fp32_engine": fp32_mode, "scoring": scoring}
     if not args.no_cpu:
-        r = cpu_reference(w, 200 if args.workload != "polyvore" else 2, 3 if args.workload != "polyvore" else 1)
+        r = cpu_reference(w, 4 if big else 200, 1 if big else 3)
         out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def engine_name(model):
+    from codae import _C
+    e = model.engine_dtype()
+    return {_C.BF16: "tcgen05 bf16 (fp32 accumulate in TMEM)", _C.F32: "exact-fp32 FFMA"}.get(e, str(e))
+
+
+_TRAFFIC = None
+
+
+def measured_traffic(key):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of this
+    round (profiles/r02_traffic.json, written by tools/ncu_summary.py --traffic); None when no capture exists for `key`."""
+    global _TRAFFIC
+    if _TRAFFIC is None:
+        path = os.path.join(ROOT, "profiles", "r02_traffic.json")
+        _TRAFFIC = json.load(open(path)) if os.path.exists(path) else {}
+    v = _TRAFFIC.get(key)
+    return None if v is None else v.get("bytes_per_launch")
 
 
 def fs_dtype(dtype, model):
@@ -470,7 +540,7 @@ def fs_dtype(dtype, model):
     return "bf16" if model.engine_dtype() == _C.BF16 else "fp32"
 
 
-def profile_step(fs, idx, B, world):
+def profile_step(fs, idx, B, world, name):
     """Per-kernel-group durations and rooflines.  One eager step is recorded (which ABI calls, with which arguments);
     every group is then captured R times into one CUDA graph and replayed between ONE CUDA-event pair on the launching
     stream, so a group's time is GPU time of exactly its launches (no host launch gaps).  Rooflines use ALGORITHMIC bytes / flops
@@ -480,7 +550,7 @@ def profile_step(fs, idx, B, world):
     model = fs.model
     dims = model.dims
     wrapped = ["corrupt_fwd", "linear_fwd", "mse_loss_fwd_bwd", "linear_wgrad", "linear_dgrad", "grad_sqnorm", "counter_add", "adam_step",
-               "clip_adam_step", "linear_wgrad_sq", "adam_step_partials", "linear_chain"]
+               "clip_adam_step", "linear_wgrad_sq", "adam_step_partials", "dp_adam_step"]
     orig = {n: getattr(_C, n) for n in wrapped}
     calls = {n: [] for n in wrapped}
 
@@ -574,25 +644,25 @@ def profile_step(fs, idx, B, world):
         ach = work / (gemm_ms / 1e3) / (1e9 if bound == "hbm" else 1e12)
         peak = pk["hbm"] if bound == "hbm" else tensor_peak
         roof = {"bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak,
-                "traffic": None, "kernel": "tc05_gemm_kernel (fwd + dgrad + wgrad launches)" if bf else "simt_gemm_kernel",
+                "traffic": None, "kernel": ("tc05_gemm_persistent_kernel (fwd + dgrad + wgrad launches)" if not small else
+                                            "tc05_gemm_kernel (fwd + dgrad + wgrad launches)") if bf else "simt_gemm_kernel (fwd + dgrad + wgrad launches)",
                 "share_of_step": gemm_ms / step_ms, "peak_source": pk["src"], "algorithmic_per_launch": work / launches,
                 "note": "B <= 1024: bound by streaming the weights once per contraction (weights + activations bytes), not by the "
                         "tensor pipe; latency-bound in practice, see DESIGN.md section 7" if small else
                         "dense bf16 contraction vs the sustained cuBLAS bf16 peak"}
     else:
         roof = rooflines[top_other]
-    # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture (profiles/r01_ncu_full_
-    # metrics.txt); null when no capture exists for this workload / engine.
-    measured_traffic = {("tc05", 1536, True): 5.65e6 * 19 / 29 + 0.85e6 * 10 / 29,     # fwd/dgrad 5.65 MB, wgrad 0.85 MB read
-                        # 4096-wide persistent GEMMs: fwd 166 + 98, dgrad 240 + 52, wgrad 294 + 50 MB (read + write)
-                        ("tc05", 4096, False): (10 * 264e6 + 9 * 292e6 + 10 * 344e6) / 29}
-    key = ("tc05" if bf else "simt", io, small)
-    if roof.get("kernel", "").startswith("tc05") and key in measured_traffic:
-        roof["traffic"] = measured_traffic[key]
-        roof["traffic_source"] = "profiles/r01_ncu_full_metrics.txt (dram__bytes_read.sum + dram__bytes_write.sum, mean over the launches of a step)"
-    floor_bytes = 32 * P + 3 * Wsum * sw + B * 20 * io
-    floor = {"hbm_bytes_per_step": floor_bytes, "ms_at_peak": floor_bytes / (pk["hbm"] * 1e9) * 1e3,
-             "sum_of_kernel_ms": step_ms}
+    # DRAM traffic per launch of the dominant kernel from this round's committed `ncu --set full` capture (profiles/r02_traffic.json)
+    roof["traffic"] = measured_traffic("%s_%s_%s" % (name, "bf16" if bf else "fp32", "gemm" if "gemm" in roof.get("kernel", "") else roof.get("kernel", "")))
+    hbm_bytes = 32 * P + B * 20 * io
+    if small:
+        floor_bytes = hbm_bytes + 3 * Wsum * sw
+        floor = {"bound": "hbm", "hbm_bytes_per_step": floor_bytes, "ms": floor_bytes / (pk["hbm"] * 1e9) * 1e3, "sum_of_kernel_ms": step_ms}
+    else:
+        flops = 2.0 * B * (3 * Wsum - W1)
+        floor = {"bound": "tensor", "flops_per_step": flops, "hbm_bytes_per_step": hbm_bytes,
+                 "ms": flops / (tensor_peak * 1e12) * 1e3 + hbm_bytes / (pk["hbm"] * 1e9) * 1e3,
+                 "gemm_ms_at_sustained_peak": flops / (tensor_peak * 1e12) * 1e3, "sum_of_kernel_ms": step_ms}
     return {"kernels": kernels, "roofline": roof, "rooflines": rooflines, "floor": floor}
 
 

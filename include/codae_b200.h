@@ -66,7 +66,7 @@ int codae_ctx_sm_count(const codae_ctx* ctx);
  *                     cp.async.bulk.tensor stores instead of per-thread 128-bit stores (the N & 3 tail columns of a row
  *                     are stored by the threads: TMA clips ragged row ends at 16-byte granularity).  Same values, bit for
  *                     bit; measured 98.8 -> 64.2 us for the ten weight gradients of the embedding.yaml step.
- *   CODAE_OPT_TMA_STORE_PERSISTENT  (default OFF: written, not yet measured on a B200) the same for the persistent kernel
+ *   CODAE_OPT_TMA_STORE_PERSISTENT  (default on: 7.155 -> 6.970 ms/step at 10 x 4096^2, B = 8192) the same for the persistent kernel
  *                     of the large contractions: every epilogue warp stages 32 rows x 128 bytes per store in one of two
  *                     boxes of its own and issues the bulk store itself (f32 and bf16 outputs, all fused epilogues). */
 enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1, CODAE_OPT_PERSISTENT = 2, CODAE_OPT_WEIGHT_PREFETCH = 3,
@@ -181,28 +181,6 @@ int codae_linear_wgrad_sq_slots(const codae_ctx* ctx, int M, int N, int K, int d
 int codae_linear_wgrad_sq(codae_ctx* ctx, const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW,
                           int64_t lddw, int M, int N, int K, int dtype, double* sq_partials, int n_slots,
                           void* stream);
-/* A CHAIN of dependent Linear layers in one persistent launch (tensor-core engine, batches of at most 128 rows):
- * the model(c_input) call of the training loop (train_dae_on_embedding.py:204; forward :137-185) or the input-gradient
- * chain of loss.backward() as ONE kernel instead of one per layer.  Layer l computes
- *     C_l[M, N] = epilogue( A_l[M, K] . B_l )      A_l bf16 [M, lda]; typically A_{l+1} = C_l
- *   b_kmajor = 1: B_l = W[N, K] (pitch ldb), C = A . W^T        (forward; act = CODAE_ACT_RELU fuses the ReLU)
- *   b_kmajor = 0: B_l = W[K, N] (pitch ldb), C = A . W          (input gradient; mask_src [M, ldm] bf16: C *= (mask > 0))
- *   c_dtype: CODAE_BF16 (feeds the next layer) or CODAE_F32 (last layer).
- * Same tiles, k order and rank-ordered split-K reduction as codae_linear_fwd / codae_linear_dgrad at these sizes.
- * OPT-IN: written and compiled, not yet validated on a B200 (FusedStep(chain_forward=True) / CODAE_CHAIN=1).
- * workspace >= codae_linear_chain_workspace_bytes(); it is zeroed with a memset node on `stream` before the launch. */
-#define CODAE_CHAIN_MAX_LAYERS 16
-typedef struct codae_chain_layer {
-    const void* A; int64_t lda;
-    const void* B; int64_t ldb; int b_kmajor;
-    void* C; int64_t ldc; int c_dtype;
-    int N, K;
-    int act;
-    const void* mask_src; int64_t ldm;
-} codae_chain_layer;
-size_t codae_linear_chain_workspace_bytes(const codae_ctx* ctx);
-int codae_linear_chain(codae_ctx* ctx, const codae_chain_layer* layers, int n_layers, int M, void* workspace,
-                       size_t ws_bytes, void* stream);
 /* Tabular widths (abalone: Linear layers of at most 11 x 11): the WHOLE network in one launch, exact fp32 FMA arithmetic.
  * Replaces the per-layer codae_linear_fwd / codae_linear_dgrad / codae_linear_wgrad launches of
  * MixedVariableDenoisingAutoencoder.forward (codae/model/mixed_variable_denoising_autoencoder.py:133-181) and of
@@ -211,7 +189,8 @@ int codae_linear_chain(codae_ctx* ctx, const codae_chain_layer* layers, int n_la
  *   fwd: acts[l+1][r, o] = act_l(sum_{k <= bcol} acts[l][r, k] W'_l[o, k])                      acts: L+1 device pointers (host array)
  *   bwd: dW'_l[o, k] = sum_r g_l[r, o] acts[l][r, k] ;  g_{l-1}[r, k] = (sum_o g_l[r, o] W'_l[o, k]) * (acts[l][r, k] > 0 if ReLU
  *        follows layer l-1), with g_l in g3[l % 3] ([B, ld_g] f32; g3[(L-1) % 3] holds dL/dy on entry)
- * OPT-IN, not yet run on a B200 (FusedStep(tiny_mlp=True)); the arithmetic (csrc/tiny_mlp.h) is unit-tested on the CPU. */
+ * Default for tabular widths (FusedStep(tiny_mlp=None)): parity-checked on a B200 against the reference's abalone goldens
+ * (tests/test_gpu_variants.py); the arithmetic (csrc/tiny_mlp.h) is also unit-tested on the CPU. */
 typedef struct codae_tiny_layer {
     int64_t w_off;
     int32_t ld, bcol, in, out, relu;
@@ -257,6 +236,34 @@ int codae_adam_step_partials(codae_ctx* ctx, float* p, const float* g, float* m,
                              double grad_scale, const int32_t* step_dev, void* stream);
 /* *counter += delta on the device (the Adam step counter of a CUDA-graph-captured training step). */
 int codae_counter_add(codae_ctx* ctx, int32_t* counter, int delta, void* stream);
+
+/* ---- K4 under data parallelism: reduce-scatter + clip + Adam + all-gather as ONE kernel over NVLink peer memory ----------
+ * Replaces, per step, the reference-equivalent DP sequence  all-reduce(grads) -> clip_grad_norm_ -> Adam.step on every replica
+ * (train_dae_on_embedding.py:209-215 under one process per GPU).  Rank r owns elements [r S, (r+1) S) of the flat buffers,
+ * S = codae_dp_shard_elems(n, world): it sums that shard of every rank's gradient buffer through peer loads (rank order,
+ * deterministic), exchanges the shard's sum of squares with the peers (same clip scale, bit for bit, on every rank), applies
+ * Adam to the shard (p: this rank's f32 master [n], only the shard is updated; m, v: SHARD-sized moments [S]) and stores the
+ * new weights into EVERY rank's weight buffer w_out[q] ([n] bf16 shadow -- CODAE_BF16 -- or the f32 master itself --
+ * CODAE_F32, then w_out[rank] == p).  When the kernel ends on a rank, that rank's weight buffer is complete and no peer reads
+ * its gradients any more.  grads / w_out / signals are device pointers valid in THIS process for every rank's buffer (CUDA IPC /
+ * torch symmetric memory); signals[q]: CODAE_DP_SIGNAL_BYTES bytes, zeroed once before the first call, owned by the library
+ * afterwards.  Every rank must call it the same number of times; cross-GPU waits are bounded (CODAE_DP_TIMEOUT_S, default 30 s:
+ * the kernel traps and the next CUDA call reports it).  Cooperative launch, no host synchronisation, CUDA-graph capturable.
+ * n % 8 == 0 (the flat layout pads rows to 64 elements), world <= CODAE_DP_MAX_WORLD. */
+#define CODAE_DP_MAX_WORLD 8
+#define CODAE_DP_SIGNAL_BYTES 512
+typedef struct codae_dp_peers {
+    int32_t world, rank;
+    const float* grads[CODAE_DP_MAX_WORLD];
+    void* w_out[CODAE_DP_MAX_WORLD];
+    void* signals[CODAE_DP_MAX_WORLD];
+} codae_dp_peers;
+size_t codae_dp_workspace_bytes(const codae_ctx* ctx);
+int64_t codae_dp_shard_elems(int64_t n, int world);
+int codae_dp_adam_step(codae_ctx* ctx, const codae_dp_peers* peers, float* p, float* m, float* v, int w_dtype, int64_t n,
+                       double lr, double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
+                       float* sqnorm_out, void* workspace, size_t ws_bytes, double grad_scale, const int32_t* step_dev,
+                       void* stream);
 
 /* ---- K3: complementarity inference -------------------------------------------------------------- */
 /* Scores every row of a catalog shard against Q query vectors and keeps the best k per query.

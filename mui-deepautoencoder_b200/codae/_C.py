@@ -47,8 +47,6 @@ SIGNATURES = {
     "codae_linear_wgrad": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
     "codae_linear_wgrad_sq_slots": (_i, [_vp, _i, _i, _i, _i]),
     "codae_linear_wgrad_sq": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp]),
-    "codae_linear_chain_workspace_bytes": (_sz, [_vp]),
-    "codae_linear_chain": (_i, [_vp, _vp, _i, _i, _vp, _sz, _vp]),
     "codae_tiny_mlp_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _i, _vp]),
     "codae_tiny_mlp_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp]),
     "codae_cast_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
@@ -58,6 +56,9 @@ SIGNATURES = {
     "codae_clip_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _vp, _sz, _d, _vp, _vp]),
     "codae_adam_step_partials": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _i, _vp, _d, _vp, _vp]),
     "codae_counter_add": (_i, [_vp, _vp, _i, _vp]),
+    "codae_dp_workspace_bytes": (_sz, [_vp]),
+    "codae_dp_shard_elems": (_i64, [_i64, _i]),
+    "codae_dp_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _vp, _sz, _d, _vp, _vp]),
     "codae_score_topk_workspace_bytes": (_sz, [_vp, _i, _i]),
     "codae_score_topk": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "codae_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
@@ -67,13 +68,15 @@ SIGNATURES = {
                                    _sz, _vp]),
 }
 
-class ChainLayer(ctypes.Structure):
-    """struct codae_chain_layer (include/codae_b200.h)."""
-    _fields_ = [("A", _vp), ("lda", _i64), ("B", _vp), ("ldb", _i64), ("b_kmajor", _i), ("C", _vp), ("ldc", _i64),
-                ("c_dtype", _i), ("N", _i), ("K", _i), ("act", _i), ("mask_src", _vp), ("ldm", _i64)]
+DP_MAX_WORLD = 8
+DP_SIGNAL_BYTES = 512
 
 
-CHAIN_MAX_LAYERS = 16
+class DpPeers(ctypes.Structure):
+    """struct codae_dp_peers (include/codae_b200.h): every rank's gradient buffer, weight buffer and signal pad as device
+    pointers valid in this process."""
+    _fields_ = [("world", _c.c_int32), ("rank", _c.c_int32), ("grads", _vp * DP_MAX_WORLD), ("w_out", _vp * DP_MAX_WORLD),
+                ("signals", _vp * DP_MAX_WORLD)]
 
 
 class TinyLayer(ctypes.Structure):
@@ -273,22 +276,30 @@ def linear_wgrad_sq(dY, X, dW, M, N, K, dtype, sq_partials):
                                       p(sq_partials), sq_partials.numel(), stream()), c)
 
 
-def linear_chain_workspace(device):
+def dp_shard_elems(n, world):
+    """Elements of the flat buffers every rank owns under the sharded data-parallel update (host arithmetic, no GPU needed)."""
+    return int(lib().codae_dp_shard_elems(n, world))
+
+
+def dp_workspace(device):
     c = ctx(device)
-    return torch.zeros(int(lib().codae_linear_chain_workspace_bytes(c)), dtype=torch.uint8, device=device)
+    return torch.zeros(int(lib().codae_dp_workspace_bytes(c)), dtype=torch.uint8, device=device)
 
 
-def chain_layer(A, B, b_kmajor, C, N, K, act=ACT_NONE, mask_src=None):
-    """One entry of a codae_linear_chain call: C[M, N] = epilogue(A[M, K] . B), see include/codae_b200.h."""
-    return ChainLayer(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), 1 if b_kmajor else 0, C.data_ptr(), C.stride(0), dt(C),
-                      N, K, act, None if mask_src is None else mask_src.data_ptr(), 0 if mask_src is None else mask_src.stride(0))
+def dp_peers(world, rank, grad_ptrs, w_ptrs, signal_ptrs):
+    pe = DpPeers()
+    pe.world, pe.rank = world, rank
+    for q in range(world):
+        pe.grads[q], pe.w_out[q], pe.signals[q] = int(grad_ptrs[q]), int(w_ptrs[q]), int(signal_ptrs[q])
+    return pe
 
 
-def linear_chain(layers, M, ws):
-    """layers: list of ChainLayer (their tensors must stay alive until the stream reaches the launch)."""
-    c = ctx(ws.device)
-    arr = (ChainLayer * len(layers))(*layers)
-    check(lib().codae_linear_chain(c, ctypes.cast(arr, _vp), len(layers), M, p(ws), ws.numel(), stream()), c)
+def dp_adam_step(peers, pf, m, v, w_dtype, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm_out, ws, grad_scale, step_dev=None):
+    """Reduce-scatter + clip + Adam on this rank's shard + all-gather of the new weights, one kernel over peer memory."""
+    _dev_check(pf, m, v, sqnorm_out, ws)
+    c = ctx(pf.device)
+    check(lib().codae_dp_adam_step(c, ctypes.byref(peers), p(pf), p(m), p(v), w_dtype, pf.numel(), lr, beta1, beta2, eps, wd, step,
+                                   max_norm, p(sqnorm_out), p(ws), ws.numel(), grad_scale, p(step_dev), stream()), c)
 
 
 def _ptr_array(tensors):

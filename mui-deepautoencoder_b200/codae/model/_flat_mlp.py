@@ -121,6 +121,15 @@ class FlatMLP(torch.nn.Module):
         self.flat = flat
         self.flat_bf16 = None
 
+    def rebind_flat(self, new_flat):
+        """Moves the flat fp32 parameter buffer into `new_flat` (same layout; e.g. a symmetric-memory allocation the peers of a
+        data-parallel run can write) and re-points every Parameter view."""
+        new_flat.copy_(self.flat)
+        for l, lin in enumerate(self.linears()):
+            lin.weight.data = self.weight_view(new_flat, l)
+            lin.bias.data = self.bias_view(new_flat, l)
+        self.flat = new_flat
+
     def set_compute_dtype(self, name):
         """"fp32": exact-fp32 FFMA engine (reference precision).  "bf16": tcgen05 tensor cores with fp32
         accumulation and fp32 master weights; falls back to nothing -- layers the tensor-core engine cannot
@@ -143,8 +152,9 @@ class FlatMLP(torch.nn.Module):
         _C.cast_bf16(self.flat, self.flat_bf16)
 
     def sync_weights(self):
-        """A trainer that defers its optimizer update (FusedStep(deferred_update=True)) registers its flush() here; every entry
-        point of the model that reads the weights applies the pending update first.  No-op otherwise."""
+        """A data-parallel trainer with a sharded update (FusedStep, dp_mode="peer") registers its flush() here: every entry
+        point of the model that reads the fp32 master weights first gathers the other ranks' shards (a COLLECTIVE: call it on
+        all ranks).  No-op otherwise."""
         hook = getattr(self, "_flush_hook", None)
         if hook is not None:
             hook()

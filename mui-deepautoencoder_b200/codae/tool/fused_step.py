@@ -12,15 +12,7 @@ Replaces, per step (script/train_dae_on_embedding.py:198-223; script/train_dae_o
   clip_grad_norm_ + Adam   -> codae_clip_adam_step: one cooperative launch over the flat buffers (norm, grid barrier,
                               update); or codae_grad_sqnorm + codae_adam_step; or (wgrad_sqnorm=True, single GPU,
                               tensor-core engine) codae_linear_wgrad_sq + codae_adam_step_partials: the weight-gradient
-                              kernels leave sum(dW^2) behind and the optimizer never reads g for the norm; or
-                              (layerwise_adam=True, no clipping, single GPU) codae_adam_step per layer on the weight-gradient
-                              stream as soon as that layer's wgrad and dgrad are done: the HBM-bound optimizer overlaps the
-                              latency-bound input-gradient chain (modanet_merge_top_bottom_shoe.yaml has no TRUNK_GRAD)
-  [deferred_update=True]   -> the update of step s is issued at the START of step s+1, layer by layer on its own stream, and
-                              the forward GEMM of layer l only waits for layer l's update: the HBM-bound optimizer (124 us)
-                              hides the latency-bound forward chain (72 us) of the next step.  Same arithmetic, same results;
-                              weights are final after flush() (evaluate() flushes).  Opt-in.  Without the per-CTA partials
-                              (data parallel, fp32 engine) the prologue takes the norm with codae_grad_sqnorm first.
+                              kernels leave sum(dW^2) behind and the optimizer never reads g for the norm
 No host synchronisation happens inside a step; monitors stay on the device until read_monitors().
 The whole sequence can be captured once per batch size into a CUDA graph (use_graph=True).
 """
@@ -42,13 +34,16 @@ class FusedStep:
 
     def __init__(self, model, corrupter, data, lr, weight_decay, clip=True, betas=(0.9, 0.999), eps=1e-8,
                  max_norm=1.0, world_size=1, process_group=None, use_graph=False, mixed=None, overlap_allreduce=True,
-                 fused_clip_adam=True, wgrad_sqnorm=None, layerwise_adam=None, chain_forward=None, chain_backward=None, deferred_update=None,
-                 tiny_mlp=None):
+                 fused_clip_adam=True, wgrad_sqnorm=None, tiny_mlp=None, dp_mode=None):
         """model: FlatMLP on a CUDA device; corrupter: codae.tool.Corrupter; data: resident [N, io] fp32 CUDA
         tensor (dataset.data).  mixed: None for the embedding loss (MSE mean over all elements) or a dict
         {arch, weight, norm_scale, norm_min, norm_first} for the abalone CombinedCriterion loss + monitors.
         world_size > 1: gradients are summed across `process_group` (each rank computes dL/dy with the GLOBAL
-        batch size, so the sum is the global-batch gradient the single-process reference would see)."""
+        batch size, so the sum is the global-batch gradient the single-process reference would see).
+        dp_mode (world_size > 1): "peer" (default) -- codae_dp_adam_step: reduce-scatter + clip + Adam on this rank's shard +
+        all-gather of the new weights as one kernel over NVLink peer memory (gradient / weight buffers live in torch symmetric
+        memory; moments are shard-sized; the fp32 master weights of the other shards are gathered by flush()); "nccl" -- NCCL
+        all-reduce of the flat gradient buffer in buckets overlapped with the backward pass, whole update on every replica."""
         if model.flat is None:
             raise RuntimeError("codae: FusedStep needs model.to(cuda_device) first; there is no CPU fallback")
         if not data.is_cuda:
@@ -67,11 +62,19 @@ class FusedStep:
         self.eng = model.engine_dtype()
         self.adt = torch.bfloat16 if self.eng == _C.BF16 else torch.float32
         n = model.flat.numel()
-        self.gflat = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.m = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(n, dtype=torch.float32, device=dev)
         if self.eng == _C.BF16:
             model.refresh_shadow()
+        self.dp_mode = None
+        self._master_stale = False
+        self._peers = None
+        if world_size > 1:
+            if mixed is not None:
+                raise RuntimeError("codae: the tabular (CombinedCriterion) step is single-GPU (792 parameters: replicas only)")
+            self.dp_mode = self._setup_data_parallel(dp_mode, n)
+        if self.dp_mode != "peer":
+            self.gflat = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.m = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.v = torch.zeros(n, dtype=torch.float32, device=dev)
         self.sqnorm = torch.zeros(1, dtype=torch.float32, device=dev)
         self.norm_ws = _C.sqnorm_workspace(dev)
         self.loss_ws = _C.loss_workspace(dev)
@@ -80,6 +83,9 @@ class FusedStep:
         self.step_count = 0
         self.kernel_launches = 0
         if mixed is not None:
+            # the tabular loss kernel writes dL/dy in f32 and normalises by the local batch (RMSE over the batch couples all rows)
+            if self.eng != _C.F32:
+                raise RuntimeError("codae: the tabular (CombinedCriterion) loss runs on the fp32 engine only")
             V = len(mixed["arch"])
             self.var_tables = arch_tables(mixed["arch"], dev)
             self.weight = torch.tensor(list(mixed["weight"]), dtype=torch.float32, device=dev)
@@ -101,56 +107,93 @@ class FusedStep:
         tiny_ok = (self.eng == _C.F32 and world_size == 1 and len(model.dims) <= _C.TINY_MAX_LAYERS
                    and max(max(i, o) for i, o in model.dims) <= 64)
         if tiny_mlp is None:
-            # opt-in, not yet run on a B200: tabular widths as ONE forward and ONE backward launch (codae_tiny_mlp_fwd / _bwd)
-            tiny_mlp = os.environ.get("CODAE_TINY_MLP") == "1" and tiny_ok
+            # tabular widths: ONE forward and ONE backward launch (codae_tiny_mlp_fwd / _bwd), 22 -> 7 launches per abalone step;
+            # CODAE_TINY_MLP=0 keeps the per-layer FFMA kernels (A/B)
+            tiny_mlp = os.environ.get("CODAE_TINY_MLP", "1") != "0" and tiny_ok
         if tiny_mlp and not tiny_ok:
             raise RuntimeError("codae: tiny_mlp needs the fp32 engine, a single GPU, at most %d layers of width <= 64" % _C.TINY_MAX_LAYERS)
         self.tiny_mlp = bool(tiny_mlp)
         self._tiny_layers = [_C.TinyLayer(lay[l][0], lay[l][1], lay[l][2], i, o, 1 if model.relu[l] else 0)
                              for l, (i, o) in enumerate(model.dims)] if self.tiny_mlp else None
-        if chain_forward is None:
-            # opt-in, not yet validated on a B200: the whole forward pass as ONE persistent launch (codae_linear_chain)
-            chain_forward = os.environ.get("CODAE_CHAIN") == "1" and self.eng == _C.BF16 and mixed is None
-        if chain_forward and (self.eng != _C.BF16 or len(model.dims) > _C.CHAIN_MAX_LAYERS):
-            raise RuntimeError("codae: chain_forward needs the tensor-core engine and at most %d layers" % _C.CHAIN_MAX_LAYERS)
-        self.chain_forward = bool(chain_forward)
-        if chain_backward is None:
-            # same switch: the input-gradient chain as one launch, then all weight gradients side by side on three streams
-            chain_backward = (os.environ.get("CODAE_CHAIN") == "1" and self.eng == _C.BF16 and mixed is None and world_size == 1)
-        if chain_backward and (self.eng != _C.BF16 or len(model.dims) > _C.CHAIN_MAX_LAYERS or world_size > 1):
-            raise RuntimeError("codae: chain_backward needs the tensor-core engine, at most %d layers and a single GPU "
-                               "(the data-parallel schedule reduces finished layers while the backward pass runs)" % _C.CHAIN_MAX_LAYERS)
-        self.chain_backward = bool(chain_backward)
-        self.chain_ws = _C.linear_chain_workspace(dev) if (self.chain_forward or self.chain_backward) else None
-        self._wgrad_stream2 = torch.cuda.Stream(device=dev) if self.chain_backward else None
-        if layerwise_adam is None:
-            # opt-in until measured on the target: CODAE_LAYERWISE_ADAM=1 turns it on wherever it applies
-            layerwise_adam = os.environ.get("CODAE_LAYERWISE_ADAM") == "1" and not clip and world_size == 1 and self.eng == _C.BF16
-        if layerwise_adam and (clip or world_size > 1):
-            raise RuntimeError("codae: layerwise_adam needs clip=False (the clip scale depends on every layer's gradient) and a "
-                               "single GPU (the update follows the gradient all-reduce)")
-        self.layerwise_adam = bool(layerwise_adam)
-        if self.layerwise_adam:
-            self.wgrad_sqnorm = False          # no norm is needed at all
         if self.wgrad_sqnorm and (world_size > 1 or self.eng != _C.BF16):
             raise RuntimeError("codae: wgrad_sqnorm needs a single GPU (the norm of a data-parallel run is taken after the "
                                "all-reduce) and the tensor-core engine")
-        if deferred_update is None:
-            # opt-in until measured on the target: CODAE_DEFERRED_UPDATE=1 turns it on wherever it applies
-            deferred_update = os.environ.get("CODAE_DEFERRED_UPDATE") == "1" and not self.layerwise_adam and mixed is None
-        if deferred_update and self.layerwise_adam:
-            raise RuntimeError("codae: deferred_update excludes layerwise_adam (both schedule the per-layer updates)")
-        self.deferred_update = bool(deferred_update)
-        self.deferred_chunk = max(1, int(os.environ.get("CODAE_DEFERRED_CHUNK", "1")))     # tuning knob: layers per update launch
-        self._pending = None                       # (B, sum-of-squares partials | None) of the step whose gradients await their update
-        if self.deferred_update:
-            model._flush_hook = self.flush         # state_dict() / forward() / encode() / decode() of the model flush first
-        self._update_stream = torch.cuda.Stream(device=dev) if self.deferred_update else None
         self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
         self._wgrad_stream = torch.cuda.Stream(device=dev)
         self._bufs = {}
         self._graphs = {}
         self._calls = {}
+
+    # ---- data parallel plumbing ----------------------------------------------------------------------
+    def _setup_data_parallel(self, want, n):
+        """Chooses the data-parallel schedule.  "peer": the flat gradient buffer, the weight buffer the GEMMs read and a signal
+        pad are allocated in torch symmetric memory and rendezvoused over the process group, which yields every rank's buffer as
+        a device pointer valid in this process (PyTorch is the plumbing; the data path is codae_dp_adam_step).  All ranks take
+        the same decision: if the rendezvous fails anywhere and "peer" was not requested explicitly, everyone uses "nccl"."""
+        import torch.distributed as dist
+        explicit = want is not None or os.environ.get("CODAE_DP_MODE") is not None
+        want = want or os.environ.get("CODAE_DP_MODE", "peer")
+        if want not in ("peer", "nccl"):
+            raise RuntimeError("codae: dp_mode must be 'peer' or 'nccl'")
+        if want == "nccl":
+            return "nccl"
+        group = self.pg if self.pg is not None else dist.group.WORLD
+        dev, model = self.dev, self.model
+        ok, err = 1, None
+        try:
+            if self.world_size > _C.DP_MAX_WORLD or n % 8:
+                raise RuntimeError("peer mode supports at most %d ranks and flat sizes that are multiples of 8" % _C.DP_MAX_WORLD)
+            import torch.distributed._symmetric_memory as symm
+            rank = dist.get_rank(group)
+            g = symm.empty(n, dtype=torch.float32, device=dev)
+            g.zero_()
+            w = symm.empty(n, dtype=torch.bfloat16 if self.eng == _C.BF16 else torch.float32, device=dev)
+            w.copy_(model.flat_bf16 if self.eng == _C.BF16 else model.flat)
+            sig = symm.empty(_C.DP_SIGNAL_BYTES // 8, dtype=torch.int64, device=dev)
+            sig.zero_()
+            handles = [symm.rendezvous(t, group) for t in (g, w, sig)]
+            ptrs = [[int(x) for x in h.buffer_ptrs] for h in handles]
+            assert all(len(x) == self.world_size for x in ptrs) and ptrs[0][rank] == g.data_ptr()
+        except Exception as ex:            # noqa: BLE001 -- reported below, every rank must reach the vote
+            ok, err = 0, ex
+        vote = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(vote, op=dist.ReduceOp.MIN, group=group)
+        if int(vote.item()) == 0:
+            if explicit:
+                raise RuntimeError("codae: dp_mode='peer' is not available on this system: %r" % (err,))
+            import warnings
+            warnings.warn("codae: symmetric-memory rendezvous failed (%r); data parallel falls back to the NCCL all-reduce schedule" % (err,))
+            return "nccl"
+        if self.eng == _C.BF16:
+            model.flat_bf16 = w
+        else:
+            model.rebind_flat(w)
+        self.gflat = g
+        S = _C.dp_shard_elems(n, self.world_size)
+        self._shard = (min(n, rank * S), min(n, (rank + 1) * S), S)
+        self.m = torch.zeros(S, dtype=torch.float32, device=dev)            # moments exist for this rank's shard only
+        self.v = torch.zeros(S, dtype=torch.float32, device=dev)
+        self._peers = _C.dp_peers(self.world_size, rank, *ptrs)
+        self._symm = (g, w, sig, handles)                                    # keep the mappings alive
+        self.dp_ws = _C.dp_workspace(dev)
+        self._dp_group = group
+        model._flush_hook = self.flush                                       # reading the weights gathers the master shards first
+        torch.cuda.synchronize()
+        dist.barrier(group=group)                                            # every pad is zeroed before anyone's first step
+        return "peer"
+
+    def _gather_master(self):
+        """COLLECTIVE: all-gather of the fp32 master-weight shards (peer mode on the tensor-core engine keeps only this rank's
+        shard of model.flat current; the bf16 weights every GEMM reads are always complete)."""
+        import torch.distributed as dist
+        lo, hi, S = self._shard
+        n = self.model.flat.numel()
+        mine = torch.zeros(S, dtype=torch.float32, device=self.dev)
+        mine[:hi - lo] = self.model.flat[lo:hi]
+        full = torch.empty(S * self.world_size, dtype=torch.float32, device=self.dev)
+        dist.all_gather_into_tensor(full, mine, group=self._dp_group)
+        self.model.flat.copy_(full[:n])
+        self._master_stale = False
 
     # ---- buffers ------------------------------------------------------------------------------------
     def _buffers(self, B):
@@ -172,9 +215,6 @@ class FusedStep:
                      idx=torch.zeros(B, dtype=torch.int64, device=dev),
                      x=torch.zeros((B, wmax), dtype=torch.float32, device=dev) if self.mixed is not None else None,
                      mon=torch.zeros((B, len(self.mixed["arch"])), dtype=torch.float32, device=dev) if self.mixed is not None else None)
-            if self.chain_backward and B <= 128:
-                # the chain keeps every layer's dL/d(out_l) until the weight gradients have read it
-                b["gchain"] = [torch.zeros((B, wmax), dtype=adt, device=dev) for _ in dims]
             if self.wgrad_sqnorm:
                 # one slot per CTA of every weight-gradient launch of this batch size
                 slots = [_C.linear_wgrad_sq_slots(dev, B, o, _round_up(i, 8) + 1, self.eng) for i, o in dims]
@@ -189,97 +229,44 @@ class FusedStep:
         return b
 
     # ---- the kernel sequence ----------------------------------------------------------------------------
-    def _enqueue(self, B, b, run, global_batch, data, idx, table, train=True, pending=None):
+    def _enqueue(self, B, b, run, global_batch, data, idx, table, train=True):
         model, dims, eng = self.model, self.model.dims, self.eng
         L = len(dims)
         _, bits, col_var, nmiss = self.corrupter.device_tables()
         acts = b["acts"]
         n = 0
-        updated = None
-        if pending is not None:
-            # The previous step's update, layer by layer (first layer first) on the update stream; this step's corruption and
-            # forward GEMMs run beside it on the current stream, layer l waiting only for layer l's new weights.
-            main, upd = torch.cuda.current_stream(), self._update_stream
-            fork = torch.cuda.Event()
-            fork.record(main)
-            upd.wait_event(fork)                      # the gradients and their sum-of-squares partials are complete
-            pb = model.flat_bf16 if eng == _C.BF16 else None
-            updated = []
-            with torch.cuda.stream(upd):
-                _C.counter_add(self.step_dev, 1); n += 1
-                partials = pending[1]
-                if partials is None and self.clip:          # no per-CTA partials (data parallel / fp32 engine): one norm pass
-                    _C.grad_sqnorm(self.gflat, self.sqnorm, self.norm_ws); n += 1
-                chunk = self.deferred_chunk                  # layers per update launch (1: finest pipelining with the forward pass)
-                for l0 in range(0, L, chunk):
-                    l1 = min(L, l0 + chunk)
-                    lo, hi = self._layer_span[l0][0], self._layer_span[l1 - 1][1]
-                    args = (model.flat[lo:hi], self.gflat[lo:hi], self.m[lo:hi], self.v[lo:hi], None if pb is None else pb[lo:hi],
-                            self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0, self.max_norm if self.clip else -1.0)
-                    if partials is not None:
-                        _C.adam_step_partials(*args, partials, self.sqnorm, 1.0, self.step_dev)
-                    else:
-                        _C.adam_step(*args, self.sqnorm if self.clip else None, 1.0, self.step_dev)
-                    n += 1
-                    ev = torch.cuda.Event()
-                    ev.record(upd)
-                    updated.extend([ev] * (l1 - l0))
         _C.corrupt_fwd(data, idx, B, table, run, bits, col_var, self.io, acts[0], b["x"], b["mask_id"]); n += 1
         wflat = model.flat_bf16 if eng == _C.BF16 else model.flat
-        if updated is not None and self.chain_forward and B <= 128:
-            torch.cuda.current_stream().wait_stream(self._update_stream)      # the chain launch reads every layer's weights
-            _C.weights_written(self.dev)
-            updated = None
         tiny = self.tiny_mlp and len({a.stride(0) for a in acts}) == 1
-        if tiny and updated is not None:
-            torch.cuda.current_stream().wait_stream(self._update_stream)      # one launch reads every layer's weights
-            _C.weights_written(self.dev)
-            updated = None
         if tiny:
             # tabular widths: every layer of the forward pass in one launch (rows are independent: one CTA per 32 rows)
             _C.tiny_mlp_fwd(self._tiny_layers, model.flat, acts, B); n += 1
-        elif self.chain_forward and B <= 128:
-            # every layer of the forward pass in one persistent launch (batches that fit one 128-row tile)
-            _C.linear_chain([_C.chain_layer(acts[l], model.aug_view(wflat, l), True, acts[l + 1], o, _round_up(i, 8) + 1,
-                                            _C.ACT_RELU if model.relu[l] else _C.ACT_NONE) for l, (i, o) in enumerate(dims)],
-                            B, self.chain_ws); n += 1
         else:
             for l, (i, o) in enumerate(dims):
-                if updated is not None:
-                    torch.cuda.current_stream().wait_event(updated[l])
-                    _C.weights_written(self.dev)        # full dependency: no weight-tile prefetch ahead of that wait
                 _C.linear_fwd(acts[l], model.aug_view(wflat, l), None, acts[l + 1], B, o, _round_up(i, 8) + 1,
                               _C.ACT_RELU if model.relu[l] else _C.ACT_NONE, eng); n += 1
-            if updated is not None:
-                torch.cuda.current_stream().wait_stream(self._update_stream)  # join (every event above has fired by now)
         y = acts[L]
         o_last = dims[L - 1][1]
         gbuf = [b["g0"], b["g1"], b["g2"]]            # dL/d(output of layer l) lives in gbuf[l % 3]
-        chain_bwd = train and self.chain_backward and B <= 128
-        g = (b["gchain"][L - 1] if chain_bwd else gbuf[(L - 1) % 3])[:, :_round_up(o_last, 8)]
+        g = gbuf[(L - 1) % 3][:, :_round_up(o_last, 8)]
         if self.mixed is None:
             _C.mse_loss_fwd_bwd(data, idx, y, b["mask_id"], bits, col_var, B, self.io, 2.0 / (global_batch * self.io),
                                 g if train else None, self.acc, self.loss_ws); n += 1
         else:
             pos, size, typ = self.var_tables
-            gm = g if g.dtype == torch.float32 else torch.empty_like(y)
-            _C.mixed_loss_fwd_bwd(b["x"], y, pos, size, typ, self.weight, gm, self.mixed_loss); n += 1
+            _C.mixed_loss_fwd_bwd(b["x"], y, pos, size, typ, self.weight, g, self.mixed_loss); n += 1
             _C.mixed_monitor(b["x"], y, pos, size, typ, self.norm_scale, self.norm_min, self.norm_first, b["mask_id"], bits,
                              nmiss, self.corrupter.k_max, b["mon"], self.mixed_acc); n += 1
         if not train:
             return n
-        if chain_bwd:
-            return n + self._enqueue_chain_backward(B, b)
         if tiny:
             # every weight gradient and the input-gradient chain in one single-CTA launch, then the update
             _C.tiny_mlp_bwd(self._tiny_layers, model.flat, self.gflat, acts, gbuf, B); n += 1
-            if not self.deferred_update:
-                n += self._enqueue_update(b.get("sq_partials"))
-            return n
+            return n + self._enqueue_update(b.get("sq_partials"))
         # Backward.  The input-gradient chain dgrad(L-1) -> ... -> dgrad(1) is the critical path; every weight gradient
         # only needs dL/d(out_l) and the stored activation, so wgrad(l) runs on a second stream next to dgrad(l)
         # (at B=128 each of these kernels is a ~8 us latency chain that leaves most of the GPU idle).
-        overlap_comm = self.world_size > 1 and self.overlap_allreduce
+        overlap_comm = self.world_size > 1 and self.overlap_allreduce and self.dp_mode == "nccl"
         if overlap_comm:
             import torch.distributed as dist
         main = torch.cuda.current_stream()
@@ -287,17 +274,12 @@ class FusedStep:
         # kernels fill the GPU and only slow each other down (measured 7.1 vs 5.4 ms/step)
         # (two side streams were measured no better than one; at large batch both contractions fill the GPU and
         # concurrency only disturbs L2 locality, so the second stream is a small-batch device)
-        sides = [self._wgrad_stream] if (eng == _C.BF16 and B <= 1024) else [main]
+        side = self._wgrad_stream if (eng == _C.BF16 and B <= 1024) else main
         wdone = [None] * L
         bucket_hi = None
-        layerwise = self.layerwise_adam
-        pb = model.flat_bf16 if eng == _C.BF16 else None
-        if layerwise:
-            _C.counter_add(self.step_dev, 1); n += 1    # before the first per-layer update reads it
         for l in range(L - 1, -1, -1):
             i, o = dims[l]
             gl = gbuf[l % 3][:, :_round_up(o, 8)]
-            side = sides[l % len(sides)]                # weight gradients are mutually independent: alternate streams
             if side is not main:
                 ready = torch.cuda.Event()
                 ready.record(main)                      # dL/d(out_l) has been produced (loss or dgrad(l+1))
@@ -325,71 +307,18 @@ class FusedStep:
                         dist.all_reduce(self.gflat[lo:bucket_hi], op=dist.ReduceOp.SUM, group=self.pg)
                     bucket_hi = None
             if l > 0:
-                if l + 2 <= L - 1 and sides[0] is not main:
+                if l + 2 <= L - 1 and side is not main:
                     main.wait_event(wdone[l + 2])       # dgrad(l) overwrites the buffer wgrad(l+2) was reading
                 gp = gbuf[(l - 1) % 3][:, :_round_up(i, 8)]
                 _C.linear_dgrad(gl, model.weight_view(wflat, l), acts[l] if model.relu[l - 1] else None, gp, B, o, i, eng); n += 1
-            if layerwise:
-                # layer l's weights may change once BOTH its weight gradient (side stream order) and dgrad(l), which reads
-                # them, are done: the update runs on the weight-gradient stream beside the rest of the input-gradient chain
-                if side is not main:
-                    dg_done = torch.cuda.Event()
-                    dg_done.record(main)
-                    side.wait_event(dg_done)
-                lo, hi = self._layer_span[l]
-                with torch.cuda.stream(side):
-                    _C.adam_step(model.flat[lo:hi], self.gflat[lo:hi], self.m[lo:hi], self.v[lo:hi],
-                                 None if pb is None else pb[lo:hi], self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0,
-                                 -1.0, None, 1.0, self.step_dev); n += 1
-        for side in sides:
-            if side is not main:
-                main.wait_stream(side)
-        if layerwise and sides[0] is not main:
-            _C.weights_written(self.dev)       # the per-layer updates ran on the side stream: full dependency for the next launch
+        if side is not main:
+            main.wait_stream(side)
         if overlap_comm:
             main.wait_stream(self._comm_stream)
-        elif self.world_size > 1:
+        elif self.world_size > 1 and self.dp_mode == "nccl":
             import torch.distributed as dist
             dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
-        if not layerwise and not self.deferred_update:
-            n += self._enqueue_update(b.get("sq_partials"))
-        return n
-
-    def _enqueue_chain_backward(self, B, b):
-        """Backward pass around codae_linear_chain: dgrad(L-1) .. dgrad(1) in ONE persistent launch (every dL/d(out_l) is kept),
-        then the L mutually independent weight gradients spread over three streams, then the update."""
-        model, dims, eng = self.model, self.model.dims, self.eng
-        L = len(dims)
-        acts, gch = b["acts"], b["gchain"]
-        wflat = model.flat_bf16
-        n = 0
-        if L > 1:
-            layers = []
-            for l in range(L - 1, 0, -1):
-                i, o = dims[l]
-                layers.append(_C.chain_layer(gch[l][:, :_round_up(o, 8)], model.weight_view(wflat, l), False,
-                                             gch[l - 1][:, :_round_up(i, 8)], i, o, _C.ACT_NONE,
-                                             acts[l] if model.relu[l - 1] else None))
-            _C.linear_chain(layers, B, self.chain_ws); n += 1
-        main = torch.cuda.current_stream()
-        streams = [main, self._wgrad_stream, self._wgrad_stream2]
-        ready = torch.cuda.Event()
-        ready.record(main)
-        for s in streams[1:]:
-            s.wait_event(ready)
-        for l in range(L - 1, -1, -1):
-            i, o = dims[l]
-            gl = gch[l][:, :_round_up(o, 8)]
-            with torch.cuda.stream(streams[l % 3]):
-                if self.wgrad_sqnorm:
-                    sq = b["sq_partials"][b["sq_off"][l]:b["sq_off"][l + 1]]
-                    _C.linear_wgrad_sq(gl, acts[l], model.aug_view(self.gflat, l), B, o, _round_up(i, 8) + 1, eng, sq)
-                else:
-                    _C.linear_wgrad(gl, acts[l], model.aug_view(self.gflat, l), None, B, o, _round_up(i, 8) + 1, eng)
-                n += 1
-        for s in streams[1:]:
-            main.wait_stream(s)
-        return n if self.deferred_update else n + self._enqueue_update(b.get("sq_partials"))
+        return n + self._enqueue_update(b.get("sq_partials"))
 
     def _enqueue_update(self, sq_partials=None):
         """Step counter + clip + Adam over the flat buffers (after the gradients are final)."""
@@ -397,6 +326,12 @@ class FusedStep:
         n = 0
         _C.counter_add(self.step_dev, 1); n += 1
         pb = model.flat_bf16 if eng == _C.BF16 else None
+        if self.dp_mode == "peer":
+            # gradients of every rank -> this rank's shard: reduce, global clip scale, Adam, new weights to every rank (one kernel)
+            _C.dp_adam_step(self._peers, model.flat, self.m, self.v, eng, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0,
+                            self.max_norm if self.clip else -1.0, self.sqnorm, self.dp_ws, 1.0, self.step_dev); n += 1
+            self._master_stale = eng == _C.BF16
+            return n
         if sq_partials is not None:
             # the weight-gradient launches of this step left sum(dW^2) per CTA: no norm pass, no grid barrier
             _C.adam_step_partials(model.flat, self.gflat, self.m, self.v, pb, self.lr, self.betas[0], self.betas[1], self.eps,
@@ -417,10 +352,10 @@ class FusedStep:
         return n
 
     def _step_without_samples(self):
-        """This rank holds no sample of the (ragged, last) global batch: contribute zero gradients to the all-reduce and
-        apply the same update as every other rank."""
+        """This rank holds no sample of the (ragged, last) global batch: contribute zero gradients to the reduction and
+        take part in the same update as every other rank."""
         self.gflat.zero_()
-        if self.world_size > 1:
+        if self.dp_mode == "nccl":
             import torch.distributed as dist
             if self.overlap_allreduce:      # same bucket boundaries as the ranks that do have samples
                 L, hi = len(self.model.dims), None
@@ -442,7 +377,6 @@ class FusedStep:
         B = int(batch_idx.numel()) if staged is None else int(staged[0].shape[0])
         gb = B * self.world_size if global_batch is None else global_batch
         if B == 0:
-            self.flush()
             self.step_count += 1
             self._step_without_samples()
             return
@@ -454,20 +388,14 @@ class FusedStep:
             data, idx = self.data, b["idx"]
             idx.copy_(batch_idx, non_blocking=True)
         self.step_count += 1
-        pending = None
-        if self.deferred_update:
-            if self._pending is not None and self._pending[0] != B:
-                self.flush()             # the partials buffer belongs to the other batch size: apply that update on its own
-            pending = self._pending
-            self._pending = (B, b.get("sq_partials"))
-        key = (B, run, gb, None if staged is None else (staged[0].data_ptr(), staged[1].data_ptr()), pending is not None)
+        key = (B, run, gb, None if staged is None else (staged[0].data_ptr(), staged[1].data_ptr()))
         if not self.use_graph:
-            self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table, pending=pending)
+            self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table)
             return
         calls = self._calls.get(key, 0)
         self._calls[key] = calls + 1
         if calls == 0:            # first step of this shape runs eagerly (lazy attribute setup, warm caches)
-            self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table, pending=pending)
+            self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table)
             return
         gr = self._graphs.get(key)
         if gr is None:
@@ -476,21 +404,21 @@ class FusedStep:
             self._static = getattr(self, "_static", {})
             self._static[key] = (data, idx, table)
             with torch.cuda.graph(gr):
-                self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table, pending=pending)
+                self.kernel_launches = self._enqueue(B, b, run, gb, data, idx, table)
             self._graphs[key] = gr
         gr.replay()
 
     def flush(self):
-        """deferred_update: apply the update that the last step() left pending (one launch over the flat buffers).  After it
-        the weights, moments and the bf16 shadow are those the reference has after optimizer.step().  No-op otherwise."""
-        if self._pending is not None:
-            self._enqueue_update(self._pending[1])       # partials, or None -> the cooperative / two-kernel norm + update
-            self._pending = None
+        """Makes model.flat (the fp32 master weights) current on this rank.  Single GPU and the NCCL all-reduce schedule: no-op
+        (every replica applies the whole update).  Sharded data-parallel update (dp_mode="peer"): COLLECTIVE -- every rank
+        gathers the other ranks' master-weight shards; call it on all ranks before reading or saving the weights."""
+        if self.dp_mode == "peer" and self._master_stale:
+            self._gather_master()
 
     def evaluate(self, batch_idx, run=0):
         """Validation pass: corruption + forward + monitor sums only (train_dae_on_embedding.py:241-259),
-        without building any autograd state.  Returns the reconstruction [B, io] (device, fp32)."""
-        self.flush()
+        without building any autograd state.  Returns the reconstruction [B, io] (device, fp32).  Reads the weight buffer the
+        GEMMs use, which is complete on every rank after every step (no master-weight gather needed)."""
         B = int(batch_idx.numel())
         b = self._buffers(B)
         b["idx"].copy_(batch_idx, non_blocking=True)

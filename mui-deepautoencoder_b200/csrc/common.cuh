@@ -22,7 +22,7 @@ struct codae_ctx {
     int pdl;             // 1: training-step kernels are launched with programmatic dependent launch (default on)
     int weight_prefetch; // 1: fwd / dgrad GEMMs issue the TMA loads of their WEIGHT tiles before griddepcontrol.wait
     int tma_store;       // 1: single-pass f32 output tiles leave through TMA bulk stores (default on)
-    int tma_store_persistent;  // 1: the persistent kernel's epilogue warps store through per-warp TMA boxes (opt-in, not yet measured)
+    int tma_store_persistent;  // 1: the persistent kernel's epilogue warps store through per-warp TMA boxes (default on)
     int weights_dirty;   // a weight-writing kernel (Adam, clip+Adam, bf16 cast) was the last codae launch on dirty_stream
     cudaStream_t dirty_stream;
     std::mutex mu;

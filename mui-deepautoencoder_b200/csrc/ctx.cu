@@ -85,7 +85,7 @@ int codae_ctx_create(int device, codae_ctx** out) {
     }
     {
         const char* e = getenv("CODAE_TMA_STORE_PERSISTENT");
-        c->tma_store_persistent = e ? (atoi(e) != 0) : 0;
+        c->tma_store_persistent = e ? (atoi(e) != 0) : 1;   // default on: 7.155 -> 6.970 ms/step at 10 x 4096^2, B = 8192
     }
     c->weights_dirty = 0;
     c->dirty_stream = nullptr;

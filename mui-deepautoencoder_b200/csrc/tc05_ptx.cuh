@@ -1,5 +1,5 @@
 // tcgen05 / TMA / mbarrier / cluster PTX wrappers and the shared-memory / instruction descriptors shared by the tensor-core
-// kernels (gemm_tcgen05.cu, gemm_chain.cu).  sm_100a only.
+// kernels (gemm_tcgen05.cu).  sm_100a only.
 #pragma once
 #include <cuda.h>
 

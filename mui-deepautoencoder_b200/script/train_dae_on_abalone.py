@@ -31,6 +31,8 @@ def parse():
     parser.add_argument('--nb_missing', type=int, default=1)
     parser.add_argument('--synthetic', type=int, default=0)
     parser.add_argument('--epochs', type=int, default=None)
+    parser.add_argument('--dtype', type=str, default="fp32", choices=["fp32"],
+                        help="tabular widths (11 x 11 layers) run on the exact-fp32 engine only; the flag exists for symmetry")
     return parser.parse_args()
 
 

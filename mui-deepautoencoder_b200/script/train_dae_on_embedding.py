@@ -32,6 +32,8 @@ def parse():
     parser.add_argument('--synthetic', type=int, default=0)
     parser.add_argument('--graph', action="store_true")
     parser.add_argument('--epochs', type=int, default=None)
+    parser.add_argument('--dtype', type=str, default=None, choices=["fp32", "bf16"],
+                        help="compute engine: fp32 (reference precision) or bf16 tensor cores; overrides MODEL.DTYPE of the config")
     return parser.parse_args()
 
 
@@ -64,7 +66,7 @@ if __name__ == "__main__":
                                           nb_input_layer=config["MODEL"]["NB_INPUT_LAYER"],
                                           nb_output_layer=config["MODEL"]["NB_OUTPUT_LAYER"],
                                           steep_layer_size=config["MODEL"]["STEEP_LAYER_SIZE"])
-    model.set_compute_dtype(config["MODEL"].get("DTYPE", "fp32"))
+    model.set_compute_dtype(args.dtype or config["MODEL"].get("DTYPE", "fp32"))
     model.to(device)
     dataset.to(device)
     corrupter = Corrupter(nb_observation=dataset.nb_observation, arch=dataset.arch, k_max=args.nb_missing, device=device,
@@ -124,7 +126,7 @@ if __name__ == "__main__":
             log.info("VALIDATION PARTIAL ERROR = %7f" % pvl)
             log.info("VALIDATION RANKING ERROR = %7f" % book["rl"][-1])
 
-    trainer.flush()        # a deferred update (CODAE_DEFERRED_UPDATE=1) is applied before the weights are read; no-op otherwise
+    trainer.flush()        # data parallel: collective gather of the sharded fp32 master weights before they are read; no-op on one GPU
     if rank == 0:
         log.info("TRAINING HAS ENDED.")
         d = os.path.join(args.output_path, get_date() + "_train_" + config["DATASET"]["NAME"])

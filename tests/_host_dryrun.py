@@ -71,32 +71,6 @@ for dtype in ("fp32", "bf16"):
         fq.step(torch.arange(8)); fq.step(torch.arange(5)); fq.step(torch.arange(0))
         assert fq._bufs[8]["sq_partials"].numel() == 7 * len(m.dims) and fq.kernel_launches == 2
         fq.step(torch.arange(8)); print("wgrad_sqnorm launches", fq.kernel_launches)
-        fl = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=False, layerwise_adam=True)      # per-layer updates beside the dgrad chain
-        fl.step(torch.arange(8)); print("layerwise launches", fl.kernel_launches)          # 1 + 8 + 1 + counter + 8 wgrad + 7 dgrad + 8 adam
-        assert fl.kernel_launches == 34 and not fl.wgrad_sqnorm
-        fc = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, chain_forward=True)          # forward pass as one chain launch
-        fc.step(torch.arange(8)); print("chain launches", fc.kernel_launches)               # 27 - 8 fwd + 1 chain
-        assert fc.kernel_launches == 20
-        fc.evaluate(torch.arange(4))
-        fd = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, deferred_update=True)         # update pipelined into the next step
-        fd.step(torch.arange(8)); first = fd.kernel_launches                                 # nothing pending: no update launches
-        fd.step(torch.arange(8)); second = fd.kernel_launches                                # counter + 8 per-layer updates first
-        print("deferred launches", first, second)
-        assert first == 25 and second == 25 + 1 + 8 and fd._pending is not None
-        fd.step(torch.arange(5)); assert fd._pending[0] == 5                                 # other batch size: flushed, then pending again
-        fd.evaluate(torch.arange(4)); assert fd._pending is None
-        fd.step(torch.arange(8)); assert fd._pending is not None
-        m.state_dict(); assert fd._pending is None                                           # reading the weights flushes
-        fd.step(torch.arange(8)); m(ds.data[:3]); assert fd._pending is None                 # so does the legacy forward pass
-        fd.flush()
-        m._flush_hook = None
-        fb = FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, chain_forward=True, chain_backward=True)
-        fb.step(torch.arange(8)); print("chain fwd+bwd launches", fb.kernel_launches)       # corrupt, chain, loss, chain, 8 wgrad, counter, adam
-        assert fb.kernel_launches == 14
-        try:
-            FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, layerwise_adam=True); raise AssertionError("layerwise_adam accepted clipping")
-        except RuntimeError:
-            pass
     else:
         try:
             FusedStep(m, cor, ds.data, 1e-3, 1e-4, clip=True, wgrad_sqnorm=True); raise AssertionError("fp32 engine accepted wgrad_sqnorm")

@@ -187,32 +187,27 @@ def clip_adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_nor
     op("clip_adam_step", [pf, g, m, v, step_dev], [pf, m, v, p_bf16, sqnorm_out, ws], writes_weights=True)
 
 
+def dp_adam_step(peers, pf, m, v, w_dtype, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm_out, ws, grad_scale, step_dev=None):
+    # reads every rank's gradients (this rank's buffer stands for all of them), rewrites its own shard in place, writes the
+    # weight buffer of every rank (the local one is PEER_BUFS["w"]) and the local master / moments
+    META["whole"] = True
+    op("dp_adam_step", [PEER_BUFS["g"], pf, m, v, step_dev], [PEER_BUFS["g"], pf, m, v, PEER_BUFS["w"], sqnorm_out, ws], writes_weights=True)
+
+
+PEER_BUFS = {}
+
+
 def cast_bf16(src, dst):
     op("cast_bf16", [src], [dst], writes_weights=True)
 
 
-def chain_layer(A, B, b_kmajor, C, N, K, act=0, mask_src=None):
-    return (A, B, b_kmajor, C, N, K, mask_src)
-
-
-def linear_chain(layers, M, ws):
-    reads, writes = [], [ws]
-    for A, B, bk, C, N, K, mask in layers:
-        reads += [A[:M, :K], B[:N, :K] if bk else B[:K, :N], None if mask is None else mask[:M, :N]]
-        writes.append(C[:M, :N])
-    # the kernel orders its own layers (grid barrier); towards the rest of the step it is ONE node
-    META["layers"] = len(layers)
-    op("linear_chain", reads, writes)
-
-
 for _n in ("corrupt_fwd", "linear_fwd", "linear_dgrad", "linear_wgrad", "linear_wgrad_sq", "mse_loss_fwd_bwd", "counter_add",
-           "grad_sqnorm", "adam_step", "adam_step_partials", "clip_adam_step", "cast_bf16", "chain_layer", "linear_chain"):
+           "grad_sqnorm", "adam_step", "adam_step_partials", "clip_adam_step", "cast_bf16", "dp_adam_step"):
     setattr(_C, _n, globals()[_n])
 _C.linear_engine = lambda device, dtype, M, N, K: 1 if (dtype == 1 and N >= 32 and K >= 32) else 0
 _C.linear_wgrad_sq_slots = lambda device, M, N, K, dtype: 7 if dtype == 1 else 0
 _C.sqnorm_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
 _C.loss_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
-_C.linear_chain_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
 _C.ctx = lambda device=None: ctypes.c_void_p(1)
 _C.weights_written = lambda device: mark_written() if USE_MARKS[0] else None
 
@@ -238,6 +233,50 @@ def _all_reduce(t, op=None, group=None):
 
 
 dist.all_reduce = _all_reduce
+
+
+def _all_gather_into_tensor(out, inp, group=None):
+    globals()["op"]("all_gather", [inp], [out])
+
+
+dist.all_gather_into_tensor = _all_gather_into_tensor
+dist.get_rank = lambda group=None: 0
+dist.barrier = lambda group=None: None
+
+
+class _FakeGroup:
+    WORLD = object()
+
+
+dist.group = _FakeGroup
+import types  # noqa: E402
+
+_symm = types.ModuleType("torch.distributed._symmetric_memory")
+_symm_allocs = []
+
+
+def _symm_empty(n, dtype=None, device=None):
+    t = torch.zeros(n, dtype=dtype)
+    _symm_allocs.append(t)
+    if len(_symm_allocs) % 3 == 1:
+        PEER_BUFS["g"] = t
+    elif len(_symm_allocs) % 3 == 2:
+        PEER_BUFS["w"] = t
+    return t
+
+
+class _Handle:
+    def __init__(self, t):
+        self.buffer_ptrs = [t.data_ptr(), t.data_ptr() + 0]
+
+
+_symm.empty = _symm_empty
+_symm.rendezvous = lambda t, group: _Handle(t)
+sys.modules["torch.distributed._symmetric_memory"] = _symm
+dist._symmetric_memory = _symm
+_C.dp_shard_elems = lambda n, world: ((n + world - 1) // world + 7) // 8 * 8
+_C.dp_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
+_C.dp_peers = lambda world, rank, g, w, s: (world, rank, g, w, s)
 
 from codae.dataset import ConcatenatedEmbeddingDataset  # noqa: E402
 from codae.model import EmbeddingDenoisingAutoencoder  # noqa: E402
@@ -281,8 +320,8 @@ def check(tag):
 # for the embedding.yaml shapes (profiles/r01_bench_embedding_bf16_final.json; per-layer optimizer launches = 1/10 of the
 # one-launch kernel + 1.5 us).  No resource contention, no launch gaps: a lower bound that ranks schedules, not a prediction.
 DUR = {"corrupt_fwd": 2.8, "linear_fwd": 7.2, "linear_dgrad": 7.5, "linear_wgrad": 6.4, "linear_wgrad_sq": 6.9,
-       "mse_loss_fwd_bwd": 5.7, "counter_add": 1.0, "grad_sqnorm": 20.0, "all_reduce": 80.0, "linear_chain": 3.5}
-FULL_UPDATE = {"adam_step": 110.0, "adam_step_partials": 124.0, "clip_adam_step": 138.0}
+       "mse_loss_fwd_bwd": 5.7, "counter_add": 1.0, "grad_sqnorm": 20.0, "all_reduce": 80.0}
+FULL_UPDATE = {"adam_step": 110.0, "adam_step_partials": 124.0, "clip_adam_step": 138.0, "dp_adam_step": 100.0}
 
 
 def critical_path(n_layers, first, last):
@@ -296,8 +335,6 @@ def critical_path(n_layers, first, last):
         elif name in FULL_UPDATE:
             whole = sum(b - a for a, b in nd["writes"][:1]) > 0 and nd.get("whole", False)
             d = FULL_UPDATE[name] if nd.get("whole") else FULL_UPDATE[name] / n_layers + 1.5
-        elif name == "linear_chain":
-            d = DUR["linear_chain"] * nd.get("layers", n_layers)
         else:
             d = DUR.get(name, 1.0)
         start = max([end.get(i, 0.0) for i in nd["preds"] if i >= first] + [0.0])
@@ -347,26 +384,12 @@ bad += scenario("cooperative clip+Adam", wgrad_sqnorm=False,
 bad += scenario("separate norm + Adam kernels", wgrad_sqnorm=False, fused_clip_adam=False)
 bad += scenario("fp32 engine (one stream)", dtype="fp32")
 bad += scenario("un-clipped", clip=False)
-bad += scenario("layer-wise Adam", clip=False, layerwise_adam=True)
-bad += scenario("deferred update", deferred_update=True)
-bad += scenario("deferred update, ragged batch", deferred_update=True, batches=(8, 8, 5, 8))
-bad += scenario("deferred update, norm pass (no partials)", deferred_update=True, wgrad_sqnorm=False)
-bad += scenario("deferred update, fp32 engine", dtype="fp32", deferred_update=True)
-bad += scenario("deferred update, un-clipped", clip=False, deferred_update=True)
-bad += scenario("deferred update, data parallel", world=2, deferred_update=True)
-bad += scenario("chain forward", chain_forward=True)
-bad += scenario("chain forward + backward", chain_forward=True, chain_backward=True)
-bad += scenario("chain + deferred update", chain_forward=True, chain_backward=True, deferred_update=True)
-bad += scenario("chain backward + deferred update", chain_backward=True, deferred_update=True)
-bad += scenario("data parallel, overlapped all-reduce", world=2,
+bad += scenario("data parallel, peer kernel", world=2, dp_mode="peer",
+                expect=[MAIN_DEFAULT + ["counter_add", "dp_adam_step"], ["linear_wgrad"] * 10])
+bad += scenario("data parallel, peer kernel, fp32 engine", world=2, dp_mode="peer", dtype="fp32")
+bad += scenario("data parallel, overlapped all-reduce", world=2, dp_mode="nccl",
                 expect=[MAIN_DEFAULT + ["counter_add", "clip_adam_step"], ["linear_wgrad"] * 10, ["all_reduce"]])
-bad += scenario("data parallel, one all-reduce", world=2, overlap_allreduce=False)
-
-# mutation: without the explicit codae_weights_written marks the deferred schedule lets a weight-tile prefetch overtake the
-# per-layer update it waits for -- the checker must see that
-USE_MARKS[0] = False
-assert scenario("mutation: deferred update without marks", deferred_update=True) > 0
-USE_MARKS[0] = True
+bad += scenario("data parallel, one all-reduce", world=2, dp_mode="nccl", overlap_allreduce=False)
 
 # the checker itself: a schedule with a known race must be flagged
 del NODES[:]

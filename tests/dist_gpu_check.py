@@ -1,7 +1,10 @@
-"""Multi-GPU parity check (run under torchrun, NCCL, one rank per GPU; not collected by pytest).
+"""Multi-GPU parity check (run under torchrun, one rank per GPU; tests/test_gpu_dist.py launches it on 2 GPUs and the
+tools/ scripts on 2 / 4 / 8).
 
-  * data-parallel invariance: G ranks x B/G samples with one all-reduce of the flat gradient buffer == one process on the
-    whole global batch (loss, weights after 2 steps), eagerly and under CUDA-graph capture of the step (NCCL included);
+  * data-parallel invariance: G ranks x B/G samples == one process on the whole global batch (weights after 5 steps incl. a
+    ragged last batch), for BOTH schedules -- dp_mode="peer" (codae_dp_adam_step: reduce-scatter + clip + Adam on the shard +
+    all-gather of the weights in one kernel over NVLink peer memory) and dp_mode="nccl" (bucketed all-reduce) -- eagerly and
+    under CUDA-graph capture of the step; replicas bitwise equal (fp32 master after flush(), and the weight buffer the GEMMs read);
   * sharded catalog: per-rank top-k + all-gather + codae_topk_merge == unsharded top-k (bit-exact indices and scores);
   * mask ids are a function of (seed, observation) only: every rank holds the same table.
 """
@@ -26,18 +29,18 @@ from codae.tool import Corrupter, FusedStep
 from codae.tool.inference import ComplementarityScorer, shard_rows
 
 
-def build(dtype, ws, graph, overlap=True, deferred=False):
+def build(dtype, ws, graph, overlap=True, mode=None, z=None):
     torch.manual_seed(3)
     S, E, N = 3, 128, 1024
     cats = [torch.randn(N, E).abs() for _ in range(S)]
     ds = ConcatenatedEmbeddingDataset.from_tensors(cats)
-    m = EmbeddingDenoisingAutoencoder(S * E, S * E, E, 2, 2, False)
+    m = EmbeddingDenoisingAutoencoder(S * E, z or S * E, E, 2 if z is None else 3, 2 if z is None else 3, False)
     m.set_compute_dtype(dtype)
     m.to(dev)
     ds.to(dev)
     cor = Corrupter(N, ds.arch, 1, dev, seed=77)
     fs = FusedStep(m, cor, ds.data, lr=1e-3, weight_decay=1e-4, clip=True, world_size=ws, use_graph=graph, overlap_allreduce=overlap,
-                   deferred_update=deferred)
+                   dp_mode=mode)
     return ds, m, cor, fs
 
 
@@ -46,57 +49,50 @@ def flat(m):
 
 
 ok = True
-for dtype, graph, tol in [("fp32", False, 1e-5), ("bf16", False, 1e-2), ("bf16", True, 1e-2)]:
-  for overlap in (True, False):
-      GB = 64 * world
-      rng = np.random.RandomState(5)
-      batches = [rng.permutation(1024)[:GB] for _ in range(4)]
-      batches.append(rng.permutation(1024)[:1])      # ragged last global batch: every rank but 0 holds no sample
-      ds, m, cor, fs = build(dtype, world, graph, overlap)
-      tbl32 = cor.device_tables()[0].to(torch.int32)          # NCCL has no int16
-      tables = [torch.empty_like(tbl32) for _ in range(world)]
-      dist.all_gather(tables, tbl32)
-      same_table = all(torch.equal(t, tables[0]) for t in tables)
-      for gidx in batches:
-          local_idx = torch.as_tensor(gidx[rank::world], dtype=torch.int64, device=dev)
-          fs.step(local_idx, global_batch=len(gidx))
-      w_dp = flat(m)
-      gathered = [torch.empty_like(w_dp) for _ in range(world)]
-      dist.all_gather(gathered, w_dp)
-      replicas_equal = all(torch.equal(g, gathered[0]) for g in gathered)       # every rank applied the same update
-      # single-process reference on the whole global batch (same device, world_size=1)
-      ds1, m1, cor1, fs1 = build(dtype, 1, False)
-      for gidx in batches:
-          fs1.step(torch.as_tensor(gidx, dtype=torch.int64, device=dev), global_batch=len(gidx))
-      w_1 = flat(m1)
-      err = float((w_dp - w_1).abs().max() / w_1.abs().max())
-      good = same_table and replicas_equal and err < tol
-      ok &= good
-      if rank == 0:
-          print("DP %s graph=%s overlap=%s: tables_equal=%s replicas_bitwise_equal=%s |w_dp - w_1|/|w| = %.2e (tol %.0e) -> %s"
-                % (dtype, graph, overlap, same_table, replicas_equal, err, tol, "OK" if good else "FAIL"), flush=True)
-      del fs, fs1
-
-# deferred update under data parallelism (opt-in schedule): same weights as the immediate update up to the summation order of
-# the norm (cooperative kernel there, codae_grad_sqnorm here: the clip scale may differ by an fp32 ulp)
-if os.environ.get("CODAE_EXPERIMENTAL") == "1":
-    for graph in (False, True):
-        rng = np.random.RandomState(6)
-        batches = [rng.permutation(1024)[:64 * world] for _ in range(5)]
-        res = {}
-        for deferred in (False, True):
-            ds, m, cor, fs = build("bf16", world, graph, True, deferred)
-            for gidx in batches:
-                fs.step(torch.as_tensor(gidx[rank::world], dtype=torch.int64, device=dev), global_batch=len(gidx))
-            fs.flush()
-            torch.cuda.synchronize()
-            res[deferred] = flat(m)
-            del fs
-        err = float((res[False] - res[True]).abs().max() / res[False].abs().max())
-        good = err < 1e-4
+CASES = [("peer", "fp32", False, 1e-5, None), ("peer", "bf16", False, 1e-2, None), ("peer", "bf16", True, 1e-2, None),
+         ("peer", "bf16", True, 1e-2, 40),              # bottleneck widths (odd layer sizes): shard boundaries inside layers
+         ("nccl", "fp32", False, 1e-5, None), ("nccl", "bf16", True, 1e-2, None)]
+for mode, dtype, graph, tol, z in CASES:
+    for overlap in ((True, False) if mode == "nccl" else (True,)):
+        GB = 64 * world
+        rng = np.random.RandomState(5)
+        batches = [rng.permutation(1024)[:GB] for _ in range(4)]
+        batches.append(rng.permutation(1024)[:1])      # ragged last global batch: every rank but 0 holds no sample
+        ds, m, cor, fs = build(dtype, world, graph, overlap, mode, z)
+        assert fs.dp_mode == mode, (fs.dp_mode, mode)
+        tbl32 = cor.device_tables()[0].to(torch.int32)          # NCCL has no int16
+        tables = [torch.empty_like(tbl32) for _ in range(world)]
+        dist.all_gather(tables, tbl32)
+        same_table = all(torch.equal(t, tables[0]) for t in tables)
+        for gidx in batches:
+            local_idx = torch.as_tensor(gidx[rank::world], dtype=torch.int64, device=dev)
+            fs.step(local_idx, global_batch=len(gidx))
+        fs.flush()                                              # peer mode: gather the fp32 master shards (collective)
+        w_dp = flat(m)
+        gathered = [torch.empty_like(w_dp) for _ in range(world)]
+        dist.all_gather(gathered, w_dp)
+        replicas_equal = all(torch.equal(g, gathered[0]) for g in gathered)       # every rank holds the same weights
+        if m.flat_bf16 is not None and fs.eng == 1:
+            sh = m.flat_bf16.view(torch.int16).to(torch.int32)
+            gs = [torch.empty_like(sh) for _ in range(world)]
+            dist.all_gather(gs, sh)
+            replicas_equal &= all(torch.equal(g, gs[0]) for g in gs)
+            replicas_equal &= bool(torch.equal(m.flat_bf16, m.flat.to(torch.bfloat16)))    # shadow == rounded master
+        shard_moments = mode != "peer" or fs.m.numel() <= (w_dp.numel() + world - 1) // world + 8
+        # single-process reference on the whole global batch (same device, world_size=1)
+        ds1, m1, cor1, fs1 = build(dtype, 1, False, z=z)
+        for gidx in batches:
+            fs1.step(torch.as_tensor(gidx, dtype=torch.int64, device=dev), global_batch=len(gidx))
+        w_1 = flat(m1)
+        err = float((w_dp - w_1).abs().max() / w_1.abs().max())
+        good = same_table and replicas_equal and shard_moments and err < tol
         ok &= good
         if rank == 0:
-            print("DP deferred update graph=%s: |w_deferred - w_immediate|/|w| = %.2e -> %s" % (graph, err, "OK" if good else "FAIL"), flush=True)
+            print("DP mode=%s %s graph=%s overlap=%s z=%s: tables_equal=%s replicas_bitwise_equal=%s shard_moments=%s "
+                  "|w_dp - w_1|/|w| = %.2e (tol %.0e) -> %s"
+                  % (mode, dtype, graph, overlap, z, same_table, replicas_equal, shard_moments, err, tol, "OK" if good else "FAIL"), flush=True)
+        m._flush_hook = None
+        del fs, fs1
 
 # sharded catalog
 torch.manual_seed(9)

@@ -16,7 +16,7 @@ def header_functions():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     out = {}
-    for m in re.finditer(r"\b(?:int|size_t|const char\*)\s+(codae_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+    for m in re.finditer(r"\b(?:int|int64_t|size_t|const char\*)\s+(codae_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
         args = m.group(2).strip()
         n = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
         out[m.group(1)] = n
@@ -83,24 +83,48 @@ def test_product_never_imports_oracle():
                 assert "oracle" not in s.replace("# oracle", ""), os.path.join(d, f)
 
 
-def test_chain_layer_struct_layout_matches_header(tmp_path):
-    """codae._C.ChainLayer / TinyLayer mirror struct codae_chain_layer / codae_tiny_layer: same size and field offsets as the C
-    compiler sees them."""
+def test_tiny_layer_struct_layout_matches_header(tmp_path):
+    """codae._C.TinyLayer mirrors struct codae_tiny_layer: same size and field offsets as the C compiler sees them."""
     import ctypes
     from codae import _C
-    fields = [f[0] for f in _C.ChainLayer._fields_]
     tfields = [f[0] for f in _C.TinyLayer._fields_]
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "codae_b200.h"\nint main(void) {\n'
-                   '  printf("%zu", sizeof(codae_chain_layer));\n' +
-                   "".join('  printf(" %%zu", offsetof(codae_chain_layer, %s));\n' % f for f in fields) +
-                   '  printf(" %d", CODAE_CHAIN_MAX_LAYERS);\n  printf(" %zu", sizeof(codae_tiny_layer));\n' +
+                   '  printf("%zu", sizeof(codae_tiny_layer));\n' +
                    "".join('  printf(" %%zu", offsetof(codae_tiny_layer, %s));\n' % f.rstrip("_") for f in tfields) +
                    '  printf("\\n");\n  return 0;\n}\n')
     exe = tmp_path / "layout"
     r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
-    want = ([ctypes.sizeof(_C.ChainLayer)] + [getattr(_C.ChainLayer, f).offset for f in fields] + [_C.CHAIN_MAX_LAYERS] +
-            [ctypes.sizeof(_C.TinyLayer)] + [getattr(_C.TinyLayer, f).offset for f in tfields])
+    want = [ctypes.sizeof(_C.TinyLayer)] + [getattr(_C.TinyLayer, f).offset for f in tfields]
     assert got == want, (got, want)
+
+
+def test_dp_peers_struct_layout_matches_header(tmp_path):
+    """codae._C.DpPeers mirrors struct codae_dp_peers (the pointer tables of the data-parallel peer kernel)."""
+    import ctypes
+    from codae import _C
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "codae_b200.h"\nint main(void) {\n'
+                   '  printf("%zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(codae_dp_peers), offsetof(codae_dp_peers, world), '
+                   'offsetof(codae_dp_peers, rank), offsetof(codae_dp_peers, grads), offsetof(codae_dp_peers, w_out), '
+                   'offsetof(codae_dp_peers, signals), CODAE_DP_MAX_WORLD, CODAE_DP_SIGNAL_BYTES);\n  return 0;\n}\n')
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
+    P = _C.DpPeers
+    assert got == [ctypes.sizeof(P), P.world.offset, P.rank.offset, P.grads.offset, P.w_out.offset, P.signals.offset,
+                   _C.DP_MAX_WORLD, _C.DP_SIGNAL_BYTES], got
+
+
+def test_dp_shard_arithmetic():
+    """codae_dp_shard_elems: shards are multiples of 8 elements, cover [0, n) and never overlap (host arithmetic, no GPU)."""
+    from codae import _C
+    for n in (0, 8, 64, 792 // 8 * 8, 23_608_320, 167_813_120, 1_000_000 // 8 * 8):
+        for world in (1, 2, 3, 4, 8):
+            S = _C.dp_shard_elems(n, world)
+            assert S % 8 == 0 and S * world >= n and (world == 1 or S * (world - 1) < n + 8 * world)
+            spans = [(min(n, r * S), min(n, (r + 1) * S)) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))

@@ -199,11 +199,15 @@ def test_abalone_fused_and_legacy(name):
         assert rel(mon_c.get_per_k(ml, masks), g["mon_per_k%d" % s]) < 1e-5
 
 
-@pytest.mark.parametrize("cfg,B,dtype,tol", [("embedding", 128, "fp32", 1e-5), ("modanet", 32, "fp32", 1e-5),
-                                             ("modanet", 32, "bf16", 1e-2), ("bottleneck", 64, "fp32", 1e-5)])
-def test_full_size_step_vs_oracle(cfg, B, dtype, tol):
+@pytest.mark.parametrize("cfg,B,dtype,tol,graph", [("embedding", 128, "fp32", 1e-5, False), ("modanet", 32, "fp32", 1e-5, False),
+                                                   ("modanet", 32, "bf16", 1e-2, False), ("bottleneck", 64, "fp32", 1e-5, False),
+                                                   ("embedding", 128, "bf16", 1e-2, False), ("embedding", 128, "bf16", 1e-2, True),
+                                                   ("bottleneck", 64, "bf16", 1e-2, True)])
+def test_full_size_step_vs_oracle(cfg, B, dtype, tol, graph):
     """BASELINE configs at their real layer sizes (10 x 1536^2 / 8 x 1536^2 / the 1067-598-... bottleneck):
-    two fused steps vs the oracle on the same seeded inputs."""
+    fused steps vs the oracle on the same seeded inputs.  ("embedding", 128, "bf16", graph=True) is exactly what bench.py's
+    embedding.yaml block runs: tcgen05 engine, CUDA-graph replay, sum(dW^2) from the weight-gradient epilogue (the first step
+    of a shape runs eagerly, the second is captured and replayed, the third is a pure replay)."""
     from oracle import codae_oracle as O
     from oracle.philox import philox_mask_table
     from codae.dataset import ConcatenatedEmbeddingDataset
@@ -226,12 +230,14 @@ def test_full_size_step_vs_oracle(cfg, B, dtype, tol):
     cor = Corrupter(N, ds.arch, 1, DEV, seed=2024)
     tbl = torch.from_numpy(philox_mask_table(2024, N, 3).astype(np.int64))
     assert torch.equal(tbl, cor.mask_to_use)
-    fs = FusedStep(model, cor, ds.data, lr=lr, weight_decay=wd, clip=clip)
+    fs = FusedStep(model, cor, ds.data, lr=lr, weight_decay=wd, clip=clip, use_graph=graph)
+    if dtype == "bf16":
+        assert fs.eng == 1 and (fs.wgrad_sqnorm or not clip)            # tensor-core engine, norm-free clipped step
     dae = O.OracleDAE(W, b, model.relu, lr, wd, clip)
     bm, nm, _ = O.binary_masks(ds.arch, 1)
     perm = torch.randperm(N)
     init = np.concatenate([t.numpy().ravel() for pair in zip(W, b) for t in pair])
-    for s in range(2):
+    for s in range(3 if graph else 2):
         idx = perm[s * B:(s + 1) * B]
         before = flat_params(model)
         fs.step(idx.to(DEV), run=0)

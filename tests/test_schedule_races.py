@@ -1,5 +1,5 @@
 """CPU: FusedStep's multi-stream schedules are free of data races.  tests/_schedule_check.py replays every schedule (default,
-cooperative, layer-wise Adam, deferred update, chain kernels, data parallel) against fake streams / events that record the
+cooperative, fp32 engine, data parallel) against fake streams / events that record the
 ordering the real ones impose, and checks that every pair of kernel calls touching overlapping bytes (at least one write) is
 ordered by stream order, wait_event or wait_stream -- across three consecutive steps, evaluate() and flush().  The weight-tile
 prefetch that programmatic dependent launches issue ahead of griddepcontrol.wait is modelled as a separate, earlier read.
@@ -14,9 +14,5 @@ def test_every_conflicting_pair_of_launches_is_ordered():
     r = subprocess.run([sys.executable, os.path.join(here, "_schedule_check.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "SCHEDULES OK" in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
     assert "self-test: missing wait_event        2 calls on 2 streams, 1 unordered" in r.stdout      # the checker can see a race
-    # ... and the programmatic-launch hazard: without codae_weights_written the deferred schedule's weight-tile prefetch races
-    # with the per-layer update (the script asserts > 0 races for that mutation before it prints SCHEDULES OK)
-    assert "mutation: deferred update without marks" in r.stdout
-    for tag in ("default (norm-free update)", "deferred update", "chain forward + backward", "layer-wise Adam",
-                "data parallel, overlapped all-reduce"):
+    for tag in ("default (norm-free update)", "cooperative clip+Adam", "data parallel, peer kernel", "data parallel, overlapped all-reduce"):
         assert tag in r.stdout
