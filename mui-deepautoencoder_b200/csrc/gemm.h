@@ -23,6 +23,11 @@ struct Tc05Gemm {
     bool b_is_weight = false;                    // B holds layer weights: its tiles may be fetched ahead of the stream dependency
     double* sq_partial = nullptr;                // f32 outputs: every CTA writes the sum of squares of what it stored into its slot
     int sq_slots = 0;                            // must equal codae_tc05_gemm_ctas(ctx, g)
+    // fp32-parity mode (CODAE_F32X3): A and B are THREE bf16 planes each (hi, mid, lo: x = hi + mid + lo to 2^-24), plane p at
+    // base + p * plane_stride elements; six MMAs per k-step (hh | hm, mh | mm, hl, lh) into three TMEM accumulators by
+    // magnitude class, summed in the epilogue.  C is f32 (c_dtype CODAE_F32) or three bf16 planes (c_dtype CODAE_F32X3).
+    int planes = 1;
+    int64_t a_plane_stride = 0, b_plane_stride = 0, c_plane_stride = 0;
 };
 bool codae_tc05_supported(const codae_ctx* ctx, const Tc05Gemm& g);
 int codae_tc05_gemm(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s);
