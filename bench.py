@@ -240,7 +240,7 @@ def train_block(name, dtype, K, Wm, args, env, e2e=True):
     loss_last = fs.last_loss(B)
     out = {"metric": "train samples/s", "value": world * B * K / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": K,
            "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-           "dtype": "f32" if fs_dtype(dtype, model) == "fp32" else "bf16", "data": "synthetic",
+           "dtype": "bf16" if fs_dtype(dtype, model) == "bf16" else "f32", "data": "synthetic",
            "config": workload_config(name, w, dims, world), "engine": engine_name(model), "dp_mode": fs.dp_mode,
            "loss_last_step": loss_last, "clocks": clocks, "gpu_launches": launches, "cuda_graph": not args.no_graph}
 
@@ -419,7 +419,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", type=str, default="polyvore", choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", type=str, default=None, choices=["fp32", "bf16"])
+    ap.add_argument("--dtype", type=str, default=None, choices=["fp32", "bf16", "fp32_simt"],
+                    help="fp32: the reference's precision on tensor cores (bf16 triples); bf16: 1e-2 mode; fp32_simt: FFMA engine (A/B)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-scoring", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip the small-batch configs reported beside the primary workload")
@@ -518,7 +519,8 @@ def main():
 def engine_name(model):
     from codae import _C
     e = model.engine_dtype()
-    return {_C.BF16: "tcgen05 bf16 (fp32 accumulate in TMEM)", _C.F32: "exact-fp32 FFMA"}.get(e, str(e))
+    return {_C.BF16: "tcgen05 bf16 (fp32 accumulate in TMEM)", _C.F32: "exact-fp32 FFMA",
+            _C.F32X3: "tcgen05 fp32-parity (bf16 triples hi/mid/lo, 6 MMAs per k-step, fp32 accumulate in TMEM)"}.get(e, str(e))
 
 
 _TRAFFIC = None
@@ -537,7 +539,7 @@ def measured_traffic(key):
 
 def fs_dtype(dtype, model):
     from codae import _C
-    return "bf16" if model.engine_dtype() == _C.BF16 else "fp32"
+    return {_C.BF16: "bf16", _C.F32X3: "fp32x3"}.get(model.engine_dtype(), "fp32")
 
 
 def profile_step(fs, idx, B, world, name):
@@ -605,12 +607,16 @@ def profile_step(fs, idx, B, world, name):
     io = dims[0][0]
     act = sum(i + o for i, o in dims)
     bf = fs.eng == _C.BF16
-    sw = 2 if bf else 4
+    x3 = fs.eng == _C.F32X3
+    tc = bf or x3
+    # bytes per GEMM operand element in the engine's own format: bf16 2, fp32 4, fp32 as a bf16 triple 6
+    sw = 2 if bf else (6 if x3 else 4)
+    shadow = 2 if bf else (6 if x3 else 0)
     small = B <= 1024      # small batch: a contraction is bound by streaming its weights / writing dW once, not by the tensor pipe
     algo = {  # name: (bound, algorithmic bytes or flops per STEP, unit note)
-        "adam_step": ("hbm", (28 + (2 if bf else 0)) * P),
-        "clip_adam_step": ("hbm", (32 + (2 if bf else 0)) * P),
-        "adam_step_partials": ("hbm", (28 + (2 if bf else 0)) * P),
+        "adam_step": ("hbm", (28 + shadow) * P),
+        "clip_adam_step": ("hbm", (32 + shadow) * P),
+        "adam_step_partials": ("hbm", (28 + shadow) * P),
         "grad_sqnorm": ("hbm", 4 * P),
         "corrupt_fwd": ("hbm", B * io * (4 + sw)),
         "mse_loss_fwd_bwd": ("hbm", B * io * (4 + 4 + sw)),
@@ -619,7 +625,8 @@ def profile_step(fs, idx, B, world, name):
         "linear_wgrad": ("hbm", Wsum * 4 + B * act * sw) if small else ("tensor", 2.0 * B * Wsum),
     }
     algo["linear_wgrad_sq"] = algo["linear_wgrad"]
-    tensor_peak = pk["tensor_sustained"] if bf else pk["tensor_sustained"] / 2
+    # useful flops against the bf16 tensor peak; the fp32-parity engine issues six bf16 MMAs per fp32 product
+    tensor_peak = pk["tensor_sustained"] if bf else (pk["tensor_sustained"] / 6 if x3 else pk["tensor_sustained"] / 2)
     rooflines = {}
     for n, (bound, work) in algo.items():
         if n not in kernels:
@@ -645,16 +652,22 @@ def profile_step(fs, idx, B, world, name):
         peak = pk["hbm"] if bound == "hbm" else tensor_peak
         roof = {"bound": bound, "achieved": ach, "peak": peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s", "frac": ach / peak,
                 "traffic": None, "kernel": ("tc05_gemm_persistent_kernel (fwd + dgrad + wgrad launches)" if not small else
-                                            "tc05_gemm_kernel (fwd + dgrad + wgrad launches)") if bf else "simt_gemm_kernel (fwd + dgrad + wgrad launches)",
+                                            "tc05_gemm_kernel (fwd + dgrad + wgrad launches)") if bf else
+                                           ("tc05_gemm_kernel<BN, 3 planes> (fwd + dgrad + wgrad launches)" if x3 else
+                                            "simt_gemm_kernel (fwd + dgrad + wgrad launches)"),
                 "share_of_step": gemm_ms / step_ms, "peak_source": pk["src"], "algorithmic_per_launch": work / launches,
                 "note": "B <= 1024: bound by streaming the weights once per contraction (weights + activations bytes), not by the "
                         "tensor pipe; latency-bound in practice, see DESIGN.md section 7" if small else
-                        "dense bf16 contraction vs the sustained cuBLAS bf16 peak"}
+                        ("useful fp32 flops vs 1/6 of the sustained cuBLAS bf16 peak (six bf16 MMAs per fp32 product)" if x3 else
+                         "dense bf16 contraction vs the sustained cuBLAS bf16 peak")}
+        if x3 and bound == "hbm":
+            # the same time against the fp32 information content (4 B per weight / activation element instead of the triple's 6)
+            roof["frac_at_fp32_bytes"] = roof["frac"] * 4.0 / 6.0
     else:
         roof = rooflines[top_other]
     # DRAM traffic per launch of the dominant kernel from this round's committed `ncu --set full` capture (profiles/r02_traffic.json)
-    roof["traffic"] = measured_traffic("%s_%s_%s" % (name, "bf16" if bf else "fp32", "gemm" if "gemm" in roof.get("kernel", "") else roof.get("kernel", "")))
-    hbm_bytes = 32 * P + B * 20 * io
+    roof["traffic"] = measured_traffic("%s_%s_%s" % (name, "bf16" if bf else ("fp32x3" if x3 else "fp32"), "gemm" if "gemm" in roof.get("kernel", "") else roof.get("kernel", "")))
+    hbm_bytes = (32 + (4 if x3 else 0)) * P + B * 20 * io
     if small:
         floor_bytes = hbm_bytes + 3 * Wsum * sw
         floor = {"bound": "hbm", "hbm_bytes_per_step": floor_bytes, "ms": floor_bytes / (pk["hbm"] * 1e9) * 1e3, "sum_of_kernel_ms": step_ms}

@@ -33,12 +33,14 @@ extern "C" {
 typedef struct codae_ctx codae_ctx;
 
 enum codae_status { CODAE_OK = 0, CODAE_EINVAL = -1, CODAE_EARCH = -2, CODAE_ECUDA = -3, CODAE_ENOMEM = -4 };
-enum codae_dtype { CODAE_F32 = 0, CODAE_BF16 = 1 };
+/* CODAE_F32X3: an fp32 tensor held as THREE bf16 planes (hi, mid, lo; x = hi + mid + lo to 2^-24 |x|), plane p at
+ * base + p * plane_stride elements.  The operand format of the fp32-parity tensor-core engine (codae_linear_*_x3). */
+enum codae_dtype { CODAE_F32 = 0, CODAE_BF16 = 1, CODAE_F32X3 = 2 };
 enum codae_act { CODAE_ACT_NONE = 0, CODAE_ACT_RELU = 1 };
 enum codae_metric { CODAE_METRIC_SQERR = 0, CODAE_METRIC_COSINE = 1 };
 enum codae_vartype { CODAE_VAR_REGRESSION = 0, CODAE_VAR_CLASSIFICATION = 1 };
 /* GEMM engines (a shape/dtype specialisation chosen by the library, reported for tests/bench) */
-enum codae_engine { CODAE_ENGINE_SIMT_F32 = 0, CODAE_ENGINE_TCGEN05_BF16 = 1 };
+enum codae_engine { CODAE_ENGINE_SIMT_F32 = 0, CODAE_ENGINE_TCGEN05_BF16 = 1, CODAE_ENGINE_TCGEN05_F32X3 = 2 };
 
 /* ---- context ------------------------------------------------------------------------------ */
 int codae_version(void);
@@ -181,6 +183,25 @@ int codae_linear_wgrad_sq_slots(const codae_ctx* ctx, int M, int N, int K, int d
 int codae_linear_wgrad_sq(codae_ctx* ctx, const void* dY, int64_t lddy, const void* X, int64_t ldx, float* dW,
                           int64_t lddw, int M, int N, int K, int dtype, double* sq_partials, int n_slots,
                           void* stream);
+/* The same three contractions at the REFERENCE'S precision (fp32, config/embedding.yaml has no dtype) on the tensor cores:
+ * every operand is a CODAE_F32X3 triple of bf16 planes and each k-step issues six tcgen05 MMAs (hi.hi | hi.mid, mid.hi, mid.mid,
+ * hi.lo, lo.hi) into two fp32 TMEM accumulators that the epilogue adds -- products are exact, accumulation is fp32, the
+ * dropped terms and the representation error are 2^-24: results track torch's fp32 nn.Linear to fp32 rounding (1e-5 gate in
+ * tests/test_gpu_f32x3.py), where the bf16 engine is a 1e-2 mode.  Same shapes / pitches / epilogues as codae_linear_fwd,
+ * _dgrad, _wgrad[_sq]; *_plane = elements between planes (multiple of 8).  out_dtype: CODAE_F32 (the last layer: the loss reads
+ * fp32) or CODAE_F32X3 (the next contraction's operand).  A_prev_hi = plane 0 of this layer's input (x > 0 <=> hi > 0).
+ * sq_partials may be NULL (n_slots ignored); otherwise as codae_linear_wgrad_sq with dtype CODAE_F32X3 for the slot count. */
+int codae_linear_fwd_x3(codae_ctx* ctx, const void* X, int64_t ldx, int64_t x_plane, const void* W, int64_t ldw, int64_t w_plane,
+                        void* Y, int64_t ldy, int64_t y_plane, int M, int N, int K, int act, int out_dtype, void* stream);
+int codae_linear_dgrad_x3(codae_ctx* ctx, const void* dY, int64_t lddy, int64_t dy_plane, const void* W, int64_t ldw,
+                          int64_t w_plane, const void* A_prev_hi, int64_t lda, void* dX, int64_t lddx, int64_t dx_plane, int M,
+                          int N, int K, int out_dtype, void* stream);
+int codae_linear_wgrad_x3(codae_ctx* ctx, const void* dY, int64_t lddy, int64_t dy_plane, const void* X, int64_t ldx,
+                          int64_t x_plane, float* dW, int64_t lddw, int M, int N, int K, double* sq_partials, int n_slots,
+                          void* stream);
+/* f32 -> CODAE_F32X3 planes of n elements (weight shadow of the fp32-parity engine, activation / gradient split of the legacy
+ * autograd path); n and plane_stride multiples of 4. */
+int codae_split_x3(codae_ctx* ctx, const float* src, void* dst, int64_t n, int64_t plane_stride, void* stream);
 /* Tabular widths (abalone: Linear layers of at most 11 x 11): the WHOLE network in one launch, exact fp32 FMA arithmetic.
  * Replaces the per-layer codae_linear_fwd / codae_linear_dgrad / codae_linear_wgrad launches of
  * MixedVariableDenoisingAutoencoder.forward (codae/model/mixed_variable_denoising_autoencoder.py:133-181) and of
@@ -212,17 +233,18 @@ int codae_grad_sqnorm(codae_ctx* ctx, const float* g, int64_t n, float* out_sqno
  * 160-163,215).  g_eff = g * grad_scale * min(1, max_norm / (sqrt(sqnorm)*grad_scale + 1e-6));
  * g_eff += wd*p ; m = lerp(m, g_eff, 1-b1) ; v = b2*v + (1-b2) g_eff^2 ;
  * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
- *   max_norm < 0 or sqnorm == NULL: no clipping.  p_bf16 (or NULL): bf16 shadow of p, rewritten.
+ *   max_norm < 0 or sqnorm == NULL: no clipping.  p_shadow (or NULL): the copy of p the tensor-core GEMMs read, rewritten
+ *   with the update -- shadow_dtype CODAE_BF16: bf16 [n]; CODAE_F32X3: three bf16 planes [3][n] (fp32-parity engine).
  *   Hyper-parameters are doubles: the bias corrections are derived in double like torch's Python code,
  *   then rounded to f32 once.  `step` is 1-based; step_dev (device int32, or NULL) overrides it so that a
  *   captured CUDA graph can advance the step count without new scalar arguments.                       */
-int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
+int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_shadow, int shadow_dtype, int64_t n,
                     double lr, double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
                     const float* sqnorm, double grad_scale, const int32_t* step_dev, void* stream);
 /* codae_grad_sqnorm + codae_adam_step in ONE cooperative launch (grid barrier between the norm and the update): same
  * arithmetic and argument meaning; sqnorm_out (f32[1]) receives sum g^2.  max_norm < 0 computes the norm but does not clip.
  * workspace >= codae_sqnorm_workspace_bytes(). */
-int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr,
+int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_shadow, int shadow_dtype, int64_t n, double lr,
                          double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
                          float* sqnorm_out, void* workspace, size_t ws_bytes, double grad_scale, const int32_t* step_dev,
                          void* stream);
@@ -230,7 +252,7 @@ int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, flo
  * codae_linear_wgrad_sq launches of this step (summed in index order by every CTA: reproducible).  Same arithmetic
  * and argument meaning otherwise; sqnorm_out (f32[1]) receives the sum.  Not for data-parallel runs (the norm must
  * be taken after the gradient all-reduce). */
-int codae_adam_step_partials(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n,
+int codae_adam_step_partials(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_shadow, int shadow_dtype, int64_t n,
                              double lr, double beta1, double beta2, double eps, double weight_decay, int step,
                              double max_norm, const double* sq_partials, int n_partials, float* sqnorm_out,
                              double grad_scale, const int32_t* step_dev, void* stream);

@@ -14,11 +14,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_lib", "libcodae_b200.so")
 
 OK, EINVAL, EARCH, ECUDA, ENOMEM = 0, -1, -2, -3, -4
-F32, BF16 = 0, 1
+F32, BF16, F32X3 = 0, 1, 2     # F32X3: an fp32 tensor as three bf16 planes [3, ...] (hi, mid, lo)
 ACT_NONE, ACT_RELU = 0, 1
 METRIC_SQERR, METRIC_COSINE = 0, 1
 VAR_REGRESSION, VAR_CLASSIFICATION = 0, 1
-ENGINE_SIMT_F32, ENGINE_TCGEN05_BF16 = 0, 1
+ENGINE_SIMT_F32, ENGINE_TCGEN05_BF16, ENGINE_TCGEN05_F32X3 = 0, 1, 2
 
 _c = ctypes
 _vp, _i, _i64, _u64, _f, _d, _sz = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64, _c.c_float, _c.c_double, _c.c_size_t
@@ -47,14 +47,18 @@ SIGNATURES = {
     "codae_linear_wgrad": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _vp]),
     "codae_linear_wgrad_sq_slots": (_i, [_vp, _i, _i, _i, _i]),
     "codae_linear_wgrad_sq": (_i, [_vp, _vp, _i64, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp, _i, _vp]),
+    "codae_linear_fwd_x3": (_i, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _i, _vp]),
+    "codae_linear_dgrad_x3": (_i, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp]),
+    "codae_linear_wgrad_x3": (_i, [_vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _i, _i, _i, _vp, _i, _vp]),
+    "codae_split_x3": (_i, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "codae_tiny_mlp_fwd": (_i, [_vp, _vp, _i, _vp, _vp, _i64, _i, _vp]),
     "codae_tiny_mlp_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i64, _vp, _i64, _i, _vp]),
     "codae_cast_bf16": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "codae_sqnorm_workspace_bytes": (_sz, [_vp]),
     "codae_grad_sqnorm": (_i, [_vp, _vp, _i64, _vp, _vp, _sz, _vp]),
-    "codae_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _d, _vp, _vp]),
-    "codae_clip_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _vp, _sz, _d, _vp, _vp]),
-    "codae_adam_step_partials": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _i, _vp, _d, _vp, _vp]),
+    "codae_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _d, _vp, _vp]),
+    "codae_clip_adam_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _vp, _sz, _d, _vp, _vp]),
+    "codae_adam_step_partials": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i64, _d, _d, _d, _d, _d, _i, _d, _vp, _i, _vp, _d, _vp, _vp]),
     "codae_counter_add": (_i, [_vp, _vp, _i, _vp]),
     "codae_dp_workspace_bytes": (_sz, [_vp]),
     "codae_dp_shard_elems": (_i64, [_i64, _i]),
@@ -172,12 +176,40 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def is_x3(t):
+    """A CODAE_F32X3 matrix: three bf16 planes stacked along a leading dimension, [3, rows, pitch] (2-D bf16 tensors are plain
+    bf16 matrices; the flat weight shadow [3, n] only ever goes to the optimizer wrappers)."""
+    return t is not None and t.dtype == torch.bfloat16 and t.dim() == 3 and t.shape[0] == 3
+
+
+def new_x3(shape, device):
+    return torch.zeros((3,) + tuple(shape), dtype=torch.bfloat16, device=device)
+
+
+def x3_to_f32(t):
+    """fp32 value of a CODAE_F32X3 tensor (hi + mid + lo, exact in fp32)."""
+    return (t[0].float() + t[1].float()) + t[2].float()
+
+
 def dt(t):
+    if is_x3(t):
+        return F32X3
     if t.dtype == torch.float32:
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
     raise TypeError("codae: unsupported dtype %s" % t.dtype)
+
+
+def ld(t):
+    """Row pitch in elements (of one plane for CODAE_F32X3)."""
+    return t.stride(1) if is_x3(t) else t.stride(0)
+
+
+def _own_planes(t, B):
+    """CODAE_F32X3 outputs of the elementwise kernels are [3, B, ld] with plane stride B * ld."""
+    if is_x3(t) and t.stride(0) != B * t.stride(1):
+        raise RuntimeError("codae: a CODAE_F32X3 output of this kernel must be a whole [3, B, ld] buffer (plane stride B * ld)")
 
 
 def _dev_check(*ts):
@@ -197,9 +229,10 @@ def mask_table_philox(seed, first_obs, n_obs, nb_run, device):
 
 def corrupt_fwd(data, batch_idx, B, mask_table, run, mask_bits, col_var, io, out_cx, out_x=None, out_mask_id=None):
     _dev_check(data, batch_idx, mask_table, out_cx)
+    _own_planes(out_cx, B)
     c = ctx(data.device)
     check(lib().codae_corrupt_fwd(c, p(data), data.stride(0), p(batch_idx), B, p(mask_table), mask_table.shape[1], run,
-                                  p(mask_bits), p(col_var), io, p(out_cx), dt(out_cx), out_cx.stride(0), p(out_x),
+                                  p(mask_bits), p(col_var), io, p(out_cx), dt(out_cx), ld(out_cx), p(out_x),
                                   0 if out_x is None else out_x.stride(0), p(out_mask_id), stream()), c)
 
 
@@ -223,10 +256,12 @@ def loss_workspace(device):
 
 def mse_loss_fwd_bwd(x, batch_idx, y, mask_id, mask_bits, col_var, B, io, grad_scale, dy, acc, ws):
     _dev_check(x, y, acc, ws)
+    if dy is not None:
+        _own_planes(dy, B)
     c = ctx(x.device)
     check(lib().codae_mse_loss_fwd_bwd(c, p(x), x.stride(0), p(batch_idx), p(y), dt(y), y.stride(0), p(mask_id), p(mask_bits),
                                        p(col_var), B, io, grad_scale, p(dy), F32 if dy is None else dt(dy),
-                                       0 if dy is None else dy.stride(0), p(acc), p(ws), ws.numel(), stream()), c)
+                                       0 if dy is None else ld(dy), p(acc), p(ws), ws.numel(), stream()), c)
 
 
 def mixed_loss_fwd_bwd(x, y, var_pos, var_size, var_type, weight, dy, loss_out):
@@ -249,12 +284,25 @@ def mixed_monitor(x, y, var_pos, var_size, var_type, norm_scale, norm_min, norm_
 
 def linear_fwd(X, W, bias, Y, M, N, K, act, dtype):
     c = ctx(X.device)
+    if dtype == F32X3:
+        assert is_x3(X) and is_x3(W) and bias is None, "codae: the fp32-parity engine contracts CODAE_F32X3 operands (bias = augmented column)"
+        check(lib().codae_linear_fwd_x3(c, p(X), ld(X), X.stride(0), p(W), ld(W), W.stride(0), p(Y), ld(Y),
+                                        Y.stride(0) if is_x3(Y) else 0, M, N, K, act, dt(Y), stream()), c)
+        return
     check(lib().codae_linear_fwd(c, p(X), X.stride(0), p(W), W.stride(0), p(bias), p(Y), Y.stride(0), M, N, K, act, dtype,
                                  dt(Y), stream()), c)
 
 
 def linear_dgrad(dY, W, A_prev, dX, M, N, K, dtype):
     c = ctx(dY.device)
+    if dtype == F32X3:
+        assert is_x3(dY) and is_x3(W)
+        hi = None if A_prev is None else (A_prev[0] if is_x3(A_prev) else A_prev)      # x > 0 <=> its hi plane > 0
+        assert hi is None or hi.dtype == torch.bfloat16
+        check(lib().codae_linear_dgrad_x3(c, p(dY), ld(dY), dY.stride(0), p(W), ld(W), W.stride(0), p(hi),
+                                          0 if hi is None else hi.stride(0), p(dX), ld(dX), dX.stride(0) if is_x3(dX) else 0,
+                                          M, N, K, dt(dX), stream()), c)
+        return
     check(lib().codae_linear_dgrad(c, p(dY), dY.stride(0), p(W), W.stride(0), p(A_prev),
                                    0 if A_prev is None else A_prev.stride(0), p(dX), dX.stride(0), M, N, K, dtype, dt(dX),
                                    stream()), c)
@@ -262,6 +310,11 @@ def linear_dgrad(dY, W, A_prev, dX, M, N, K, dtype):
 
 def linear_wgrad(dY, X, dW, db, M, N, K, dtype):
     c = ctx(dY.device)
+    if dtype == F32X3:
+        assert is_x3(dY) and is_x3(X) and db is None, "codae: the fp32-parity engine takes the bias gradient from the augmented column"
+        check(lib().codae_linear_wgrad_x3(c, p(dY), ld(dY), dY.stride(0), p(X), ld(X), X.stride(0), p(dW), dW.stride(0), M, N, K,
+                                          None, 0, stream()), c)
+        return
     check(lib().codae_linear_wgrad(c, p(dY), dY.stride(0), p(X), X.stride(0), p(dW), dW.stride(0), p(db), M, N, K, dtype,
                                    stream()), c)
 
@@ -272,8 +325,21 @@ def linear_wgrad_sq_slots(device, M, N, K, dtype):
 
 def linear_wgrad_sq(dY, X, dW, M, N, K, dtype, sq_partials):
     c = ctx(dY.device)
+    if dtype == F32X3:
+        assert is_x3(dY) and is_x3(X)
+        check(lib().codae_linear_wgrad_x3(c, p(dY), ld(dY), dY.stride(0), p(X), ld(X), X.stride(0), p(dW), dW.stride(0), M, N, K,
+                                          p(sq_partials), sq_partials.numel(), stream()), c)
+        return
     check(lib().codae_linear_wgrad_sq(c, p(dY), dY.stride(0), p(X), X.stride(0), p(dW), dW.stride(0), M, N, K, dtype,
                                       p(sq_partials), sq_partials.numel(), stream()), c)
+
+
+def split_x3(src, dst):
+    """fp32 (contiguous, numel % 4 == 0) -> CODAE_F32X3 planes dst [3, ...] of the same per-plane shape."""
+    assert dst.dtype == torch.bfloat16 and dst.shape[0] == 3 and src.dtype == torch.float32
+    assert src.is_contiguous() and dst[0].is_contiguous() and dst[0].numel() == src.numel()
+    c = ctx(src.device)
+    check(lib().codae_split_x3(c, p(src), p(dst), src.numel(), dst.stride(0), stream()), c)
 
 
 def dp_shard_elems(n, world):
@@ -338,22 +404,33 @@ def grad_sqnorm(g, out, ws):
     check(lib().codae_grad_sqnorm(c, p(g), g.numel(), p(out), p(ws), ws.numel(), stream()), c)
 
 
-def adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm, grad_scale, step_dev=None):
+def _shadow_dt(shadow, pf):
+    """Weight copy the GEMMs read: None, bf16 [n], or CODAE_F32X3 planes [3, n] (contiguous)."""
+    if shadow is None:
+        return BF16
+    if shadow.dim() == 2:
+        assert shadow.dtype == torch.bfloat16 and shadow.shape == (3, pf.numel()) and shadow.is_contiguous()
+        return F32X3
+    assert shadow.dtype == torch.bfloat16 and shadow.numel() == pf.numel()
+    return BF16
+
+
+def adam_step(pf, g, m, v, shadow, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm, grad_scale, step_dev=None):
     c = ctx(pf.device)
-    check(lib().codae_adam_step(c, p(pf), p(g), p(m), p(v), p(p_bf16), pf.numel(), lr, beta1, beta2, eps, wd, step, max_norm,
+    check(lib().codae_adam_step(c, p(pf), p(g), p(m), p(v), p(shadow), _shadow_dt(shadow, pf), pf.numel(), lr, beta1, beta2, eps, wd, step, max_norm,
                                 p(sqnorm), grad_scale, p(step_dev), stream()), c)
 
 
-def clip_adam_step(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm_out, ws, grad_scale, step_dev=None):
+def clip_adam_step(pf, g, m, v, shadow, lr, beta1, beta2, eps, wd, step, max_norm, sqnorm_out, ws, grad_scale, step_dev=None):
     c = ctx(pf.device)
-    check(lib().codae_clip_adam_step(c, p(pf), p(g), p(m), p(v), p(p_bf16), pf.numel(), lr, beta1, beta2, eps, wd, step, max_norm,
+    check(lib().codae_clip_adam_step(c, p(pf), p(g), p(m), p(v), p(shadow), _shadow_dt(shadow, pf), pf.numel(), lr, beta1, beta2, eps, wd, step, max_norm,
                                      p(sqnorm_out), p(ws), ws.numel(), grad_scale, p(step_dev), stream()), c)
 
 
-def adam_step_partials(pf, g, m, v, p_bf16, lr, beta1, beta2, eps, wd, step, max_norm, sq_partials, sqnorm_out, grad_scale,
+def adam_step_partials(pf, g, m, v, shadow, lr, beta1, beta2, eps, wd, step, max_norm, sq_partials, sqnorm_out, grad_scale,
                        step_dev=None):
     c = ctx(pf.device)
-    check(lib().codae_adam_step_partials(c, p(pf), p(g), p(m), p(v), p(p_bf16), pf.numel(), lr, beta1, beta2, eps, wd, step,
+    check(lib().codae_adam_step_partials(c, p(pf), p(g), p(m), p(v), p(shadow), _shadow_dt(shadow, pf), pf.numel(), lr, beta1, beta2, eps, wd, step,
                                          max_norm, p(sq_partials), sq_partials.numel(), p(sqnorm_out), grad_scale,
                                          p(step_dev), stream()), c)
 

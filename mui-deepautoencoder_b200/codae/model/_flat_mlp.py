@@ -51,6 +51,7 @@ class FlatMLP(torch.nn.Module):
         self.nb_encoder = nb_encoder
         self.flat = None          # fp32 [P_padded] on the CUDA device
         self.flat_bf16 = None     # bf16 shadow (tensor-core engine)
+        self.flat_x3 = None       # [3, P_padded] bf16 planes hi / mid / lo of flat (fp32-parity tensor-core engine)
         self.compute_dtype = "fp32"
         self._layout = None
 
@@ -72,12 +73,17 @@ class FlatMLP(torch.nn.Module):
         return self._layout
 
     def aug_view(self, flat, l):
-        """W'[out, bcol + 1] (pitch ld): the operand the GEMMs contract over (weights, zero pad, bias column)."""
+        """W'[out, bcol + 1] (pitch ld): the operand the GEMMs contract over (weights, zero pad, bias column).  `flat` may be
+        the [3, n] plane shadow of the fp32-parity engine: the view is then [3, out, bcol + 1]."""
         (w_off, ld, bcol), (i, o) = self.layout()[0][l], self.dims[l]
+        if flat.dim() == 2:
+            return flat[:, w_off:w_off + o * ld].view(3, o, ld)[:, :, :bcol + 1]
         return flat[w_off:w_off + o * ld].view(o, ld)[:, :bcol + 1]
 
     def weight_view(self, flat, l):
         (w_off, ld, _), (i, o) = self.layout()[0][l], self.dims[l]
+        if flat.dim() == 2:
+            return flat[:, w_off:w_off + o * ld].view(3, o, ld)[:, :, :i]
         return flat[w_off:w_off + o * ld].view(o, ld)[:, :i]
 
     def bias_view(self, flat, l):
@@ -92,6 +98,12 @@ class FlatMLP(torch.nn.Module):
 
     @staticmethod
     def new_activation(B, w, dtype, device, width=None):
+        """dtype: torch.float32 / torch.bfloat16, or "x3" for the three bf16 planes of the fp32-parity engine ([3, B, pitch];
+        the constant 1 is (1, 0, 0))."""
+        if dtype == "x3":
+            a = _C.new_x3((B, width or FlatMLP.act_width(w)), device)
+            a[0, :, _round_up(w, 8)] = 1
+            return a
         a = torch.zeros((B, width or FlatMLP.act_width(w)), dtype=dtype, device=device)
         a[:, _round_up(w, 8)] = 1
         return a
@@ -120,6 +132,7 @@ class FlatMLP(torch.nn.Module):
             lin.bias.data = self.bias_view(flat, l)
         self.flat = flat
         self.flat_bf16 = None
+        self.flat_x3 = None
 
     def rebind_flat(self, new_flat):
         """Moves the flat fp32 parameter buffer into `new_flat` (same layout; e.g. a symmetric-memory allocation the peers of a
@@ -131,25 +144,47 @@ class FlatMLP(torch.nn.Module):
         self.flat = new_flat
 
     def set_compute_dtype(self, name):
-        """"fp32": exact-fp32 FFMA engine (reference precision).  "bf16": tcgen05 tensor cores with fp32
-        accumulation and fp32 master weights; falls back to nothing -- layers the tensor-core engine cannot
-        tile (tabular widths) make the whole model stay on the fp32 engine, decided here, up front."""
-        if name not in ("fp32", "bf16"):
+        """"fp32" (default, the reference's precision): tcgen05 tensor cores on bf16 triples of the fp32 values (six MMAs per
+        k-step, fp32 accumulation; tracks torch's fp32 nn.Linear to fp32 rounding) for every width the tensor-core path can tile;
+        tabular widths (abalone) run the exact-fp32 FFMA engine.  "bf16": tcgen05 tensor cores on bf16 operands with fp32
+        accumulation and fp32 master weights (1e-2 mode).  "fp32_simt": the FFMA engine regardless of width (A/B and tests).
+        Nothing falls back silently: the engine is decided here, up front, from the layer widths."""
+        if name not in ("fp32", "bf16", "fp32_simt"):
             raise Exception("Unknown compute dtype.")
         self.compute_dtype = name
         return self
 
     def engine_dtype(self):
-        if self.compute_dtype == "bf16" and self.flat is not None:
-            ok = all(_C.linear_engine(self.flat.device, _C.BF16, 128, o, i) == _C.ENGINE_TCGEN05_BF16 for i, o in self.dims)
-            if ok:
-                return _C.BF16
+        """_C.BF16 / _C.F32X3 (tensor cores) or _C.F32 (FFMA)."""
+        if self.flat is not None and self.compute_dtype in ("bf16", "fp32"):
+            want = _C.BF16 if self.compute_dtype == "bf16" else _C.F32X3
+            eng = _C.ENGINE_TCGEN05_BF16 if want == _C.BF16 else _C.ENGINE_TCGEN05_F32X3
+            if all(_C.linear_engine(self.flat.device, want, 128, o, i) == eng for i, o in self.dims):
+                return want
         return _C.F32
 
+    @staticmethod
+    def act_dtype(eng):
+        """Activation buffer type of an engine for new_activation()."""
+        return {_C.BF16: torch.bfloat16, _C.F32X3: "x3"}.get(eng, torch.float32)
+
     def refresh_shadow(self):
-        if self.flat_bf16 is None:
-            self.flat_bf16 = torch.empty(self.flat.numel(), dtype=torch.bfloat16, device=self.flat.device)
-        _C.cast_bf16(self.flat, self.flat_bf16)
+        """Rewrites the copy of the weights the tensor-core GEMMs read from the fp32 master (after a load_state_dict, an
+        external optimizer step, ...); the fused optimizer kernels keep it current by themselves."""
+        eng = self.engine_dtype()
+        if eng == _C.BF16:
+            if self.flat_bf16 is None:
+                self.flat_bf16 = torch.empty(self.flat.numel(), dtype=torch.bfloat16, device=self.flat.device)
+            _C.cast_bf16(self.flat, self.flat_bf16)
+        elif eng == _C.F32X3:
+            if self.flat_x3 is None:
+                self.flat_x3 = torch.empty((3, self.flat.numel()), dtype=torch.bfloat16, device=self.flat.device)
+            _C.split_x3(self.flat, self.flat_x3)
+
+    def gemm_weights(self, eng=None):
+        """The buffer the GEMMs of engine `eng` read: flat (FFMA), flat_bf16 or flat_x3."""
+        eng = self.engine_dtype() if eng is None else eng
+        return {_C.BF16: self.flat_bf16, _C.F32X3: self.flat_x3}.get(eng, self.flat)
 
     def sync_weights(self):
         """A data-parallel trainer with a sharded update (FusedStep, dp_mode="peer") registers its flush() here: every entry
@@ -177,14 +212,18 @@ class FlatMLP(torch.nn.Module):
         eng = self.engine_dtype()
         B = x.shape[0]
         dev = self.flat.device
-        adt = torch.bfloat16 if eng == _C.BF16 else torch.float32
-        wflat = self.flat
-        if eng == _C.BF16:
-            self.refresh_shadow()
-            wflat = self.flat_bf16
+        adt = self.act_dtype(eng)
+        self.refresh_shadow()
+        wflat = self.gemm_weights(eng)
         in_w = self.dims[first][0]
-        a0 = self.new_activation(B, in_w, adt, dev)
-        a0[:, :in_w] = x
+        if eng == _C.F32X3:
+            t = self.new_activation(B, in_w, torch.float32, dev)
+            t[:, :in_w] = x
+            a0 = _C.new_x3(t.shape, dev)
+            _C.split_x3(t, a0)
+        else:
+            a0 = self.new_activation(B, in_w, adt, dev)
+            a0[:, :in_w] = x
         out = [a0]
         for l in range(first, last):
             i, o = self.dims[l]
@@ -199,27 +238,33 @@ class FlatMLP(torch.nn.Module):
         """dW/db of Linear[first:last] into `gflat` (flat layout) and optionally dL/dx."""
         eng = self.engine_dtype()
         dev = self.flat.device
-        adt = torch.bfloat16 if eng == _C.BF16 else torch.float32
-        wflat = self.flat_bf16 if eng == _C.BF16 else self.flat
+        adt = self.act_dtype(eng)
+        wflat = self.gemm_weights(eng)
         B = dy.shape[0]
         o_last = self.dims[last - 1][1]
-        g = torch.zeros((B, _round_up(o_last, 8)), dtype=adt, device=dev)
-        g[:, :o_last] = dy
+        if eng == _C.F32X3:
+            t = torch.zeros((B, _round_up(o_last, 8)), dtype=torch.float32, device=dev)
+            t[:, :o_last] = dy
+            g = _C.new_x3(t.shape, dev)
+            _C.split_x3(t, g)
+        else:
+            g = torch.zeros((B, _round_up(o_last, 8)), dtype=adt, device=dev)
+            g[:, :o_last] = dy
         # the last Linear of a chain may itself be followed by ReLU (encode() alone never is; decode() neither)
         dx = None
         for l in range(last - 1, first - 1, -1):
             i, o = self.dims[l]
             a_in = acts[l - first]
-            if a_in.dtype != adt:
+            if eng != _C.F32X3 and a_in.dtype != adt:
                 a_in = a_in.to(adt)
             _C.linear_wgrad(g, a_in, self.aug_view(gflat, l), None, B, o, _round_up(i, 8) + 1, eng)
             if l > first or need_dx:
-                gp = torch.zeros((B, _round_up(i, 8)), dtype=adt, device=dev)
+                gp = _C.new_x3((B, _round_up(i, 8)), dev) if eng == _C.F32X3 else torch.zeros((B, _round_up(i, 8)), dtype=adt, device=dev)
                 prev_relu = l > 0 and self.relu[l - 1] and l > first
                 _C.linear_dgrad(g, self.weight_view(wflat, l), a_in if prev_relu else None, gp, B, o, i, eng)
                 g = gp
                 if l == first:
-                    dx = gp[:, :i].float()
+                    dx = _C.x3_to_f32(gp)[:, :i] if eng == _C.F32X3 else gp[:, :i].float()
         return dx
 
     def _run(self, x, first, last):

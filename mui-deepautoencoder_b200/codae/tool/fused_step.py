@@ -60,9 +60,10 @@ class FusedStep:
         self.dev = dev
         self.io = model.dims[0][0]
         self.eng = model.engine_dtype()
-        self.adt = torch.bfloat16 if self.eng == _C.BF16 else torch.float32
+        self.adt = model.act_dtype(self.eng)       # torch.float32 / torch.bfloat16 / "x3" (three bf16 planes per fp32 tensor)
+        self.tc = self.eng != _C.F32               # a tensor-core engine (bf16, or fp32 parity on bf16 triples)
         n = model.flat.numel()
-        if self.eng == _C.BF16:
+        if self.tc:
             model.refresh_shadow()
         self.dp_mode = None
         self._master_stale = False
@@ -101,7 +102,7 @@ class FusedStep:
         self._layer_span = [(lay[l][0], lay[l + 1][0] if l + 1 < len(lay) else total) for l in range(len(lay))]
         if wgrad_sqnorm is None:
             # on wherever it applies (embedding.yaml step: 0.3446 -> 0.3367 ms); CODAE_WGRAD_SQNORM=0 switches it off
-            self.wgrad_sqnorm = (os.environ.get("CODAE_WGRAD_SQNORM", "1") != "0" and world_size == 1 and self.eng == _C.BF16
+            self.wgrad_sqnorm = (os.environ.get("CODAE_WGRAD_SQNORM", "1") != "0" and world_size == 1 and self.tc
                                  and fused_clip_adam)
         lay = model.layout()[0]
         tiny_ok = (self.eng == _C.F32 and world_size == 1 and len(model.dims) <= _C.TINY_MAX_LAYERS
@@ -115,7 +116,7 @@ class FusedStep:
         self.tiny_mlp = bool(tiny_mlp)
         self._tiny_layers = [_C.TinyLayer(lay[l][0], lay[l][1], lay[l][2], i, o, 1 if model.relu[l] else 0)
                              for l, (i, o) in enumerate(model.dims)] if self.tiny_mlp else None
-        if self.wgrad_sqnorm and (world_size > 1 or self.eng != _C.BF16):
+        if self.wgrad_sqnorm and (world_size > 1 or not self.tc):
             raise RuntimeError("codae: wgrad_sqnorm needs a single GPU (the norm of a data-parallel run is taken after the "
                                "all-reduce) and the tensor-core engine")
         self._comm_stream = torch.cuda.Stream(device=dev) if world_size > 1 else None
@@ -196,6 +197,11 @@ class FusedStep:
         self._master_stale = False
 
     # ---- buffers ------------------------------------------------------------------------------------
+    def _new_grad(self, B, w):
+        if self.adt == "x3":
+            return _C.new_x3((B, w), self.dev)
+        return torch.zeros((B, w), dtype=self.adt, device=self.dev)
+
     def _buffers(self, B):
         b = self._bufs.get(B)
         if b is None:
@@ -209,8 +215,7 @@ class FusedStep:
                 last = l == len(dims) - 1
                 acts.append(M.new_activation(B, o, torch.float32 if last else adt, dev, width(o)))
             b = dict(acts=acts,
-                     g0=torch.zeros((B, wmax), dtype=adt, device=dev), g1=torch.zeros((B, wmax), dtype=adt, device=dev),
-                     g2=torch.zeros((B, wmax), dtype=adt, device=dev),
+                     g0=self._new_grad(B, wmax), g1=self._new_grad(B, wmax), g2=self._new_grad(B, wmax),
                      mask_id=torch.zeros(B, dtype=torch.int32, device=dev),
                      idx=torch.zeros(B, dtype=torch.int64, device=dev),
                      x=torch.zeros((B, wmax), dtype=torch.float32, device=dev) if self.mixed is not None else None,
@@ -236,7 +241,7 @@ class FusedStep:
         acts = b["acts"]
         n = 0
         _C.corrupt_fwd(data, idx, B, table, run, bits, col_var, self.io, acts[0], b["x"], b["mask_id"]); n += 1
-        wflat = model.flat_bf16 if eng == _C.BF16 else model.flat
+        wflat = model.gemm_weights(eng)
         tiny = self.tiny_mlp and len({a.stride(0) for a in acts}) == 1
         if tiny:
             # tabular widths: every layer of the forward pass in one launch (rows are independent: one CTA per 32 rows)
@@ -248,7 +253,7 @@ class FusedStep:
         y = acts[L]
         o_last = dims[L - 1][1]
         gbuf = [b["g0"], b["g1"], b["g2"]]            # dL/d(output of layer l) lives in gbuf[l % 3]
-        g = gbuf[(L - 1) % 3][:, :_round_up(o_last, 8)]
+        g = gbuf[(L - 1) % 3][..., :_round_up(o_last, 8)]
         if self.mixed is None:
             _C.mse_loss_fwd_bwd(data, idx, y, b["mask_id"], bits, col_var, B, self.io, 2.0 / (global_batch * self.io),
                                 g if train else None, self.acc, self.loss_ws); n += 1
@@ -274,12 +279,12 @@ class FusedStep:
         # kernels fill the GPU and only slow each other down (measured 7.1 vs 5.4 ms/step)
         # (two side streams were measured no better than one; at large batch both contractions fill the GPU and
         # concurrency only disturbs L2 locality, so the second stream is a small-batch device)
-        side = self._wgrad_stream if (eng == _C.BF16 and B <= 1024) else main
+        side = self._wgrad_stream if (self.tc and B <= 1024) else main
         wdone = [None] * L
         bucket_hi = None
         for l in range(L - 1, -1, -1):
             i, o = dims[l]
-            gl = gbuf[l % 3][:, :_round_up(o, 8)]
+            gl = gbuf[l % 3][..., :_round_up(o, 8)]
             if side is not main:
                 ready = torch.cuda.Event()
                 ready.record(main)                      # dL/d(out_l) has been produced (loss or dgrad(l+1))
@@ -309,7 +314,7 @@ class FusedStep:
             if l > 0:
                 if l + 2 <= L - 1 and side is not main:
                     main.wait_event(wdone[l + 2])       # dgrad(l) overwrites the buffer wgrad(l+2) was reading
-                gp = gbuf[(l - 1) % 3][:, :_round_up(i, 8)]
+                gp = gbuf[(l - 1) % 3][..., :_round_up(i, 8)]
                 _C.linear_dgrad(gl, model.weight_view(wflat, l), acts[l] if model.relu[l - 1] else None, gp, B, o, i, eng); n += 1
         if side is not main:
             main.wait_stream(side)
@@ -325,12 +330,16 @@ class FusedStep:
         model, eng = self.model, self.eng
         n = 0
         _C.counter_add(self.step_dev, 1); n += 1
-        pb = model.flat_bf16 if eng == _C.BF16 else None
+        pb = model.gemm_weights(eng) if self.tc else None       # the copy of the weights the tensor-core GEMMs read
         if self.dp_mode == "peer":
             # gradients of every rank -> this rank's shard: reduce, global clip scale, Adam, new weights to every rank (one kernel)
-            _C.dp_adam_step(self._peers, model.flat, self.m, self.v, eng, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0,
+            wdt = _C.BF16 if eng == _C.BF16 else _C.F32
+            _C.dp_adam_step(self._peers, model.flat, self.m, self.v, wdt, self.lr, self.betas[0], self.betas[1], self.eps, self.wd, 0,
                             self.max_norm if self.clip else -1.0, self.sqnorm, self.dp_ws, 1.0, self.step_dev); n += 1
             self._master_stale = eng == _C.BF16
+            if eng == _C.F32X3:
+                # fp32-parity engine: the peers exchanged fp32 weights (complete when the kernel ends); re-split them locally
+                _C.split_x3(model.flat, model.flat_x3); n += 1
             return n
         if sq_partials is not None:
             # the weight-gradient launches of this step left sum(dW^2) per CTA: no norm pass, no grid barrier

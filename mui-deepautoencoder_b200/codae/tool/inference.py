@@ -108,11 +108,13 @@ class SwapScorer:
         if self._acts is None:
             m, dev = self.model, self.catalog.device
             eng = m.engine_dtype()
-            adt = torch.bfloat16 if eng == _C.BF16 else torch.float32
+            adt = m.act_dtype(eng)
             acts = [m.new_activation(self.chunk, self.io, adt, dev)]
             for l, (i, o) in enumerate(m.dims):
                 acts.append(m.new_activation(self.chunk, o, torch.float32 if l == len(m.dims) - 1 else adt, dev))
-            self._acts = (eng, acts)
+            # fp32-parity engine: the swap rows are built in fp32 and split into the engine's three bf16 planes
+            stage = m.new_activation(self.chunk, self.io, torch.float32, dev) if eng == _C.F32X3 else None
+            self._acts = (eng, acts, stage)
         return self._acts
 
     def topk_local(self, outfit, slot):
@@ -121,11 +123,10 @@ class SwapScorer:
         if not 0 <= slot < self.io // self.E:
             raise Exception("Slot out of range.")
         outfit = outfit.to(torch.float32).contiguous().view(-1)
-        eng, acts = self._buffers()
-        wflat = m.flat
-        if eng == _C.BF16:
-            m.refresh_shadow()
-            wflat = m.flat_bf16
+        m.sync_weights()          # a sharded data-parallel trainer gathers the master weights first (collective)
+        eng, acts, stage = self._buffers()
+        m.refresh_shadow()
+        wflat = m.gemm_weights(eng)
         n = self.catalog.shape[0]
         n_chunks = max(1, (n + self.chunk - 1) // self.chunk)
         ls = torch.full((n_chunks, 1, self.k), float("inf"), dtype=torch.float32, device=dev)
@@ -133,7 +134,11 @@ class SwapScorer:
         for c in range(n_chunks if n else 0):
             first = c * self.chunk
             B = min(self.chunk, n - first)
-            _C.swap_build(outfit, self.catalog, first, B, self.E, slot, self.io, self.inv_scale, acts[0])
+            if stage is None:
+                _C.swap_build(outfit, self.catalog, first, B, self.E, slot, self.io, self.inv_scale, acts[0])
+            else:
+                _C.swap_build(outfit, self.catalog, first, B, self.E, slot, self.io, self.inv_scale, stage)
+                _C.split_x3(stage, acts[0])
             for l, (i, o) in enumerate(m.dims):
                 _C.linear_fwd(acts[l], m.aug_view(wflat, l), None, acts[l + 1], B, o, (i + 7) // 8 * 8 + 1,
                               _C.ACT_RELU if m.relu[l] else _C.ACT_NONE, eng)

@@ -126,6 +126,37 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// CODAE_F32X3 -- three-way bf16 split of an fp32 value: x = hi + mid + lo with |x - (hi + mid + lo)| <= 2^-24 |x| (both
+// residuals are exact in fp32).  The fp32-parity tensor-core engine (gemm_tcgen05.cu, NP = 3) contracts such triples.
+__device__ __forceinline__ void split3(float x, float& h, float& m, float& l) {
+    h = __bfloat162float(__float2bfloat16_rn(x));
+    const float r1 = __fsub_rn(x, h);
+    m = __bfloat162float(__float2bfloat16_rn(r1));
+    l = __fsub_rn(r1, m);
+}
+// Four consecutive fp32 values -> the same four columns of the three bf16 planes (8-byte stores; `dst` = plane 0).
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* dst, int64_t plane_stride, float4 x) {
+    float h[4], m[4], l[4];
+    split3(x.x, h[0], m[0], l[0]);
+    split3(x.y, h[1], m[1], l[1]);
+    split3(x.z, h[2], m[2], l[2]);
+    split3(x.w, h[3], m[3], l[3]);
+    uint2 q;
+    q.x = pack_bf16x2(h[0], h[1]); q.y = pack_bf16x2(h[2], h[3]);
+    *reinterpret_cast<uint2*>(dst) = q;
+    q.x = pack_bf16x2(m[0], m[1]); q.y = pack_bf16x2(m[2], m[3]);
+    *reinterpret_cast<uint2*>(dst + plane_stride) = q;
+    q.x = pack_bf16x2(l[0], l[1]); q.y = pack_bf16x2(l[2], l[3]);
+    *reinterpret_cast<uint2*>(dst + 2 * plane_stride) = q;
+}
+__device__ __forceinline__ void store_planes1(__nv_bfloat16* dst, int64_t plane_stride, float x) {
+    float h, m, l;
+    split3(x, h, m, l);
+    dst[0] = __float2bfloat16_rn(h);
+    dst[plane_stride] = __float2bfloat16_rn(m);
+    dst[2 * plane_stride] = __float2bfloat16_rn(l);
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

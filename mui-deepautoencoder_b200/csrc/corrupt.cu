@@ -48,7 +48,8 @@ __device__ __forceinline__ float keep_of(uint64_t bits, uint32_t var) { return (
 // looked up once per row -- and for the NEXT row while the current row's data is in flight -- and every thread keeps
 // four independent 128-bit loads outstanding.
 constexpr int kRowUnroll = 4;
-template <bool kBf16Out>
+// kOut: CODAE_F32 / CODAE_BF16 / CODAE_F32X3 (three bf16 planes B * ld_cx elements apart: the operand of the fp32-parity engine)
+template <int kOut>
 __global__ void __launch_bounds__(256) corrupt_fwd_vec_kernel(const float* __restrict__ data, int64_t ld_data,
                                                               const int64_t* __restrict__ batch_idx, int B,
                                                               const int16_t* __restrict__ mask_table, int nb_run, int run,
@@ -103,7 +104,9 @@ __global__ void __launch_bounds__(256) corrupt_fwd_vec_kernel(const float* __res
                 cx.y = x[j].y * keep_of(bits, var.y);
                 cx.z = x[j].z * keep_of(bits, var.z);
                 cx.w = x[j].w * keep_of(bits, var.w);
-                if (kBf16Out) {
+                if (kOut == CODAE_F32X3) {
+                    store_planes4(reinterpret_cast<__nv_bfloat16*>(out_cx) + (int64_t)row * ld_cx + 4 * c4, (int64_t)B * ld_cx, cx);
+                } else if (kOut == CODAE_BF16) {
                     uint2 p;
                     p.x = pack_bf16x2(cx.x, cx.y);
                     p.y = pack_bf16x2(cx.z, cx.w);
@@ -204,7 +207,7 @@ int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t ld_data, const 
     CODAE_REQUIRE(ctx, B >= 0 && io >= 1, "codae_corrupt_fwd: bad shape B=%d io=%d", B, io);
     CODAE_REQUIRE(ctx, run >= 0 && run < nb_run, "codae_corrupt_fwd: run %d outside [0, %d)", run, nb_run);
     CODAE_REQUIRE(ctx, ld_data >= io && ld_cx >= io && (!out_x || ld_x >= io), "codae_corrupt_fwd: pitch < io");
-    CODAE_REQUIRE(ctx, cx_dtype == CODAE_F32 || cx_dtype == CODAE_BF16, "codae_corrupt_fwd: bad cx_dtype %d", cx_dtype);
+    CODAE_REQUIRE(ctx, cx_dtype == CODAE_F32 || cx_dtype == CODAE_BF16 || cx_dtype == CODAE_F32X3, "codae_corrupt_fwd: bad cx_dtype %d", cx_dtype);
     if (B == 0) return CODAE_OK;
     const bool bf = cx_dtype == CODAE_BF16;
     const bool vec = (io % 4 == 0) && (ld_data % 4 == 0) && (ld_cx % 4 == 0) && (!out_x || ld_x % 4 == 0) &&
@@ -216,16 +219,20 @@ int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t ld_data, const 
         int log2g = 5;
         while (log2g < 8 && (kRowUnroll << log2g) < io / 4) ++log2g;
         const int rows_per_cta = 256 >> log2g;
-        static int occ_bf = 0, occ_f32 = 0;
+        static int occ_bf = 0, occ_f32 = 0, occ_x3 = 0;
         if (!occ_bf) {
-            occ_bf = resident_ctas_per_sm(corrupt_fwd_vec_kernel<true>, 256, 0);
-            occ_f32 = resident_ctas_per_sm(corrupt_fwd_vec_kernel<false>, 256, 0);
+            occ_bf = resident_ctas_per_sm(corrupt_fwd_vec_kernel<CODAE_BF16>, 256, 0);
+            occ_f32 = resident_ctas_per_sm(corrupt_fwd_vec_kernel<CODAE_F32>, 256, 0);
+            occ_x3 = resident_ctas_per_sm(corrupt_fwd_vec_kernel<CODAE_F32X3>, 256, 0);
         }
         int g = (B + rows_per_cta - 1) / rows_per_cta;
-        const int cap = ctx->sm_count * (bf ? occ_bf : occ_f32);
+        const int cap = ctx->sm_count * (bf ? occ_bf : (cx_dtype == CODAE_F32X3 ? occ_x3 : occ_f32));
         if (g > cap) g = cap;
-        if (bf) launch_pdl(ctx, corrupt_fwd_vec_kernel<true>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
-        else launch_pdl(ctx, corrupt_fwd_vec_kernel<false>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        if (bf) launch_pdl(ctx, corrupt_fwd_vec_kernel<CODAE_BF16>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        else if (cx_dtype == CODAE_F32X3) launch_pdl(ctx, corrupt_fwd_vec_kernel<CODAE_F32X3>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        else launch_pdl(ctx, corrupt_fwd_vec_kernel<CODAE_F32>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+    } else if (cx_dtype == CODAE_F32X3) {
+        return codae_fail(ctx, CODAE_EINVAL, "codae_corrupt_fwd: CODAE_F32X3 output needs io and all pitches to be multiples of 4 and 16-byte aligned buffers");
     } else {
         const int g = grid_for(ctx, (int64_t)B * io, 256, 4);
         if (bf) corrupt_fwd_scalar_kernel<true><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io, out_cx, ld_cx, out_x, ld_x, out_mask_id);

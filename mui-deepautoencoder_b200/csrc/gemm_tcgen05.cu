@@ -56,15 +56,37 @@ struct Params {
     int tma_store;               // 1: staged f32 tile leaves through cp.async.bulk.tensor stores (nsplit == 1, plain epilogue)
     double* sq_partial;          // f32 outputs only: slot [linear CTA id] receives the sum of squares of what this CTA stored (or NULL)
     unsigned long long* trace;   // debugging: CTA (0,0,0) writes %globaltimer stamps of its phases here (or NULL)
+    int c_planes;                // NP == 3 only: 1 -> C is three bf16 planes (hi, mid, lo) c_plane_stride elements apart
+    long long c_plane_stride;
 };
 
-template <int BN>
+// NP = operand planes: 1 (bf16 engine) or 3 (fp32-parity engine, CODAE_F32X3: every operand is the bf16 triple hi + mid + lo of
+// an fp32 value; a stage holds [A_hi | A_mid | A_lo | B_hi | B_mid | B_lo]).  Six MMAs per k-step instead of one:
+//     hi.hi                         -> accumulator "big"   (TMEM columns [0, BN))
+//     hi.mid, mid.hi, mid.mid, hi.lo, lo.hi -> accumulator "small" (TMEM columns [BN, 2 BN)), everything <= 2^-8 of the big terms
+// and the epilogue adds the two.  Dropped terms (mid.lo, lo.mid, lo.lo) are <= 2^-24 of a product, the representation error of
+// the triple is 2^-24: the contraction has fp32-level accuracy (checked against the fp64 product in tests/test_host_logic.py
+// on the same arithmetic in numpy, and on the GPU against the oracle at 1e-5).
+template <int BN, int NP = 1>
 struct Cfg {
+    static_assert(NP == 1 || (NP == 3 && BN <= 128), "three-plane stages of a 256-wide tile do not fit in shared memory");
     static constexpr uint32_t kBTileBytes = BN * BK * 2;
-    static constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
-    static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+    static constexpr uint32_t kStageBytes = NP * (kATileBytes + kBTileBytes);
+    static constexpr int kStages = NP == 3 ? (BN == 128 ? 2 : 3) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t kTmemCols = NP == 3 ? 2 * BN : BN;     // power of two >= 32
 };
+
+// One operand tile per plane: plane pl lands plane_bytes after plane pl - 1.
+template <int NP>
+__device__ __forceinline__ void tma_load_op(const CUtensorMap* map, uint64_t* bar, uint8_t* dst, int c0, int c1, uint32_t plane_bytes) {
+    if constexpr (NP == 1) {
+        tma_load_2d(map, bar, dst, c0, c1);
+    } else {
+#pragma unroll
+        for (int pl = 0; pl < NP; ++pl) tma_load_3d(map, bar, dst + pl * plane_bytes, c0, c1, pl);
+    }
+}
 
 __device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
     if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
@@ -129,7 +151,18 @@ template <int W>
 __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, float (&f)[W]) {
     const bool full = col0 + W <= p.N;
     epilogue_chunk<W>(p, row, col0, f);
-    if (p.c_bf16) {
+    if (p.c_planes) {
+        // fp32-parity engine: the value leaves as its bf16 triple, one 8-byte store per plane and four columns
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < W / 4; ++j)
+                store_planes4(crow + 4 * j, p.c_plane_stride, make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < W; ++j) if (col0 + j < p.N) store_planes1(crow + j, p.c_plane_stride, f[j]);
+        }
+    } else if (p.c_bf16) {
         __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col0;
         if (full) {
 #pragma unroll
@@ -158,11 +191,12 @@ __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, 
     }
 }
 
-template <int BN>
+template <int BN, int NP>
 __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                 const __grid_constant__ CUtensorMap tma_b,
                                                                 const __grid_constant__ CUtensorMap tma_c, const Params p) {
-    using C = Cfg<BN>;
+    using C = Cfg<BN, NP>;
+    constexpr uint32_t kBOff = NP * kATileBytes;      // B planes follow the A planes of a stage
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nstages = p.stages;
@@ -194,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, BN);
+    if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -205,14 +239,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     const int npre = p.prefetch_b ? min(num_kb, nstages) : 0;
     if (warp == 0 && lane == 0) {
         for (int kb = 0; kb < npre; ++kb) {
-            uint8_t* b_dst = smem + kb * C::kStageBytes + kATileBytes;
+            uint8_t* b_dst = smem + kb * C::kStageBytes + kBOff;
             mbar_expect_tx(&full_bar[kb], C::kStageBytes);
             const int k0 = (kb_begin + kb) * BK;
             if (p.b_kmajor) {
-                tma_load_2d(&tma_b, &full_bar[kb], b_dst, k0, n0);
+                tma_load_op<NP>(&tma_b, &full_bar[kb], b_dst, k0, n0, C::kBTileBytes);
             } else {
 #pragma unroll
-                for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tma_b, &full_bar[kb], b_dst + j * 8192, n0 + 64 * j, k0);
+                for (int j = 0; j < BN / 64; ++j) tma_load_op<NP>(&tma_b, &full_bar[kb], b_dst + j * 8192, n0 + 64 * j, k0, C::kBTileBytes);
             }
         }
     }
@@ -228,21 +262,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 const bool b_requested = kb < npre;                                          // first ring pass, before the wait
                 if (!b_requested) mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* a_dst = smem + s * C::kStageBytes;
-                uint8_t* b_dst = a_dst + kATileBytes;
+                uint8_t* b_dst = a_dst + kBOff;
                 if (!b_requested) mbar_expect_tx(&full_bar[s], C::kStageBytes);
                 const int k0 = (kb_begin + kb) * BK;
                 if (p.a_kmajor) {
-                    tma_load_2d(&tma_a, &full_bar[s], a_dst, k0, m0);                       // box {64 k, 128 m}
+                    tma_load_op<NP>(&tma_a, &full_bar[s], a_dst, k0, m0, kATileBytes);              // box {64 k, 128 m}
                 } else {
-                    tma_load_2d(&tma_a, &full_bar[s], a_dst, m0, k0);                       // box {64 m, 64 k} x 2
-                    tma_load_2d(&tma_a, &full_bar[s], a_dst + 8192, m0 + 64, k0);
+                    tma_load_op<NP>(&tma_a, &full_bar[s], a_dst, m0, k0, kATileBytes);              // box {64 m, 64 k} x 2
+                    tma_load_op<NP>(&tma_a, &full_bar[s], a_dst + 8192, m0 + 64, k0, kATileBytes);
                 }
                 if (b_requested) continue;
                 if (p.b_kmajor) {
-                    tma_load_2d(&tma_b, &full_bar[s], b_dst, k0, n0);                       // box {64 k, BN n}
+                    tma_load_op<NP>(&tma_b, &full_bar[s], b_dst, k0, n0, C::kBTileBytes);           // box {64 k, BN n}
                 } else {
 #pragma unroll
-                    for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tma_b, &full_bar[s], b_dst + j * 8192, n0 + 64 * j, k0);
+                    for (int j = 0; j < BN / 64; ++j) tma_load_op<NP>(&tma_b, &full_bar[s], b_dst + j * 8192, n0 + 64 * j, k0, C::kBTileBytes);
                 }
             }
         }
@@ -259,11 +293,26 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 if (kb == 0) trace_stamp(p, 3);                    // first operands landed
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * C::kStageBytes);
-                const uint32_t b_addr = a_addr + kATileBytes;
+                const uint32_t b_addr = a_addr + kBOff;
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {
-                    umma_bf16(tmem_base, make_desc(a_addr + k * a_adv, p.a_kmajor != 0),
-                              make_desc(b_addr + k * b_adv, p.b_kmajor != 0), idesc, (kb | k) != 0);
+                    if constexpr (NP == 1) {
+                        umma_bf16(tmem_base, make_desc(a_addr + k * a_adv, p.a_kmajor != 0),
+                                  make_desc(b_addr + k * b_adv, p.b_kmajor != 0), idesc, (kb | k) != 0);
+                    } else {
+                        const bool ak = p.a_kmajor != 0, bk = p.b_kmajor != 0;
+                        const uint64_t ah = make_desc(a_addr + k * a_adv, ak), am = make_desc(a_addr + kATileBytes + k * a_adv, ak),
+                                       al = make_desc(a_addr + 2 * kATileBytes + k * a_adv, ak);
+                        const uint64_t bh = make_desc(b_addr + k * b_adv, bk), bm = make_desc(b_addr + C::kBTileBytes + k * b_adv, bk),
+                                       bl = make_desc(b_addr + 2 * C::kBTileBytes + k * b_adv, bk);
+                        const uint32_t first = (kb | k) != 0;
+                        umma_bf16(tmem_base, ah, bh, idesc, first);                 // big
+                        umma_bf16(tmem_base + BN, ah, bm, idesc, first);            // small: five terms <= 2^-8 of the big one
+                        umma_bf16(tmem_base + BN, am, bh, idesc, 1);
+                        umma_bf16(tmem_base + BN, am, bm, idesc, 1);
+                        umma_bf16(tmem_base + BN, ah, bl, idesc, 1);
+                        umma_bf16(tmem_base + BN, al, bh, idesc, 1);
+                    }
                 }
                 umma_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
             }
@@ -283,6 +332,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         for (int c = 0; c < BN / 32; ++c) {
             uint32_t v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+            if constexpr (NP == 3) {
+                uint32_t u[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
             const int col0 = n0 + c * 32;
             if (!p.staged) {
                 if (!row_ok || col0 >= p.N) continue;
@@ -408,7 +463,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                     }
                 }
                 if (p.sq_partial) sq_acc += (double)chunk_sq<4>(f, col, p.N);
-                if (p.c_bf16) {
+                if (p.c_planes) {
+                    __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col;
+                    if (full) {
+                        store_planes4(crow, p.c_plane_stride, make_float4(f[0], f[1], f[2], f[3]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) if (col + j < p.N) store_planes1(crow + j, p.c_plane_stride, f[j]);
+                    }
+                } else if (p.c_bf16) {
                     __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(p.C) + (long long)row * p.ldc + col;
                     if (full) {
                         uint2 o;
@@ -440,7 +503,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, BN);
+        tmem_dealloc(tmem_base, C::kTmemCols);
     }
     if (p.trace && threadIdx.x == 0) {          // debugging: slot 10 = exit of CTA (0,0,0), slot 11 = last CTA exit, slot 12 = first entry
         unsigned long long t;
@@ -690,14 +753,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // 2-D bf16 tensor map over a row-major [rows, cols] matrix with pitch ld (elements); box {box_cols, box_rows}.
+// planes == 3: a 3-D map {cols, rows, plane} over three such matrices plane_stride elements apart, box depth 1.
 int make_map(codae_ctx* ctx, CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_cols,
-             int box_rows) {
-    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
-    const cuuint32_t estr[2] = {1, 1};
+             int box_rows, int planes = 1, long long plane_stride = 0) {
+    const cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = reinterpret_cast<EncodeTiledFn>(ctx->encode_tiled)(
-        map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+        map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, planes == 1 ? 2 : 3, const_cast<void*>(base), dims, strides, box, estr,
         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return codae_fail(ctx, CODAE_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -729,7 +793,7 @@ int make_store_map(codae_ctx* ctx, CUtensorMap* map, void* base, int c_dtype, lo
     return CODAE_OK;
 }
 
-template <int BN>
+template <int BN, int NP = 1>
 Plan make_plan(const codae_ctx* ctx, const Tc05Gemm& g) {
     Plan pl;
     pl.gx = (g.N + BN - 1) / BN;
@@ -752,28 +816,30 @@ Plan make_plan(const codae_ctx* ctx, const Tc05Gemm& g) {
     // staged (coalesced) epilogue: always for split-K; for fp32 outputs only while the grid is at most ~2 waves
     // (measured: the direct epilogue is faster for the 4096-wide weight gradients, 247 vs 261 us)
     pl.staged = nsplit > 1 || (g.c_dtype == CODAE_F32 && tiles <= 2 * ctx->sm_count);
-    pl.persistent = nsplit == 1 && !pl.staged && ctx->persistent && tiles > 2 * ctx->sm_count;
+    pl.persistent = NP == 1 && nsplit == 1 && !pl.staged && ctx->persistent && tiles > 2 * ctx->sm_count;
     pl.ctas = pl.persistent ? ctx->sm_count : tiles * nsplit;
     return pl;
 }
 
-template <int BN>
+template <int BN, int NP = 1>
 int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
-    using C = Cfg<BN>;
-    const Plan pl = make_plan<BN>(ctx, g);
+    using C = Cfg<BN, NP>;
+    const Plan pl = make_plan<BN, NP>(ctx, g);
     if (g.sq_partial && (g.c_dtype != CODAE_F32 || g.sq_slots != pl.ctas))
         return codae_fail(ctx, CODAE_EINVAL, "codae_tc05_gemm: %d sum-of-squares slots passed, this launch writes %d (f32 outputs only)",
                           g.sq_slots, pl.ctas);
     CUtensorMap ma, mb;
     int rc;
     // A(m,k): K-major storage [M rows, K cols]; MN-major storage [K rows, M cols]
-    if (g.a_kmajor) rc = make_map(ctx, &ma, g.A, g.M, g.K, g.lda, BK, BM);
-    else rc = make_map(ctx, &ma, g.A, g.K, g.M, g.lda, 64, BK);
+    if (g.a_kmajor) rc = make_map(ctx, &ma, g.A, g.M, g.K, g.lda, BK, BM, NP, g.a_plane_stride);
+    else rc = make_map(ctx, &ma, g.A, g.K, g.M, g.lda, 64, BK, NP, g.a_plane_stride);
     if (rc) return rc;
-    if (g.b_kmajor) rc = make_map(ctx, &mb, g.B, g.N, g.K, g.ldb, BK, BN);
-    else rc = make_map(ctx, &mb, g.B, g.K, g.N, g.ldb, 64, BK);
+    if (g.b_kmajor) rc = make_map(ctx, &mb, g.B, g.N, g.K, g.ldb, BK, BN, NP, g.b_plane_stride);
+    else rc = make_map(ctx, &mb, g.B, g.K, g.N, g.ldb, 64, BK, NP, g.b_plane_stride);
     if (rc) return rc;
     Params p;
+    p.c_planes = g.c_dtype == CODAE_F32X3 ? 1 : 0;
+    p.c_plane_stride = g.c_plane_stride;
     p.M = g.M; p.N = g.N; p.K = g.K;
     p.a_kmajor = g.a_kmajor; p.b_kmajor = g.b_kmajor;
     p.C = g.C; p.ldc = g.ldc; p.c_bf16 = g.c_dtype == CODAE_BF16;
@@ -795,7 +861,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     p.prefetch_b = (g.b_is_weight && ctx->pdl && ctx->weight_prefetch) ? 1 : 0;
     p.group_m = 16;
-    if (pl.persistent) {
+    if constexpr (NP == 1) if (pl.persistent) {
         static bool pattr_set = false;
         if (!pattr_set) {
             cudaError_t e = cudaFuncSetAttribute(tc05_gemm_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -829,7 +895,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc05_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(tc05_gemm_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
         if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaFuncSetAttribute(smem=%u): %s", C::kSmemBytes, cudaGetErrorString(e));
         attr_set = true;
     }
@@ -863,10 +929,10 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, tc05_gemm_kernel<BN>, ma, mb, mc, p);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, tc05_gemm_kernel<BN, NP>, ma, mb, mc, p);
     if (le != cudaSuccess) {
         cudaGetLastError();
-        return codae_fail(ctx, CODAE_ECUDA, "tc05_gemm_kernel<%d> launch (grid %u x %u x %d, smem %zu): %s", BN, cfg.gridDim.x,
+        return codae_fail(ctx, CODAE_ECUDA, "tc05_gemm_kernel<%d, %d> launch (grid %u x %u x %d, smem %zu): %s", BN, NP, cfg.gridDim.x,
                           cfg.gridDim.y, nsplit, smem_bytes, cudaGetErrorString(le));
     }
     return codae_check_launch(ctx, "tc05_gemm_kernel");
@@ -886,27 +952,36 @@ extern "C" int codae_debug_set_trace(void* device_buf) {
 bool codae_tc05_supported(const codae_ctx* ctx, const Tc05Gemm& g) {
     if (!ctx || !ctx->encode_tiled) return false;
     if (g.M < 1 || g.N < 1 || g.K < 1) return false;
+    if (g.planes != 1 && g.planes != 3) return false;
     // TMA: 16-byte aligned bases and pitches (bf16 -> multiples of 8 elements)
     if (!al16(g.A) || !al16(g.B) || !al16(g.C) || (g.lda % 8) || (g.ldb % 8)) return false;
-    if (g.c_dtype == CODAE_BF16 ? (g.ldc % 8) : (g.ldc % 4)) return false;
+    if (g.c_dtype == CODAE_F32 ? (g.ldc % 4) : (g.ldc % 8)) return false;
     if (g.mask_src && (!al16(g.mask_src) || (g.ldm % 8))) return false;
+    if (g.planes == 3) {
+        if ((g.a_plane_stride % 8) || (g.b_plane_stride % 8) || g.a_plane_stride < 1 || g.b_plane_stride < 1) return false;
+        if (g.c_dtype == CODAE_BF16) return false;                                  // f32 or its bf16 triple
+        if (g.c_dtype == CODAE_F32X3 && ((g.c_plane_stride % 4) || g.c_plane_stride < 1)) return false;
+    } else if (g.c_dtype == CODAE_F32X3) {
+        return false;
+    }
     // tiny problems (abalone 11x11) are not worth a 128-row tensor-core tile
     if (g.N < 32) return false;
     return true;
 }
 
 // Tile width: the widest tile that still yields at least one CTA per SM (small batches want many CTAs streaming the
-// weights), 256-wide for large problems.
+// weights), 256-wide for large problems (bf16 engine only: three-plane stages of a 256-wide tile do not fit).
 static int pick_bn(const codae_ctx* ctx, const Tc05Gemm& g) {
     const long tiles_m = (g.M + BM - 1) / BM;
     const long t256 = tiles_m * ((g.N + 255) / 256), t128 = tiles_m * ((g.N + 127) / 128);
-    if (t256 >= ctx->sm_count && g.N >= 256) return 256;
+    if (g.planes == 1 && t256 >= ctx->sm_count && g.N >= 256) return 256;
     if (t128 >= ctx->sm_count && g.N >= 128) return 128;
     return 64;
 }
 
 int codae_tc05_gemm(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     if (!codae_tc05_supported(ctx, g)) return codae_fail(ctx, CODAE_EINVAL, "codae_tc05_gemm: unsupported shape/alignment");
+    if (g.planes == 3) return pick_bn(ctx, g) == 128 ? launch<128, 3>(ctx, g, s) : launch<64, 3>(ctx, g, s);
     switch (pick_bn(ctx, g)) {
         case 256: return launch<256>(ctx, g, s);
         case 128: return launch<128>(ctx, g, s);
@@ -916,6 +991,7 @@ int codae_tc05_gemm(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
 
 int codae_tc05_gemm_ctas(const codae_ctx* ctx, const Tc05Gemm& g) {
     if (!ctx || !ctx->encode_tiled || g.M < 1 || g.N < 32 || g.K < 1) return 0;
+    if (g.planes == 3) return pick_bn(ctx, g) == 128 ? make_plan<128, 3>(ctx, g).ctas : make_plan<64, 3>(ctx, g).ctas;
     switch (pick_bn(ctx, g)) {
         case 256: return make_plan<256>(ctx, g).ctas;
         case 128: return make_plan<128>(ctx, g).ctas;

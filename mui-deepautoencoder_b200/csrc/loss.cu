@@ -16,7 +16,8 @@ struct LossWs {
 
 __device__ __forceinline__ float keep_of(uint64_t bits, uint32_t var) { return ((bits >> var) & 1ull) ? 0.0f : 1.0f; }
 
-template <bool kBf16Y, bool kBf16Dy, bool kVec>
+// kDy: CODAE_F32 / CODAE_BF16 / CODAE_F32X3 (dL/dy as three bf16 planes B * ld_dy elements apart: fp32-parity engine, kVec only)
+template <bool kBf16Y, int kDy, bool kVec>
 __global__ void __launch_bounds__(kLossThreads) mse_loss_kernel(
     const float* __restrict__ x, int64_t ld_x, const int64_t* __restrict__ batch_idx, const void* __restrict__ y,
     int64_t ld_y, const int32_t* __restrict__ mask_id, const uint64_t* __restrict__ mask_bits,
@@ -78,7 +79,10 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_kernel(
                     s_part += ((1.f - keep_of(bits, var.x)) * q0 + (1.f - keep_of(bits, var.y)) * q1) +
                               ((1.f - keep_of(bits, var.z)) * q2 + (1.f - keep_of(bits, var.w)) * q3);
                     if (dy) {
-                        if (kBf16Dy) {
+                        if (kDy == CODAE_F32X3) {
+                            store_planes4(reinterpret_cast<__nv_bfloat16*>(dy) + (int64_t)row * ld_dy + c, (int64_t)B * ld_dy,
+                                          make_float4(grad_scale * d0, grad_scale * d1, grad_scale * d2, grad_scale * d3));
+                        } else if (kDy == CODAE_BF16) {
                             uint2 p;
                             p.x = pack_bf16x2(grad_scale * d0, grad_scale * d1);
                             p.y = pack_bf16x2(grad_scale * d2, grad_scale * d3);
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(kLossThreads) mse_loss_kernel(
             s_full += q;
             s_part += (1.f - keep_of(mask_bits[mask_id[row]], col_var[c])) * q;
             if (dy) {
-                if (kBf16Dy) reinterpret_cast<__nv_bfloat16*>(dy)[(int64_t)row * ld_dy + c] = __float2bfloat16_rn(grad_scale * d);
+                if (kDy == CODAE_BF16) reinterpret_cast<__nv_bfloat16*>(dy)[(int64_t)row * ld_dy + c] = __float2bfloat16_rn(grad_scale * d);
                 else reinterpret_cast<float*>(dy)[(int64_t)row * ld_dy + c] = grad_scale * d;
             }
         }
@@ -297,7 +301,8 @@ int codae_mse_loss_fwd_bwd(codae_ctx* ctx, const float* x, int64_t ld_x, const i
                   "codae_mse_loss_fwd_bwd: bad shape B=%d io=%d", B, io);
     if (ws_bytes < sizeof(LossWs))
         return codae_fail(ctx, CODAE_ENOMEM, "codae_mse_loss_fwd_bwd: workspace %zu < %zu bytes", ws_bytes, sizeof(LossWs));
-    const bool by = y_dtype == CODAE_BF16, bd = dy_dtype == CODAE_BF16;
+    const bool by = y_dtype == CODAE_BF16, bd = dy_dtype == CODAE_BF16 || dy_dtype == CODAE_F32X3;   // bd: 2-byte elements
+    const bool x3 = dy && dy_dtype == CODAE_F32X3;
     const bool vec = (io % 4 == 0) && (ld_x % 4 == 0) && (ld_y % 4 == 0) && (!dy || ld_dy % 4 == 0) && aligned16(x) &&
                      ((reinterpret_cast<uintptr_t>(y) & (by ? 7 : 15)) == 0) &&
                      (!dy || (reinterpret_cast<uintptr_t>(dy) & (bd ? 7 : 15)) == 0) &&
@@ -320,16 +325,20 @@ int codae_mse_loss_fwd_bwd(codae_ctx* ctx, const float* x, int64_t ld_x, const i
         launch_pdl(ctx, mse_loss_kernel<BY, BD, VEC>, dim3((unsigned)blocks), dim3(kLossThreads), 0, s, x, ld_x, batch_idx, y, \
                    ld_y, mask_id, mask_bits, col_var, B, io, log2g, grad_scale, dy, ld_dy, acc, ws);                \
     } while (0)
-    if (vec) {
-        if (by && bd) LAUNCH(true, true, true);
-        else if (by) LAUNCH(true, false, true);
-        else if (bd) LAUNCH(false, true, true);
-        else LAUNCH(false, false, true);
+    if (x3) {
+        if (!vec || by)
+            return codae_fail(ctx, CODAE_EINVAL, "codae_mse_loss_fwd_bwd: CODAE_F32X3 dy needs f32 y, io and all pitches multiples of 4, aligned buffers");
+        LAUNCH(false, CODAE_F32X3, true);
+    } else if (vec) {
+        if (by && bd) LAUNCH(true, CODAE_BF16, true);
+        else if (by) LAUNCH(true, CODAE_F32, true);
+        else if (bd) LAUNCH(false, CODAE_BF16, true);
+        else LAUNCH(false, CODAE_F32, true);
     } else {
-        if (by && bd) LAUNCH(true, true, false);
-        else if (by) LAUNCH(true, false, false);
-        else if (bd) LAUNCH(false, true, false);
-        else LAUNCH(false, false, false);
+        if (by && bd) LAUNCH(true, CODAE_BF16, false);
+        else if (by) LAUNCH(true, CODAE_F32, false);
+        else if (bd) LAUNCH(false, CODAE_BF16, false);
+        else LAUNCH(false, CODAE_F32, false);
     }
 #undef LAUNCH
     return codae_check_launch(ctx, "mse_loss_kernel");

@@ -86,9 +86,26 @@ __device__ __forceinline__ float adam_one(float& p, float g, float& m, float& v,
     return p;
 }
 
+// Weight copy the GEMMs read, rewritten with the update: one bf16 plane (pb_plane == 0, tensor-core engine) or the three
+// planes of the fp32-parity engine (CODAE_F32X3, planes pb_plane elements apart).
+__device__ __forceinline__ void store_shadow4(__nv_bfloat16* pb, int64_t pb_plane, int64_t e, const float4& pv) {
+    if (pb_plane) {
+        store_planes4(pb + 4 * e, pb_plane, pv);
+    } else {
+        uint2 q;
+        q.x = pack_bf16x2(pv.x, pv.y);
+        q.y = pack_bf16x2(pv.z, pv.w);
+        *reinterpret_cast<uint2*>(pb + 4 * e) = q;
+    }
+}
+__device__ __forceinline__ void store_shadow1(__nv_bfloat16* pb, int64_t pb_plane, int64_t i, float pv) {
+    if (pb_plane) store_planes1(pb + i, pb_plane, pv);
+    else pb[i] = __float2bfloat16_rn(pv);
+}
+
 __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                         float* __restrict__ m, float* __restrict__ v,
-                                                        __nv_bfloat16* __restrict__ pb, int64_t n, AdamArgs a,
+                                                        __nv_bfloat16* __restrict__ pb, int64_t pb_plane, int64_t n, AdamArgs a,
                                                         const float* __restrict__ sqnorm,
                                                         const int32_t* __restrict__ step_dev) {
     pdl_launch_dependents();
@@ -118,19 +135,14 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
         *reinterpret_cast<float4*>(p + 4 * e) = pv;
         *reinterpret_cast<float4*>(m + 4 * e) = mv;
         *reinterpret_cast<float4*>(v + 4 * e) = vv;
-        if (pb) {
-            uint2 q;
-            q.x = pack_bf16x2(pv.x, pv.y);
-            q.y = pack_bf16x2(pv.z, pv.w);
-            *reinterpret_cast<uint2*>(pb + 4 * e) = q;
-        }
+        if (pb) store_shadow4(pb, pb_plane, e, pv);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const int64_t i = (n4 << 2) + threadIdx.x;
         float pv = p[i], mv = m[i], vv = v[i];
         adam_one(pv, g[i], mv, vv, a, coef);
         p[i] = pv; m[i] = mv; v[i] = vv;
-        if (pb) pb[i] = __float2bfloat16_rn(pv);
+        if (pb) store_shadow1(pb, pb_plane, i, pv);
     }
 }
 
@@ -139,7 +151,7 @@ __global__ void __launch_bounds__(kThreads) adam_kernel(float* __restrict__ p, c
 // same fixed order, so all CTAs use the same scale and the result is bitwise reproducible.
 __global__ void __launch_bounds__(kThreads) adam_partials_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                                  float* __restrict__ m, float* __restrict__ v,
-                                                                 __nv_bfloat16* __restrict__ pb, int64_t n, AdamArgs a,
+                                                                 __nv_bfloat16* __restrict__ pb, int64_t pb_plane, int64_t n, AdamArgs a,
                                                                  const double* __restrict__ partials, int n_partials,
                                                                  float* __restrict__ sqnorm_out,
                                                                  const int32_t* __restrict__ step_dev) {
@@ -179,19 +191,14 @@ __global__ void __launch_bounds__(kThreads) adam_partials_kernel(float* __restri
         *reinterpret_cast<float4*>(p + 4 * e) = pv;
         *reinterpret_cast<float4*>(m + 4 * e) = mv;
         *reinterpret_cast<float4*>(v + 4 * e) = vv;
-        if (pb) {
-            uint2 q;
-            q.x = pack_bf16x2(pv.x, pv.y);
-            q.y = pack_bf16x2(pv.z, pv.w);
-            *reinterpret_cast<uint2*>(pb + 4 * e) = q;
-        }
+        if (pb) store_shadow4(pb, pb_plane, e, pv);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const int64_t i = (n4 << 2) + threadIdx.x;
         float pv = p[i], mv = m[i], vv = v[i];
         adam_one(pv, g[i], mv, vv, a, coef);
         p[i] = pv; m[i] = mv; v[i] = vv;
-        if (pb) pb[i] = __float2bfloat16_rn(pv);
+        if (pb) store_shadow1(pb, pb_plane, i, pv);
     }
 }
 
@@ -200,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) adam_partials_kernel(float* __restri
 // second read is served by the 126 MB L2 for the shipped configs (94 MB of gradients), and one launch disappears.
 __global__ void __launch_bounds__(kThreads) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                              float* __restrict__ m, float* __restrict__ v,
-                                                             __nv_bfloat16* __restrict__ pb, int64_t n, AdamArgs a,
+                                                             __nv_bfloat16* __restrict__ pb, int64_t pb_plane, int64_t n, AdamArgs a,
                                                              NormWs* __restrict__ ws, float* __restrict__ sqnorm_out,
                                                              const int32_t* __restrict__ step_dev) {
     namespace cg = cooperative_groups;
@@ -259,19 +266,14 @@ __global__ void __launch_bounds__(kThreads) clip_adam_kernel(float* __restrict__
         *reinterpret_cast<float4*>(p + 4 * e) = pv;
         *reinterpret_cast<float4*>(m + 4 * e) = mv;
         *reinterpret_cast<float4*>(v + 4 * e) = vv;
-        if (pb) {
-            uint2 q;
-            q.x = pack_bf16x2(pv.x, pv.y);
-            q.y = pack_bf16x2(pv.z, pv.w);
-            *reinterpret_cast<uint2*>(pb + 4 * e) = q;
-        }
+        if (pb) store_shadow4(pb, pb_plane, e, pv);
     }
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const int64_t i = (n4 << 2) + threadIdx.x;
         float pv = p[i], mv = m[i], vv = v[i];
         adam_one(pv, g[i], mv, vv, a, coef);
         p[i] = pv; m[i] = mv; v[i] = vv;
-        if (pb) pb[i] = __float2bfloat16_rn(pv);
+        if (pb) store_shadow1(pb, pb_plane, i, pv);
     }
 }
 
@@ -289,6 +291,12 @@ __global__ void __launch_bounds__(kThreads) cast_bf16_kernel(const float* __rest
         const int64_t i = (n4 << 2) + threadIdx.x;
         dst[i] = __float2bfloat16_rn(src[i]);
     }
+}
+
+__global__ void __launch_bounds__(kThreads) split_x3_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                                            int64_t n4, int64_t plane) {
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x)
+        store_planes4(dst + 4 * e, plane, ldg_stream_f4(src + 4 * e));
 }
 
 __global__ void counter_add_kernel(int32_t* c, int delta) {
@@ -355,15 +363,18 @@ int codae_grad_sqnorm(codae_ctx* ctx, const float* g, int64_t n, float* out_sqno
     return codae_check_launch(ctx, "sqnorm_kernel");
 }
 
-int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr,
+int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_shadow, int shadow_dtype, int64_t n, double lr,
                     double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
                     const float* sqnorm, double grad_scale, const int32_t* step_dev, void* stream) {
     CODAE_REQUIRE(ctx, ctx && p && g && m && v && n >= 0 && (step >= 1 || step_dev), "codae_adam_step: bad argument");
     if (step < 1) step = 1;
+    CODAE_REQUIRE(ctx, !p_shadow || shadow_dtype == CODAE_BF16 || (shadow_dtype == CODAE_F32X3 && n % 8 == 0),
+                  "weight shadow: CODAE_BF16, or CODAE_F32X3 ([3][n] planes, n a multiple of 8)");
+    const int64_t pb_plane = (p_shadow && shadow_dtype == CODAE_F32X3) ? n : 0;
     CODAE_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_shadow) & 7) == 0,
                   "codae_adam_step: buffers must be 16-byte aligned");
-    CODAE_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(p_bf16) & 15) == 0, "codae_adam_step: p_bf16 must be 16-byte aligned");
+    CODAE_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(p_shadow) & 15) == 0, "codae_adam_step: p_shadow must be 16-byte aligned");
     const AdamArgs a = make_adam_args(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale);
     if (n == 0) return CODAE_OK;
     // one resident wave: 4 CTAs per SM measured best for this access pattern (more CTAs per SM: 156 vs 138 us on 23.6 M
@@ -372,27 +383,30 @@ int codae_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v
     if (grid > ctx->sm_count * 4) grid = ctx->sm_count * 4;
     if (adam_uses_pdl()) {
         launch_pdl(ctx, adam_kernel, dim3(grid), dim3(kThreads), 0, as_stream(stream), p, (const float*)g, m, v,
-                   reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a, sqnorm, step_dev);
+                   reinterpret_cast<__nv_bfloat16*>(p_shadow), pb_plane, n, a, sqnorm, step_dev);
     } else {
-        adam_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(p, (const float*)g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a,
-                                                             sqnorm, step_dev);
+        adam_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(p, (const float*)g, m, v, reinterpret_cast<__nv_bfloat16*>(p_shadow), pb_plane,
+                                                             n, a, sqnorm, step_dev);
     }
     codae_mark_weights_written(ctx, as_stream(stream));
     return codae_check_launch(ctx, "adam_kernel");
 }
 
-int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr,
+int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_shadow, int shadow_dtype, int64_t n, double lr,
                          double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
                          float* sqnorm_out, void* workspace, size_t ws_bytes, double grad_scale, const int32_t* step_dev,
                          void* stream) {
     CODAE_REQUIRE(ctx, ctx && p && g && m && v && sqnorm_out && workspace && n >= 0 && (step >= 1 || step_dev),
                   "codae_clip_adam_step: bad argument");
     CODAE_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_bf16) & 7) == 0,
+                         reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(p_shadow) & 7) == 0,
                   "codae_clip_adam_step: buffers must be 16-byte aligned");
     if (ws_bytes < sizeof(NormWs))
         return codae_fail(ctx, CODAE_ENOMEM, "codae_clip_adam_step: workspace %zu < %zu bytes", ws_bytes, sizeof(NormWs));
     if (step < 1) step = 1;
+    CODAE_REQUIRE(ctx, !p_shadow || shadow_dtype == CODAE_BF16 || (shadow_dtype == CODAE_F32X3 && n % 8 == 0),
+                  "weight shadow: CODAE_BF16, or CODAE_F32X3 ([3][n] planes, n a multiple of 8)");
+    const int64_t pb_plane = (p_shadow && shadow_dtype == CODAE_F32X3) ? n : 0;
     const AdamArgs a = make_adam_args(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale);
     if (n == 0) return CODAE_OK;
     // cooperative launch: the grid must be co-resident
@@ -416,7 +430,7 @@ int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, flo
     attr[0].val.cooperative = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, clip_adam_kernel, p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a,
+    cudaError_t le = cudaLaunchKernelEx(&cfg, clip_adam_kernel, p, g, m, v, reinterpret_cast<__nv_bfloat16*>(p_shadow), pb_plane, n, a,
                                         reinterpret_cast<NormWs*>(workspace), sqnorm_out, step_dev);
     if (le != cudaSuccess) {
         cudaGetLastError();
@@ -426,17 +440,20 @@ int codae_clip_adam_step(codae_ctx* ctx, float* p, const float* g, float* m, flo
     return codae_check_launch(ctx, "clip_adam_kernel");
 }
 
-int codae_adam_step_partials(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_bf16, int64_t n, double lr,
+int codae_adam_step_partials(codae_ctx* ctx, float* p, const float* g, float* m, float* v, void* p_shadow, int shadow_dtype, int64_t n, double lr,
                              double beta1, double beta2, double eps, double weight_decay, int step, double max_norm,
                              const double* sq_partials, int n_partials, float* sqnorm_out, double grad_scale,
                              const int32_t* step_dev, void* stream) {
     CODAE_REQUIRE(ctx, ctx && p && g && m && v && sq_partials && sqnorm_out && n >= 0 && n_partials >= 1 && (step >= 1 || step_dev),
                   "codae_adam_step_partials: bad argument");
     CODAE_REQUIRE(ctx, ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
-                         reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(p_bf16)) & 15) == 0 &&
+                         reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(p_shadow)) & 15) == 0 &&
                             (reinterpret_cast<uintptr_t>(sq_partials) & 7) == 0,
                   "codae_adam_step_partials: buffers must be 16-byte aligned (sq_partials: 8)");
     if (step < 1) step = 1;
+    CODAE_REQUIRE(ctx, !p_shadow || shadow_dtype == CODAE_BF16 || (shadow_dtype == CODAE_F32X3 && n % 8 == 0),
+                  "weight shadow: CODAE_BF16, or CODAE_F32X3 ([3][n] planes, n a multiple of 8)");
+    const int64_t pb_plane = (p_shadow && shadow_dtype == CODAE_F32X3) ? n : 0;
     const AdamArgs a = make_adam_args(lr, beta1, beta2, eps, weight_decay, step, max_norm, grad_scale);
     if (n == 0) return CODAE_OK;
     int grid = grid_for(ctx, n >> 2, 2);
@@ -444,10 +461,10 @@ int codae_adam_step_partials(codae_ctx* ctx, float* p, const float* g, float* m,
     cudaError_t le;
     if (adam_uses_pdl()) {
         le = launch_pdl(ctx, adam_partials_kernel, dim3(grid), dim3(kThreads), 0, as_stream(stream), p, (const float*)g, m, v,
-                        reinterpret_cast<__nv_bfloat16*>(p_bf16), n, a, sq_partials, n_partials, sqnorm_out, step_dev);
+                        reinterpret_cast<__nv_bfloat16*>(p_shadow), pb_plane, n, a, sq_partials, n_partials, sqnorm_out, step_dev);
     } else {
-        adam_partials_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(p, (const float*)g, m, v, reinterpret_cast<__nv_bfloat16*>(p_bf16),
-                                                                      n, a, sq_partials, n_partials, sqnorm_out, step_dev);
+        adam_partials_kernel<<<grid, kThreads, 0, as_stream(stream)>>>(p, (const float*)g, m, v, reinterpret_cast<__nv_bfloat16*>(p_shadow),
+                                                                      pb_plane, n, a, sq_partials, n_partials, sqnorm_out, step_dev);
         le = cudaSuccess;
     }
     if (le != cudaSuccess) {
@@ -472,6 +489,18 @@ int codae_cast_bf16(codae_ctx* ctx, const float* src, void* dst, int64_t n, void
     cast_bf16_kernel<<<grid_for(ctx, n >> 2, 4), kThreads, 0, as_stream(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
     codae_mark_weights_written(ctx, as_stream(stream));
     return codae_check_launch(ctx, "cast_bf16_kernel");
+}
+
+int codae_split_x3(codae_ctx* ctx, const float* src, void* dst, int64_t n, int64_t plane_stride, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && src && dst && n >= 0 && plane_stride >= n, "codae_split_x3: bad argument");
+    CODAE_REQUIRE(ctx, (n % 4) == 0 && (plane_stride % 4) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                           (reinterpret_cast<uintptr_t>(dst) & 7) == 0,
+                  "codae_split_x3: n and plane_stride must be multiples of 4, src 16-byte and dst 8-byte aligned");
+    if (n == 0) return CODAE_OK;
+    split_x3_kernel<<<grid_for(ctx, n >> 2, 4), kThreads, 0, as_stream(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n >> 2,
+                                                                                 plane_stride);
+    codae_mark_weights_written(ctx, as_stream(stream));
+    return codae_check_launch(ctx, "split_x3_kernel");
 }
 
 }  // extern "C"

@@ -31,10 +31,10 @@ def parse():
     parser.add_argument('--k', type=int, default=10)
     parser.add_argument('--metric', type=str, default="sqerr", choices=["sqerr", "cosine"])
     parser.add_argument('--mode', type=str, default="slot", choices=["slot", "swap"])
-    parser.add_argument('--compute_dtype', '--dtype', dest="compute_dtype", type=str, default="fp32", choices=["fp32", "bf16"])
+    parser.add_argument('--compute_dtype', '--dtype', dest="compute_dtype", type=str, default="fp32", choices=["fp32", "bf16", "fp32_simt"])
     parser.add_argument('--queries', type=int, default=4)
     parser.add_argument('--synthetic', type=int, default=0)
-    parser.add_argument('--catalog_dtype', type=str, default="fp32", choices=["fp32", "bf16"])
+    parser.add_argument('--catalog_dtype', type=str, default="fp32", choices=["fp32", "bf16", "fp32_simt"])
     return parser.parse_args()
 
 

@@ -32,7 +32,7 @@ def parse():
     parser.add_argument('--synthetic', type=int, default=0)
     parser.add_argument('--graph', action="store_true")
     parser.add_argument('--epochs', type=int, default=None)
-    parser.add_argument('--dtype', type=str, default=None, choices=["fp32", "bf16"],
+    parser.add_argument('--dtype', type=str, default=None, choices=["fp32", "bf16", "fp32_simt"],
                         help="compute engine: fp32 (reference precision) or bf16 tensor cores; overrides MODEL.DTYPE of the config")
     return parser.parse_args()
 

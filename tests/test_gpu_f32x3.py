@@ -1,0 +1,151 @@
+"""fp32-parity tensor-core engine (CODAE_F32X3): every fp32 operand is the bf16 triple hi + mid + lo, six tcgen05 MMAs per
+k-step, fp32 accumulation in two TMEM accumulators.  The reference's arithmetic is fp32 (config/embedding.yaml has no dtype;
+embedding_denoising_autoencoder.py:166,183), so this engine is held to the fp32 gate: 1e-5 relative against an fp64 product of
+the SAME fp32 operands -- no pre-rounding of the inputs to bf16 as in the bf16-engine tests."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    from codae import _C
+    return _C
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return torch.device("cuda", 0)
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def planes(C, t, dev, pitch=None):
+    """fp32 CPU matrix -> CODAE_F32X3 device planes [3, rows, pitch] through codae_split_x3."""
+    rows, cols = t.shape
+    pitch = pitch or (cols + 7) // 8 * 8
+    src = torch.zeros(rows, pitch, device=dev)
+    src[:, :cols] = t.to(dev)
+    out = C.new_x3((rows, pitch), dev)
+    C.split_x3(src, out)
+    return out[:, :, :cols]
+
+
+def test_split_x3_is_exact_to_2_pow_minus_24(C, dev):
+    torch.manual_seed(0)
+    x = torch.cat([torch.randn(100_000) * 10.0 ** torch.randint(-6, 6, (100_000,)).float(),
+                   torch.tensor([0.0, -0.0, 1.0, -1.0, 1e-30, 3.0e38, 1.0 + 2.0 ** -23, 255.0 / 256.0])])
+    x = x[:x.numel() // 4 * 4].contiguous()
+    out = torch.empty((3, x.numel()), dtype=torch.bfloat16, device=dev)
+    C.split_x3(x.to(dev), out)
+    hi, mid, lo = (out[i].float().cpu().double() for i in range(3))
+    assert torch.equal(out[0].cpu(), x.to(torch.bfloat16))                      # hi is the plain bf16 rounding
+    err = (hi + mid + lo - x.double()).abs()
+    assert bool((err <= x.double().abs() * 2.0 ** -24).all())
+    assert bool(((x > 0) == (out[0].float().cpu() > 0)).all())                  # ReLU masks may be read from the hi plane
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (128, 1536, 1537), (32, 1536, 1536), (200, 192, 192), (33, 600, 1064),
+                                   (1, 128, 832), (300, 328, 72), (128, 512, 1536), (1024, 1536, 512), (2048, 4096, 1024)])
+def test_linear_f32x3_matches_fp64_to_1e5(C, dev, M, N, K):
+    """fwd / dgrad / wgrad on fp32 operands (not bf16-representable) vs the fp64 product: fp32-level agreement, f32 and
+    plane outputs, ReLU epilogue and ReLU-mask epilogue, cluster split-K (small M) and multi-tile grids (large M)."""
+    torch.manual_seed(6)
+    assert C.linear_engine(dev, C.F32X3, max(M, 32), N, K) == C.ENGINE_TCGEN05_F32X3
+    X = torch.randn(M, K)
+    W = torch.randn(N, K) / K ** 0.5
+    dY = torch.randn(M, N)
+    Xp, Wp, dYp = planes(C, X, dev), planes(C, W, dev), planes(C, dY, dev)
+    # what torch's own fp32 contraction achieves on these operands, for scale
+    ref32 = rel(X.mm(W.t()).numpy(), X.double().mm(W.double().t()).numpy())
+    # forward: f32 output with ReLU
+    Y = torch.zeros(M, N, device=dev)
+    C.linear_fwd(Xp, Wp, None, Y, M, N, K, C.ACT_RELU, C.F32X3)
+    want = torch.relu(X.double().mm(W.double().t()))
+    e = rel(Y.cpu().numpy(), want.numpy())
+    assert e < 2e-6, (e, ref32)
+    # forward: plane output, no activation; padding columns of the planes stay untouched
+    Np = (N + 7) // 8 * 8 + 8
+    Yp = C.new_x3((M, Np), dev)
+    Yp.fill_(7.0)
+    C.linear_fwd(Xp, Wp, None, Yp[:, :, :N], M, N, K, C.ACT_NONE, C.F32X3)
+    e = rel(C.x3_to_f32(Yp)[:, :N].cpu().numpy(), X.double().mm(W.double().t()).numpy())
+    assert e < 2e-6, e
+    assert bool((Yp[:, :, N:].float() == 7.0).all())
+    # dgrad with the ReLU mask read from the hi plane of the layer input
+    A = torch.relu(torch.randn(M, K))
+    Ap = planes(C, A, dev)
+    dX = torch.zeros(M, K, device=dev)
+    C.linear_dgrad(dYp, Wp, Ap, dX, M, N, K, C.F32X3)
+    wantdx = dY.double().mm(W.double()) * (A > 0)
+    e = rel(dX.cpu().numpy(), wantdx.numpy())
+    assert e < 2e-6, e
+    dXp = C.new_x3((M, (K + 7) // 8 * 8), dev)
+    C.linear_dgrad(dYp, Wp, None, dXp[:, :, :K], M, N, K, C.F32X3)
+    e = rel(C.x3_to_f32(dXp)[:, :K].cpu().numpy(), dY.double().mm(W.double()).numpy())
+    assert e < 2e-6, e
+    # wgrad (both operands MN-major), with and without the sum-of-squares slots
+    Kp = (K + 3) // 4 * 4
+    dW = torch.zeros(N, Kp, device=dev)
+    C.linear_wgrad(dYp, Xp, dW[:, :K], None, M, N, K, C.F32X3)
+    wantdw = dY.double().t().mm(X.double())
+    e = rel(dW[:, :K].cpu().numpy(), wantdw.numpy())
+    assert e < 2e-6, e
+    slots = C.linear_wgrad_sq_slots(dev, M, N, K, C.F32X3)
+    assert slots >= 1
+    sq = torch.zeros(slots, dtype=torch.float64, device=dev)
+    dW2 = torch.zeros(N, Kp, device=dev)
+    C.linear_wgrad_sq(dYp, Xp, dW2[:, :K], M, N, K, C.F32X3, sq)
+    assert torch.equal(dW2, dW)
+    assert abs(float(sq.sum()) - float((dW.double() ** 2).sum())) <= 1e-6 * float((dW.double() ** 2).sum())
+
+
+def test_f32x3_split_k_is_deterministic(C, dev):
+    torch.manual_seed(8)
+    M, N, K = 128, 1536, 1537
+    X, W = torch.randn(M, K), torch.randn(N, K) / 40
+    Xp, Wp = planes(C, X, dev), planes(C, W, dev)
+    outs = []
+    for _ in range(3):
+        Y = torch.zeros(M, N, device=dev)
+        C.linear_fwd(Xp, Wp, None, Y, M, N, K, C.ACT_RELU, C.F32X3)
+        outs.append(Y.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    C.set_splitk(dev, False)
+    try:
+        Y1 = torch.zeros(M, N, device=dev)
+        C.linear_fwd(Xp, Wp, None, Y1, M, N, K, C.ACT_RELU, C.F32X3)
+    finally:
+        C.set_splitk(dev, True)
+    assert rel(outs[0].cpu().numpy(), Y1.cpu().numpy()) < 2e-6
+
+
+def test_optimizer_keeps_the_plane_shadow_current(C, dev):
+    """codae_adam_step_partials / codae_clip_adam_step with shadow_dtype CODAE_F32X3: planes == split(master) bit for bit."""
+    torch.manual_seed(3)
+    n = 4096 * 6
+    p = torch.randn(n, device=dev)
+    g = torch.randn(n, device=dev) * 0.01
+    m = torch.zeros(n, device=dev)
+    v = torch.zeros(n, device=dev)
+    sh = torch.zeros((3, n), dtype=torch.bfloat16, device=dev)
+    sqn = torch.zeros(1, device=dev)
+    ws = C.sqnorm_workspace(dev)
+    C.clip_adam_step(p, g, m, v, sh, 1e-3, 0.9, 0.999, 1e-8, 1e-4, 1, 1.0, sqn, ws, 1.0)
+    want = torch.zeros((3, n), dtype=torch.bfloat16, device=dev)
+    C.split_x3(p, want)
+    assert torch.equal(sh.view(torch.int16), want.view(torch.int16))
+    part = (g.double() ** 2).sum().view(1)
+    C.adam_step_partials(p, g, m, v, sh, 1e-3, 0.9, 0.999, 1e-8, 1e-4, 2, 1.0, part, sqn, 1.0)
+    C.split_x3(p, want)
+    assert torch.equal(sh.view(torch.int16), want.view(torch.int16))
+    C.adam_step(p, g, m, v, sh, 1e-3, 0.9, 0.999, 1e-8, 1e-4, 3, -1.0, None, 1.0)
+    C.split_x3(p, want)
+    assert torch.equal(sh.view(torch.int16), want.view(torch.int16))
+    assert float((C.x3_to_f32(sh.view(3, 1, n))[0] - p).abs().max()) <= float(p.abs().max()) * 2.0 ** -23

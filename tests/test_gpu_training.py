@@ -55,11 +55,16 @@ def build_embedding(g, dtype="fp32"):
     return ds, model, cor
 
 
+# "fp32" = the reference's precision on the tensor cores (bf16 triples, CODAE_F32X3) wherever every layer is at least 32 wide
+# (emb_small, emb_k2, emb_mid), the FFMA engine otherwise (emb_bottleneck); "fp32_simt" forces the FFMA engine.
+@pytest.mark.parametrize("dtype", ["fp32", "fp32_simt"])
 @pytest.mark.parametrize("name", ["emb_small", "emb_bottleneck", "emb_k2", "emb_mid"])
-def test_legacy_api_matches_reference(name):
+def test_legacy_api_matches_reference(name, dtype):
     """The reference's own call pattern: get_masks -> corrupt -> model() -> MSELoss -> backward -> clip -> Adam.step."""
+    from codae import _C
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
-    ds, model, cor = build_embedding(g)
+    ds, model, cor = build_embedding(g, dtype)
+    assert model.engine_dtype() == (_C.F32X3 if dtype == "fp32" and name != "emb_bottleneck" else _C.F32)
     opt = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["wd"]))
     crit = torch.nn.MSELoss(reduction="mean")
     s = 0
@@ -86,13 +91,14 @@ def test_legacy_api_matches_reference(name):
     assert s >= 2
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "fp32_simt"])
 @pytest.mark.parametrize("name,graph", [("emb_small", False), ("emb_bottleneck", False), ("emb_k2", False), ("emb_mid", False),
                                         ("emb_mid", True)])
-def test_fused_step_matches_reference(name, graph):
+def test_fused_step_matches_reference(name, graph, dtype):
     """FusedStep (the scripts' fast path): same observables, no autograd, flat-buffer clip + Adam kernels."""
     from codae.tool import FusedStep
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
-    ds, model, cor = build_embedding(g)
+    ds, model, cor = build_embedding(g, dtype)
     fs = FusedStep(model, cor, ds.data, lr=float(g["lr"]), weight_decay=float(g["wd"]), clip=bool(g["clip"]), use_graph=graph)
     B = int(g["B"])
     s = 0
@@ -200,6 +206,7 @@ def test_abalone_fused_and_legacy(name):
 
 
 @pytest.mark.parametrize("cfg,B,dtype,tol,graph", [("embedding", 128, "fp32", 1e-5, False), ("modanet", 32, "fp32", 1e-5, False),
+                                                   ("embedding", 128, "fp32", 1e-5, True), ("embedding", 128, "fp32_simt", 1e-5, False),
                                                    ("modanet", 32, "bf16", 1e-2, False), ("bottleneck", 64, "fp32", 1e-5, False),
                                                    ("embedding", 128, "bf16", 1e-2, False), ("embedding", 128, "bf16", 1e-2, True),
                                                    ("bottleneck", 64, "bf16", 1e-2, True)])
@@ -233,6 +240,11 @@ def test_full_size_step_vs_oracle(cfg, B, dtype, tol, graph):
     fs = FusedStep(model, cor, ds.data, lr=lr, weight_decay=wd, clip=clip, use_graph=graph)
     if dtype == "bf16":
         assert fs.eng == 1 and (fs.wgrad_sqnorm or not clip)            # tensor-core engine, norm-free clipped step
+    if dtype == "fp32":
+        # the reference's precision on the tensor cores: bf16 triples (CODAE_F32X3), same norm-free clipped step
+        assert fs.eng == 2 and (fs.wgrad_sqnorm or not clip)
+    if dtype == "fp32_simt":
+        assert fs.eng == 0
     dae = O.OracleDAE(W, b, model.relu, lr, wd, clip)
     bm, nm, _ = O.binary_masks(ds.arch, 1)
     perm = torch.randperm(N)
@@ -246,7 +258,7 @@ def test_full_size_step_vs_oracle(cfg, B, dtype, tol, graph):
         assert abs(fs.last_loss(B) - r["loss"]) <= tol * abs(r["loss"]), (s, fs.last_loss(B), r["loss"])
         y = fs._bufs[B]["acts"][-1][:, :S * E]
         assert rel(y.cpu().numpy(), r["y"].numpy()) < tol, s
-        if dtype == "fp32":
+        if dtype.startswith("fp32"):
             # gradients.  ReLU's derivative is discontinuous: a unit whose pre-activation is within fp32 summation error
             # (~4e-8 here) of 0 passes gradient on one side and not on the other, while its forward value is ~0 either
             # way (loss and reconstruction still agree to 1e-5).  With 128 x 1536 x 8 ReLU evaluations ~2 such flips are
