@@ -28,6 +28,7 @@
 // tiles in L2-friendly groups, the accumulator is double-buffered in TMEM so that the epilogue of tile i overlaps the
 // MMAs of tile i+1, and the shared-memory ring keeps running across tile boundaries.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "gemm.h"
@@ -37,6 +38,7 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kMaxSplit = 8;     // portable cluster size limit
+constexpr int kChunkKb = 8;      // fp32-parity engine: k-blocks (of 64) accumulated in TMEM before the partial sum is folded into registers
 constexpr uint32_t kPersistentStageBytes = 4 * 2 * 4096;   // persistent kernel, bulk-store epilogue: 4 warps x 2 boxes of 32 rows x 128 B
 
 struct Params {
@@ -58,6 +60,7 @@ struct Params {
     unsigned long long* trace;   // debugging: CTA (0,0,0) writes %globaltimer stamps of its phases here (or NULL)
     int c_planes;                // NP == 3 only: 1 -> C is three bf16 planes (hi, mid, lo) c_plane_stride elements apart
     long long c_plane_stride;
+    int tmem_cols;               // TMEM columns this CTA allocates (NP == 3: 2 BN while one chunk covers the k-range, else 4 BN)
 };
 
 // NP = operand planes: 1 (bf16 engine) or 3 (fp32-parity engine, CODAE_F32X3: every operand is the bf16 triple hi + mid + lo of
@@ -74,7 +77,7 @@ struct Cfg {
     static constexpr uint32_t kStageBytes = NP * (kATileBytes + kBTileBytes);
     static constexpr int kStages = NP == 3 ? (BN == 128 ? 2 : 3) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr uint32_t kTmemCols = NP == 3 ? 2 * BN : BN;     // power of two >= 32
+    static constexpr uint32_t kTmemCols = NP == 3 ? 4 * BN : BN;     // power of two >= 32; NP == 3: two sets of {big, small}
 };
 
 // One operand tile per plane: plane pl lands plane_bytes after plane pl - 1.
@@ -191,7 +194,9 @@ __device__ __forceinline__ void store_chunk(const Params& p, int row, int col0, 
     }
 }
 
-template <int BN, int NP>
+// CH (NP == 3 only): the k-range of a CTA is longer than one chunk -> chunked accumulation with the running sum in registers
+// (BN more registers per epilogue thread; the short-k-range variant stays light enough for 2 CTAs per SM).
+template <int BN, int NP, bool CH = false>
 __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                 const __grid_constant__ CUtensorMap tma_b,
                                                                 const __grid_constant__ CUtensorMap tma_c, const Params p) {
@@ -202,8 +207,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     const int nstages = p.stages;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * C::kStageBytes);
     uint64_t* empty_bar = full_bar + nstages;
-    uint64_t* tmem_full_bar = empty_bar + nstages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+    uint64_t* tmem_full_bar = empty_bar + nstages;     // [2] (NP == 1 uses slot 0 only)
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] NP == 3: chunked accumulation, see kChunkKb
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     constexpr int kStagePitch = BN + 4;               // floats per row of the staged fp32 tile
     __shared__ double sq_red[4];
     double sq_acc = 0.0;                              // epilogue threads: sum of squares of the values this thread stored
@@ -224,11 +230,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
         if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_c)) : "memory");
         for (int s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
+    if (warp == 1) tmem_alloc(tmem_slot, (uint32_t)p.tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -300,47 +306,76 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                         umma_bf16(tmem_base, make_desc(a_addr + k * a_adv, p.a_kmajor != 0),
                                   make_desc(b_addr + k * b_adv, p.b_kmajor != 0), idesc, (kb | k) != 0);
                     } else {
+                        // chunked accumulation: k-blocks [ci kChunkKb, (ci + 1) kChunkKb) accumulate into TMEM set ci & 1 from
+                        // zero; the epilogue warps fold finished chunks into fp32 registers with round-to-nearest adds
+                        const int ci = CH ? kb / kChunkKb : 0, within = kb - ci * kChunkKb;
+                        const uint32_t d_big = tmem_base + (uint32_t)((ci & 1) * 2 * BN), d_small = d_big + BN;
+                        if (CH && within == 0 && k == 0) {
+                            mbar_wait(&tmem_empty_bar[ci & 1], (((uint32_t)ci >> 1) & 1) ^ 1);     // set drained (first use: free)
+                            tc_fence_after();
+                        }
                         const bool ak = p.a_kmajor != 0, bk = p.b_kmajor != 0;
                         const uint64_t ah = make_desc(a_addr + k * a_adv, ak), am = make_desc(a_addr + kATileBytes + k * a_adv, ak),
                                        al = make_desc(a_addr + 2 * kATileBytes + k * a_adv, ak);
                         const uint64_t bh = make_desc(b_addr + k * b_adv, bk), bm = make_desc(b_addr + C::kBTileBytes + k * b_adv, bk),
                                        bl = make_desc(b_addr + 2 * C::kBTileBytes + k * b_adv, bk);
-                        const uint32_t first = (kb | k) != 0;
-                        umma_bf16(tmem_base, ah, bh, idesc, first);                 // big
-                        umma_bf16(tmem_base + BN, ah, bm, idesc, first);            // small: five terms <= 2^-8 of the big one
-                        umma_bf16(tmem_base + BN, am, bh, idesc, 1);
-                        umma_bf16(tmem_base + BN, am, bm, idesc, 1);
-                        umma_bf16(tmem_base + BN, ah, bl, idesc, 1);
-                        umma_bf16(tmem_base + BN, al, bh, idesc, 1);
+                        const uint32_t first = (within | k) != 0;
+                        umma_bf16(d_big, ah, bh, idesc, first);                     // big
+                        umma_bf16(d_small, ah, bm, idesc, first);                   // small: five terms <= 2^-8 of the big one
+                        umma_bf16(d_small, am, bh, idesc, 1);
+                        umma_bf16(d_small, am, bm, idesc, 1);
+                        umma_bf16(d_small, ah, bl, idesc, 1);
+                        umma_bf16(d_small, al, bh, idesc, 1);
                     }
                 }
                 umma_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
+                if constexpr (NP == 3 && CH) {
+                    if ((kb + 1) % kChunkKb == 0 && kb + 1 < num_kb) umma_commit(&tmem_full_bar[(kb / kChunkKb) & 1]);   // chunk complete
+                }
             }
-            umma_commit(tmem_full_bar);              // accumulator complete
+            umma_commit(&tmem_full_bar[(NP == 3 && CH) ? ((num_kb - 1) / kChunkKb) & 1 : 0]);      // accumulator complete
             trace_stamp(p, 4);                       // all MMAs issued
         }
     } else {
         // ===== epilogue, part 1: TMEM -> registers -> HBM (direct) or -> shared-memory tile (staged) =====
-        mbar_wait(tmem_full_bar, 0);
+        const int q = warp & 3;                      // TMEM lane quarter this warp may read
+        uint32_t tmem_acc = tmem_base;               // accumulator set the last (or only) chunk lands in
+        [[maybe_unused]] float racc[(NP == 3 && CH) ? BN : 1];   // running fp32 sum of the finished chunks (this thread's row)
+        if constexpr (NP == 3 && CH) {
+#pragma unroll
+            for (int j = 0; j < BN; ++j) racc[j] = 0.f;
+            const int nchunks = (num_kb + kChunkKb - 1) / kChunkKb;
+            for (int ci = 0; ci + 1 < nchunks; ++ci) {
+                const int set = ci & 1;
+                mbar_wait(&tmem_full_bar[set], ((uint32_t)ci >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32], u[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 2 * BN + c * 32), v);
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 2 * BN + BN + c * 32), u);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[set]);
+            }
+            const int last = nchunks - 1;
+            mbar_wait(&tmem_full_bar[last & 1], ((uint32_t)last >> 1) & 1);
+            tmem_acc = tmem_base + (uint32_t)((last & 1) * 2 * BN);
+        } else {
+            mbar_wait(tmem_full_bar, 0);
+        }
         if (threadIdx.x == 64) trace_stamp(p, 5);                  // accumulator complete
         tc_fence_after();
-        const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < p.M;
         float* stage_row = reinterpret_cast<float*>(smem) + (size_t)(q * 32 + lane) * kStagePitch;
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-            if constexpr (NP == 3) {
-                uint32_t u[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), u);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-            }
+        auto emit = [&](const int c, uint32_t (&v)[32]) {
             const int col0 = n0 + c * 32;
             if (!p.staged) {
-                if (!row_ok || col0 >= p.N) continue;
+                if (!row_ok || col0 >= p.N) return;
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -370,6 +405,29 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 for (int j = 0; j < 8; ++j)
                     dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                                          __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+        };
+        if constexpr (NP == 3) {
+            // last chunk: (big + small) + the running sum; fully unrolled, racc stays in registers
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32], u[32];
+                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), u);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                    if constexpr (CH) x += racc[c * 32 + j];
+                    v[j] = __float_as_uint(x);
+                }
+                emit(c, v);
+            }
+        } else {
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
+                emit(c, v);
             }
         }
     }
@@ -503,7 +561,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, C::kTmemCols);
+        tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
     }
     if (p.trace && threadIdx.x == 0) {          // debugging: slot 10 = exit of CTA (0,0,0), slot 11 = last CTA exit, slot 12 = first entry
         unsigned long long t;
@@ -775,6 +833,8 @@ struct Plan {
     bool persistent;   // one CTA per SM walking tiles
     int gx, gy;        // output tiles along N and M
     int ctas;          // CTAs the launch will have (= sum-of-squares slots it writes)
+    int stages = 0;    // NP == 3: pipeline depth chosen by x3_geometry (0: the launch code's default)
+    int tmem_cols = 0; // NP == 3: TMEM columns per CTA
 };
 // 2-D tensor map over the row-major OUTPUT [rows, cols] with pitch ld (elements) for cp.async.bulk.tensor stores:
 // boxes of 128 bytes x box_rows rows, 128-byte swizzle (f32: 32 columns, bf16: 64 columns).
@@ -793,6 +853,47 @@ int make_store_map(codae_ctx* ctx, CUtensorMap* map, void* base, int c_dtype, lo
     return CODAE_OK;
 }
 
+// ---- fp32-parity engine: launch geometry ---------------------------------------------------------------------------------
+// Measured on a B200 (tools/probes/occ_probe.cu): a kernel that contains tcgen05.alloc is scheduled ONE CTA per SM whatever its
+// shared memory and registers are (cudaOccupancyMaxActiveBlocksPerMultiprocessor returns 1 even at 1 KB).  The bf16 split-K
+// launches (24 clusters of 6) happen to fit the GPCs; with 72 KB three-plane stages the same geometry was measured as a second
+// wave that doubled the launch (21 vs 12 us per dgrad): the cluster size is therefore the largest one for which
+// cudaOccupancyMaxActiveClusters says every cluster of the launch is resident at once.
+template <int BN, bool CH>
+bool x3_set_smem_attr() {
+    static bool ok = cudaFuncSetAttribute(tc05_gemm_kernel<BN, 3, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)Cfg<BN, 3>::kSmemBytes) == cudaSuccess;
+    return ok;
+}
+template <int BN, bool CH>
+int x3_max_clusters(int nsplit, size_t smem) {
+    static std::mutex mu;
+    static int cache[kMaxSplit + 1][Cfg<BN, 3>::kStages + 1];
+    const int st = (int)(smem / Cfg<BN, 3>::kStageBytes);
+    std::lock_guard<std::mutex> lk(mu);
+    int& slot = cache[nsplit][st];
+    if (slot == 0) {
+        x3_set_smem_attr<BN, CH>();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(1, 1, nsplit);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 1;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = nsplit;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, tc05_gemm_kernel<BN, 3, CH>, &cfg) != cudaSuccess || n < 1) {
+            cudaGetLastError();
+            n = 1 << 20;      // no answer: do not constrain
+        }
+        slot = n;
+    }
+    return slot;
+}
 template <int BN, int NP = 1>
 Plan make_plan(const codae_ctx* ctx, const Tc05Gemm& g) {
     Plan pl;
@@ -811,6 +912,24 @@ Plan make_plan(const codae_ctx* ctx, const Tc05Gemm& g) {
             const int kb_per = (total_kb + want - 1) / want;
             nsplit = (total_kb + kb_per - 1) / kb_per;               // no empty split
         }
+    }
+    if constexpr (NP == 3) {
+        using C3 = Cfg<BN, 3>;
+        auto smem_for = [](int stages) { return (size_t)stages * C3::kStageBytes + 1024 + 256; };
+        // split-K: shrink the cluster until every cluster of the launch is resident at once
+        while (nsplit > 1) {
+            const int kb_per = (total_kb + nsplit - 1) / nsplit;
+            const int st = kb_per < C3::kStages ? kb_per : C3::kStages;
+            const int fit = kb_per > kChunkKb ? x3_max_clusters<BN, true>(nsplit, smem_for(st)) : x3_max_clusters<BN, false>(nsplit, smem_for(st));
+            if (fit >= tiles) break;
+            int want = nsplit - 1;
+            const int kb2 = (total_kb + want - 1) / want;
+            nsplit = (total_kb + kb2 - 1) / kb2;
+        }
+        const int kb_per = (total_kb + nsplit - 1) / nsplit;
+        pl.tmem_cols = kb_per > kChunkKb ? 4 * BN : 2 * BN;
+        const int st = kb_per < C3::kStages ? kb_per : C3::kStages;
+        pl.stages = st;
     }
     pl.nsplit = nsplit;
     // staged (coalesced) epilogue: always for split-K; for fp32 outputs only while the grid is at most ~2 waves
@@ -895,12 +1014,19 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc05_gemm_kernel<BN, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(tc05_gemm_kernel<BN, NP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
+        if (e == cudaSuccess && NP == 3)
+            e = cudaFuncSetAttribute(tc05_gemm_kernel<BN, NP, NP == 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
         if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaFuncSetAttribute(smem=%u): %s", C::kSmemBytes, cudaGetErrorString(e));
         attr_set = true;
     }
     const int kb_per_cta = ((total_kb + nsplit - 1) / nsplit);
     p.stages = kb_per_cta < C::kStages ? (kb_per_cta < 2 ? 2 : kb_per_cta) : C::kStages;
+    p.tmem_cols = BN;
+    if constexpr (NP == 3) {
+        p.stages = pl.stages;
+        p.tmem_cols = pl.tmem_cols;
+    }
     size_t pipe_bytes = (size_t)p.stages * C::kStageBytes;
     const size_t stage_tile = (size_t)BM * (BN + 4) * sizeof(float);          // staged epilogue overlays the pipeline
     if (p.staged && pipe_bytes < stage_tile) {
@@ -929,7 +1055,17 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, tc05_gemm_kernel<BN, NP>, ma, mb, mc, p);
+    const bool chunked = NP == 3 && kb_per_cta > kChunkKb;
+    static const bool debug_plan = getenv("CODAE_DEBUG_PLAN") != nullptr;
+    if (debug_plan) {
+        int occ = -1;
+        if (chunked) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc05_gemm_kernel<BN, NP, NP == 3>, kThreads, smem_bytes);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tc05_gemm_kernel<BN, NP, false>, kThreads, smem_bytes);
+        fprintf(stderr, "codae plan: M=%d N=%d K=%d BN=%d NP=%d grid %d x %d x %d stages %d smem %zu tmem %d staged %d tma_store %d chunked %d occupancy %d\n",
+                g.M, g.N, g.K, BN, NP, pl.gx, pl.gy, nsplit, p.stages, smem_bytes, p.tmem_cols, p.staged, p.tma_store, (int)chunked, occ);
+    }
+    cudaError_t le = chunked ? cudaLaunchKernelEx(&cfg, tc05_gemm_kernel<BN, NP, NP == 3>, ma, mb, mc, p)
+                             : cudaLaunchKernelEx(&cfg, tc05_gemm_kernel<BN, NP, false>, ma, mb, mc, p);
     if (le != cudaSuccess) {
         cudaGetLastError();
         return codae_fail(ctx, CODAE_ECUDA, "tc05_gemm_kernel<%d, %d> launch (grid %u x %u x %d, smem %zu): %s", BN, NP, cfg.gridDim.x,
