@@ -50,50 +50,76 @@ __device__ __forceinline__ bool list_insert(float* ls, int64_t* li, int k, float
     return true;
 }
 
-// One candidate row against QC queries (smem), partial sums per lane.
+// R candidate rows against QC queries (smem), partial sums per lane.  All loads of a 256-element (bf16) / 128-element (f32)
+// column block of the R rows are issued before the first use: R x 16 bytes (bf16) or R x 16 bytes x 1 (f32, four column blocks
+// per unrolled pass) in flight per lane -- a 1 KB bf16 row alone leaves a warp with 2 loads in flight and the sweep at half of
+// the HBM rate (measured 0.52 of the copy bandwidth; fp32 rows are twice as long and reached 0.94).
+// The per-row arithmetic (order of the FMAs inside a lane, then the shuffle tree) does not depend on R: scores are bit-identical
+// to the one-row-at-a-time sweep.
 //   SQERR : acc[q] = sum (q_d - c_d*inv_scale)^2 ; COSINE: acc[q] = sum c_d q_d, cc = sum c_d^2
-template <int METRIC, int QC, bool kBf16>
-__device__ __forceinline__ void row_partial(const void* __restrict__ row, int E, const float* __restrict__ qs, float inv_scale,
-                                            int lane, float acc[QC], float& cc) {
+template <int METRIC, int QC, bool kBf16, int R>
+__device__ __forceinline__ void rows_partial(const unsigned char* const (&row)[R], int E, const float* __restrict__ qs,
+                                             float inv_scale, int lane, float (&acc)[R][QC], float (&cc)[R]) {
 #pragma unroll
-    for (int q = 0; q < QC; ++q) acc[q] = 0.f;
-    cc = 0.f;
+    for (int j = 0; j < R; ++j) {
+        cc[j] = 0.f;
+#pragma unroll
+        for (int q = 0; q < QC; ++q) acc[j][q] = 0.f;
+    }
     if (kBf16) {
-        const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(row);
-#pragma unroll 2
         for (int c = lane * 8; c < E; c += 256) {
-            const uint4 p = ldg_stream_u4(r + c);
-            const float v[8] = {bf16_lo(p.x), bf16_hi(p.x), bf16_lo(p.y), bf16_hi(p.y),
-                                bf16_lo(p.z), bf16_hi(p.z), bf16_lo(p.w), bf16_hi(p.w)};
+            uint4 p[R];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (METRIC == CODAE_METRIC_COSINE) cc = fmaf(v[j], v[j], cc);
+            for (int j = 0; j < R; ++j) p[j] = ldg_stream_u4(reinterpret_cast<const __nv_bfloat16*>(row[j]) + c);
 #pragma unroll
-                for (int q = 0; q < QC; ++q) {
-                    const float qv = qs[q * E + c + j];
-                    if (METRIC == CODAE_METRIC_SQERR) { const float d = qv - v[j] * inv_scale; acc[q] = fmaf(d, d, acc[q]); }
-                    else acc[q] = fmaf(v[j], qv, acc[q]);
+            for (int j = 0; j < R; ++j) {
+                const float v[8] = {bf16_lo(p[j].x), bf16_hi(p[j].x), bf16_lo(p[j].y), bf16_hi(p[j].y),
+                                    bf16_lo(p[j].z), bf16_hi(p[j].z), bf16_lo(p[j].w), bf16_hi(p[j].w)};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (METRIC == CODAE_METRIC_COSINE) cc[j] = fmaf(v[e], v[e], cc[j]);
+#pragma unroll
+                    for (int q = 0; q < QC; ++q) {
+                        const float qv = qs[q * E + c + e];
+                        if (METRIC == CODAE_METRIC_SQERR) { const float d = qv - v[e] * inv_scale; acc[j][q] = fmaf(d, d, acc[j][q]); }
+                        else acc[j][q] = fmaf(v[e], qv, acc[j][q]);
+                    }
                 }
             }
         }
     } else {
-        const float* r = reinterpret_cast<const float*>(row);
-#pragma unroll 4
         for (int c = lane * 4; c < E; c += 128) {
-            const float4 p = ldg_stream_f4(r + c);
-            const float v[4] = {p.x, p.y, p.z, p.w};
+            float4 p[R];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (METRIC == CODAE_METRIC_COSINE) cc = fmaf(v[j], v[j], cc);
+            for (int j = 0; j < R; ++j) p[j] = ldg_stream_f4(reinterpret_cast<const float*>(row[j]) + c);
 #pragma unroll
-                for (int q = 0; q < QC; ++q) {
-                    const float qv = qs[q * E + c + j];
-                    if (METRIC == CODAE_METRIC_SQERR) { const float d = qv - v[j] * inv_scale; acc[q] = fmaf(d, d, acc[q]); }
-                    else acc[q] = fmaf(v[j], qv, acc[q]);
+            for (int j = 0; j < R; ++j) {
+                const float v[4] = {p[j].x, p[j].y, p[j].z, p[j].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    if (METRIC == CODAE_METRIC_COSINE) cc[j] = fmaf(v[e], v[e], cc[j]);
+#pragma unroll
+                    for (int q = 0; q < QC; ++q) {
+                        const float qv = qs[q * E + c + e];
+                        if (METRIC == CODAE_METRIC_SQERR) { const float d = qv - v[e] * inv_scale; acc[j][q] = fmaf(d, d, acc[j][q]); }
+                        else acc[j][q] = fmaf(v[e], qv, acc[j][q]);
+                    }
                 }
             }
         }
     }
+}
+
+// One row (rank mode).
+template <int METRIC, int QC, bool kBf16>
+__device__ __forceinline__ void row_partial(const void* __restrict__ row, int E, const float* __restrict__ qs, float inv_scale,
+                                            int lane, float (&acc)[QC], float& cc) {
+    const unsigned char* const rows[1] = {reinterpret_cast<const unsigned char*>(row)};
+    float a[1][QC], c1[1];
+    rows_partial<METRIC, QC, kBf16, 1>(rows, E, qs, inv_scale, lane, a, c1);
+#pragma unroll
+    for (int q = 0; q < QC; ++q) acc[q] = a[0][q];
+    cc = c1[0];
 }
 
 template <int METRIC>
@@ -128,15 +154,33 @@ __global__ void __launch_bounds__(kThreads) score_topk_kernel(const void* __rest
     int64_t* my_i = li + warp * QC * k;
     const size_t esz = kBf16 ? 2 : 4;
     const int64_t wstride = (int64_t)gridDim.x * kWarps;
-    for (int64_t r = (int64_t)blockIdx.x * kWarps + warp; r < n_rows; r += wstride) {
-        float acc[QC], cc;
-        row_partial<METRIC, QC, kBf16>(reinterpret_cast<const unsigned char*>(catalog) + (size_t)r * ld * esz, E, qs,
-                                       inv_scale, lane, acc, cc);
-        if (METRIC == CODAE_METRIC_COSINE) cc = warp_sum(cc);
+    // rows per warp pass = independent 16-byte loads per lane and column block (fewer with four queries: register budget)
+    constexpr int R = (kBf16 ? 8 : 4) / (QC == 1 ? 1 : 2);
+    for (int64_t r = (int64_t)blockIdx.x * kWarps + warp; r < n_rows; r += R * wstride) {
+        const unsigned char* row[R];
 #pragma unroll
-        for (int q = 0; q < QC; ++q) {
-            const float s = finish_score<METRIC>(warp_sum(acc[q]), cc, qq[q]);
-            if (s == s) list_insert<METRIC>(my_s + q * k, my_i + q * k, k, s, row_offset + r, lane);  // NaN never ranks
+        for (int j = 0; j < R; ++j) {
+            const int64_t rj = r + j * wstride;
+            row[j] = reinterpret_cast<const unsigned char*>(catalog) + (size_t)(rj < n_rows ? rj : r) * ld * esz;   // tail: re-read row r, result unused
+        }
+        float acc[R][QC], cc[R];
+        rows_partial<METRIC, QC, kBf16, R>(row, E, qs, inv_scale, lane, acc, cc);
+        // R x QC independent shuffle trees: the compiler interleaves them
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            if (METRIC == CODAE_METRIC_COSINE) cc[j] = warp_sum(cc[j]);
+#pragma unroll
+            for (int q = 0; q < QC; ++q) acc[j][q] = warp_sum(acc[j][q]);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int64_t rj = r + j * wstride;
+            if (rj >= n_rows) break;
+#pragma unroll
+            for (int q = 0; q < QC; ++q) {
+                const float s = finish_score<METRIC>(acc[j][q], cc[j], qq[q]);
+                if (s == s) list_insert<METRIC>(my_s + q * k, my_i + q * k, k, s, row_offset + rj, lane);  // NaN never ranks
+            }
         }
     }
     __syncthreads();
@@ -161,23 +205,41 @@ __global__ void __launch_bounds__(kThreads) score_topk_kernel(const void* __rest
 
 // Merge `n_lists` sorted k-lists per query (layout [n_lists][Q][k]) into out [Q][k].  One CTA per query;
 // every warp folds a strided subset of the lists, then warp 0 folds the per-warp results.
+// A warp first copies its lists into shared memory with all lanes loading (hundreds of independent loads in flight), then
+// folds them from there: folding straight from global memory is a chain of dependent ~0.6 us loads per list (measured 48.9 us
+// for the 592 lists of one sweep).
+constexpr int kMergeStage = 1024;          // entries per warp staged per pass (12 KB)
+inline size_t merge_smem() { return (size_t)kWarps * kMergeStage * 12; }
 template <int METRIC>
 __global__ void __launch_bounds__(kThreads) topk_merge_kernel(const float* __restrict__ in_s, const int64_t* __restrict__ in_i,
                                                               int n_lists, int Q, int k, float* __restrict__ out_s,
                                                               int64_t* __restrict__ out_i, int q_out_offset, int q_out_stride) {
     __shared__ float ls[kWarps][kMaxK];
     __shared__ int64_t li[kWarps][kMaxK];
+    extern __shared__ __align__(16) unsigned char merge_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, q = blockIdx.x;
+    int64_t* st_i = reinterpret_cast<int64_t*>(merge_raw) + warp * kMergeStage;
+    float* st_s = reinterpret_cast<float*>(merge_raw + (size_t)kWarps * kMergeStage * 8) + warp * kMergeStage;
     for (int e = lane; e < k; e += 32) { ls[warp][e] = worst_score<METRIC>(); li[warp][e] = kEmptyIdx; }
     __syncwarp();
-    for (int l = warp; l < n_lists; l += kWarps) {
-        const float* s = in_s + ((int64_t)l * Q + q) * k;
-        const int64_t* i = in_i + ((int64_t)l * Q + q) * k;
-        for (int e = 0; e < k; ++e) {
-            const int64_t ii = i[e];
-            if (ii == kEmptyIdx || ii < 0) break;
-            if (!list_insert<METRIC>(ls[warp], li[warp], k, s[e], ii, lane)) break;
+    const int per_pass = kMergeStage / k;                              // lists per pass (k <= 128 -> at least 8)
+    const int mine = n_lists > warp ? (n_lists - warp + kWarps - 1) / kWarps : 0;    // lists warp, warp + kWarps, ...
+    for (int j0 = 0; j0 < mine; j0 += per_pass) {
+        const int nl = min(per_pass, mine - j0);
+        for (int t = lane; t < nl * k; t += 32) {
+            const int j = t / k, e = t - j * k;
+            const int64_t src = ((int64_t)(warp + (j0 + j) * kWarps) * Q + q) * k + e;
+            st_s[t] = in_s[src];
+            st_i[t] = in_i[src];
         }
+        __syncwarp();
+        for (int j = 0; j < nl; ++j)
+            for (int e = 0; e < k; ++e) {
+                const int64_t ii = st_i[j * k + e];
+                if (ii == kEmptyIdx || ii < 0) break;
+                if (!list_insert<METRIC>(ls[warp], li[warp], k, st_s[j * k + e], ii, lane)) break;
+            }
+        __syncwarp();
     }
     __syncthreads();
     if (warp == 0) {
@@ -193,6 +255,12 @@ __global__ void __launch_bounds__(kThreads) topk_merge_kernel(const float* __res
             out_i[(int64_t)qo * k + e] = empty ? -1 : li[0][e];
         }
     }
+}
+
+inline void merge_attrs() {      // the staging buffers need the opt-in shared-memory size (once per process)
+    static const bool done = (cudaFuncSetAttribute(topk_merge_kernel<CODAE_METRIC_SQERR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem()),
+                              cudaFuncSetAttribute(topk_merge_kernel<CODAE_METRIC_COSINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)merge_smem()), true);
+    (void)done;
 }
 
 // Rank mode: s_true[q] = score(query q, row true_idx[q]); out_rank[q] = #{j in subset : s_true[q] better-than s_q[j]}.
@@ -348,10 +416,12 @@ int codae_score_topk(codae_ctx* ctx, const void* catalog, int cat_dtype, int64_t
         return codae_fail(ctx, CODAE_ENOMEM, "codae_score_topk: workspace %zu < %zu bytes", ws_bytes,
                           codae_score_topk_workspace_bytes(ctx, Q, k));
     cudaStream_t s = as_stream(stream);
-    const int grid = sweep_grid(ctx, n_rows);
+    merge_attrs();
+    const int grid0 = sweep_grid(ctx, n_rows);
     int64_t* ws_idx = reinterpret_cast<int64_t*>(workspace);
-    float* ws_score = reinterpret_cast<float*>(ws_idx + (size_t)grid * 4 * k);
+    float* ws_score = reinterpret_cast<float*>(ws_idx + (size_t)grid0 * 4 * k);
     for (int q0 = 0; q0 < Q; q0 += 4) {
+        int grid = grid0;
         const int qc = (Q - q0 >= 4) ? 4 : 1;
         const int reps = (Q - q0 >= 4) ? 1 : (Q - q0);  // leftover queries one at a time
         for (int rpt = 0; rpt < reps; ++rpt) {
@@ -360,6 +430,9 @@ int codae_score_topk(codae_ctx* ctx, const void* catalog, int cat_dtype, int64_t
 #define LAUNCH(MET, QC, BF)                                                                                       \
     do {                                                                                                          \
         cudaFuncSetAttribute(score_topk_kernel<MET, QC, BF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        /* one resident wave: the grid-stride sweep balances itself only if every CTA runs from the start */          \
+        const int occ = resident_ctas_per_sm(score_topk_kernel<MET, QC, BF>, kThreads, smem);                          \
+        if (grid > ctx->sm_count * occ) grid = ctx->sm_count * occ;                                                  \
         score_topk_kernel<MET, QC, BF><<<grid, kThreads, smem, s>>>(catalog, n_rows, ld, E, row_offset, qptr, inv_scale, k, \
                                                                     ws_score, ws_idx);                           \
     } while (0)
@@ -374,9 +447,9 @@ int codae_score_topk(codae_ctx* ctx, const void* catalog, int cat_dtype, int64_t
             int rc = codae_check_launch(ctx, "score_topk_kernel");
             if (rc) return rc;
             if (metric == CODAE_METRIC_SQERR)
-                topk_merge_kernel<CODAE_METRIC_SQERR><<<qc, kThreads, 0, s>>>(ws_score, ws_idx, grid, qc, k, out_score, out_idx, q0 + rpt, 1);
+                topk_merge_kernel<CODAE_METRIC_SQERR><<<qc, kThreads, merge_smem(), s>>>(ws_score, ws_idx, grid, qc, k, out_score, out_idx, q0 + rpt, 1);
             else
-                topk_merge_kernel<CODAE_METRIC_COSINE><<<qc, kThreads, 0, s>>>(ws_score, ws_idx, grid, qc, k, out_score, out_idx, q0 + rpt, 1);
+                topk_merge_kernel<CODAE_METRIC_COSINE><<<qc, kThreads, merge_smem(), s>>>(ws_score, ws_idx, grid, qc, k, out_score, out_idx, q0 + rpt, 1);
             rc = codae_check_launch(ctx, "topk_merge_kernel");
             if (rc) return rc;
         }
@@ -388,10 +461,11 @@ int codae_topk_merge(codae_ctx* ctx, const float* scores, const int64_t* idx, in
                      float* out_score, int64_t* out_idx, void* stream) {
     CODAE_REQUIRE(ctx, ctx && scores && idx && out_score && out_idx, "codae_topk_merge: NULL argument");
     CODAE_REQUIRE(ctx, G >= 1 && Q >= 1 && k >= 1 && k <= kMaxK, "codae_topk_merge: bad shape");
+    merge_attrs();
     if (metric == CODAE_METRIC_SQERR)
-        topk_merge_kernel<CODAE_METRIC_SQERR><<<Q, kThreads, 0, as_stream(stream)>>>(scores, idx, G, Q, k, out_score, out_idx, 0, 1);
+        topk_merge_kernel<CODAE_METRIC_SQERR><<<Q, kThreads, merge_smem(), as_stream(stream)>>>(scores, idx, G, Q, k, out_score, out_idx, 0, 1);
     else if (metric == CODAE_METRIC_COSINE)
-        topk_merge_kernel<CODAE_METRIC_COSINE><<<Q, kThreads, 0, as_stream(stream)>>>(scores, idx, G, Q, k, out_score, out_idx, 0, 1);
+        topk_merge_kernel<CODAE_METRIC_COSINE><<<Q, kThreads, merge_smem(), as_stream(stream)>>>(scores, idx, G, Q, k, out_score, out_idx, 0, 1);
     else
         return codae_fail(ctx, CODAE_EINVAL, "codae_topk_merge: bad metric %d", metric);
     return codae_check_launch(ctx, "topk_merge_kernel");
@@ -433,7 +507,8 @@ int codae_swap_error_topk(codae_ctx* ctx, const float* outfit, const void* catal
         swap_error_topk_kernel<false><<<grid, kThreads, smem, s>>>(outfit, catalog, ld_cat, first_row, B, E, slot, io, inv_scale, y, ld_y, row_offset, k, ws_score, ws_idx);
     int rc = codae_check_launch(ctx, "swap_error_topk_kernel");
     if (rc) return rc;
-    topk_merge_kernel<CODAE_METRIC_SQERR><<<1, kThreads, 0, s>>>(ws_score, ws_idx, grid, 1, k, out_score, out_idx, 0, 1);
+    merge_attrs();
+    topk_merge_kernel<CODAE_METRIC_SQERR><<<1, kThreads, merge_smem(), s>>>(ws_score, ws_idx, grid, 1, k, out_score, out_idx, 0, 1);
     return codae_check_launch(ctx, "topk_merge_kernel");
 }
 

@@ -30,7 +30,8 @@ def parse():
     parser.add_argument('--rank', type=bool, default=False)
     parser.add_argument('--nb_missing', type=int, default=1)
     parser.add_argument('--synthetic', type=int, default=0)
-    parser.add_argument('--graph', action="store_true")
+    parser.add_argument('--graph', action="store_true",
+                        help="device-side sampler + CUDA graphs: one graph launch per 32 training steps (FusedStep.train_epoch)")
     parser.add_argument('--epochs', type=int, default=None)
     parser.add_argument('--dtype', type=str, default=None, choices=["fp32", "bf16", "fp32_simt"],
                         help="compute engine: fp32 (reference precision) or bf16 tensor cores; overrides MODEL.DTYPE of the config")
@@ -83,14 +84,21 @@ if __name__ == "__main__":
     B = config["MODEL"]["BATCH_SIZE"]
     rng = np.random.RandomState(config["SEED"])
     S = dataset.nb_used_category
+    train_idx_dev = torch.as_tensor(train_indices, dtype=torch.int64, device=device)
+    sampler_gen = torch.Generator(device=device)
+    sampler_gen.manual_seed(config["SEED"])
 
     for epoch in range(args.epochs or config["MODEL"]["EPOCH"]):
         if rank == 0:
             log.info("===================================================== EPOCH = %d" % epoch)
         trainer.reset_monitors()
-        for local_idx, global_b in epoch_batches(train_indices, B, rng, rank, world):
-            idx = torch.as_tensor(local_idx, dtype=torch.int64).pin_memory()
-            trainer.step(idx, run=0, global_batch=global_b)
+        if args.graph:
+            # sampler on the device, 32 steps per CUDA-graph launch (FusedStep.train_epoch); every rank draws the same permutation
+            trainer.train_epoch(train_idx_dev, B, generator=sampler_gen, rank=rank)
+        else:
+            for local_idx, global_b in epoch_batches(train_indices, B, rng, rank, world):
+                idx = torch.as_tensor(local_idx, dtype=torch.int64).pin_memory()
+                trainer.step(idx, run=0, global_batch=global_b)
         mon = trainer.read_monitors()                      # one D2H per epoch instead of two per step
         acc = torch.tensor([mon["full"], mon["partial"]], dtype=torch.float64, device=device)
         if world > 1:

@@ -424,3 +424,36 @@ def test_ragged_last_batch_and_validation_pass():
     fs.step(torch.arange(8, 11, device=DEV))     # ragged: B = 3
     assert not np.array_equal(flat_params(model), before)
     assert np.isfinite(fs.last_loss(3))
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_train_epoch_device_sampler_matches_step_loop(dtype):
+    """FusedStep.train_epoch (permutation drawn on the device, K steps per CUDA-graph launch, ragged last batch through the
+    per-step path) must leave exactly the weights and monitors of the same steps issued one by one from the host
+    (train_dae_on_embedding.py:118-128,194-223: SubsetRandomSampler + DataLoader(batch_size) + the loop body)."""
+    from codae.tool import FusedStep
+    g = np.load(os.path.join(GOLDEN, "emb_mid.npz"))
+    B, n = 16, 150                                  # 9 full batches + a ragged one of 6 rows; 3 epochs
+    train_idx = torch.arange(5, 5 + n, dtype=torch.int64, device=DEV)
+    out = {}
+    for mode in ("epoch", "loop"):
+        ds, model, cor = build_embedding(g, dtype)
+        fs = FusedStep(model, cor, ds.data, lr=float(g["lr"]), weight_decay=float(g["wd"]), clip=bool(g["clip"]), use_graph=False)
+        gen = torch.Generator(device=DEV)
+        gen.manual_seed(77)
+        steps = 0
+        for epoch in range(3):
+            if mode == "epoch":
+                steps += fs.train_epoch(train_idx, B, generator=gen, graph_steps=4)
+            else:
+                perm = train_idx[torch.randperm(n, device=DEV, generator=gen)]
+                for lo in range(0, n, B):
+                    fs.step(perm[lo:lo + B], run=0)
+                    steps += 1
+        torch.cuda.synchronize()
+        out[mode] = (model.flat.clone(), fs.read_monitors(), steps, fs.m.clone())
+    assert out["epoch"][2] == out["loop"][2] == 30
+    assert torch.equal(out["epoch"][0], out["loop"][0])            # same kernels, same order, same inputs: bit-identical weights
+    assert torch.equal(out["epoch"][3], out["loop"][3])
+    for k in ("full", "partial", "rows"):
+        assert out["epoch"][1][k] == out["loop"][1][k]
