@@ -360,7 +360,7 @@ def scoring_block(args, env, E, seed, model_for_swaps=None):
                "catalog_rows": args.catalog, "E": E, "dtype": tag, "k": 10, "ms_per_sweep": sweep_ms, "scaling": "strong",
                "kernel_ms": k_ms,
                "roofline": {"bound": "hbm", "achieved": bytes_per / (k_ms / 1e3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                            "frac": bytes_per / (k_ms / 1e3) / 1e9 / pk["hbm"], "traffic": measured_traffic("scoring_" + tag),
+                            "frac": bytes_per / (k_ms / 1e3) / 1e9 / pk["hbm"], "traffic": measured_traffic("scoring_" + tag, n_local),
                             "kernel": "score_topk_kernel", "peak_source": pk["src"],
                             "algorithmic_per_launch": bytes_per}}
         if scoring is None:
@@ -526,7 +526,7 @@ def engine_name(model):
 _TRAFFIC = None
 
 
-def measured_traffic(key):
+def measured_traffic(key, rows=None):
     """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture of this
     round (profiles/r02_traffic.json, written by tools/ncu_summary.py --traffic); None when no capture exists for `key`."""
     global _TRAFFIC
@@ -534,7 +534,12 @@ def measured_traffic(key):
         path = os.path.join(ROOT, "profiles", "r02_traffic.json")
         _TRAFFIC = json.load(open(path)) if os.path.exists(path) else {}
     v = _TRAFFIC.get(key)
-    return None if v is None else v.get("bytes_per_launch")
+    if v is None:
+        return None
+    b = v.get("bytes_per_launch")
+    if rows is not None and v.get("rows"):
+        b = b * rows / v["rows"]          # captured on a smaller catalog: DRAM bytes scale with the rows swept
+    return b
 
 
 def fs_dtype(dtype, model):

@@ -49,7 +49,9 @@ def flat(m):
 
 
 ok = True
-CASES = [("peer", "fp32", False, 1e-5, None), ("peer", "bf16", False, 1e-2, None), ("peer", "bf16", True, 1e-2, None),
+# "fp32" = the fp32-parity tensor-core engine (bf16 triples) at these widths; "fp32_simt" = the FFMA engine
+CASES = [("peer", "fp32", False, 1e-5, None), ("peer", "fp32", True, 1e-5, None), ("peer", "fp32_simt", False, 1e-5, None),
+         ("peer", "bf16", False, 1e-2, None), ("peer", "bf16", True, 1e-2, None),
          ("peer", "bf16", True, 1e-2, 40),              # bottleneck widths (odd layer sizes): shard boundaries inside layers
          ("nccl", "fp32", False, 1e-5, None), ("nccl", "bf16", True, 1e-2, None)]
 for mode, dtype, graph, tol, z in CASES:
@@ -78,6 +80,16 @@ for mode, dtype, graph, tol, z in CASES:
             dist.all_gather(gs, sh)
             replicas_equal &= all(torch.equal(g, gs[0]) for g in gs)
             replicas_equal &= bool(torch.equal(m.flat_bf16, m.flat.to(torch.bfloat16)))    # shadow == rounded master
+        if dtype == "fp32":
+            assert fs.eng == 2, fs.eng                       # CODAE_F32X3
+            sh = m.flat_x3.view(torch.int16).to(torch.int32)
+            gs = [torch.empty_like(sh) for _ in range(world)]
+            dist.all_gather(gs, sh)
+            replicas_equal &= all(torch.equal(g, gs[0]) for g in gs)
+            want = torch.empty_like(m.flat_x3)
+            from codae import _C as _CC
+            _CC.split_x3(m.flat, want)
+            replicas_equal &= bool(torch.equal(m.flat_x3.view(torch.int16), want.view(torch.int16)))   # planes == split(master)
         shard_moments = mode != "peer" or fs.m.numel() <= (w_dp.numel() + world - 1) // world + 8
         # single-process reference on the whole global batch (same device, world_size=1)
         ds1, m1, cor1, fs1 = build(dtype, 1, False, z=z)

@@ -35,6 +35,38 @@ def summarise(path):
                 print("      %-66s %s %s" % (m, r[col[m]], units[col[m]]))
 
 
+def traffic(pairs):
+    """--traffic key=report.ncu-rep[:kernel-substring] ... -> JSON {key: {bytes_per_launch, launches, kernels, read, write, source}}:
+    mean dram__bytes_read.sum + dram__bytes_write.sum per captured launch (bench.py reads it as roofline.traffic)."""
+    import json
+    out = {}
+    for pair in pairs:
+        key, rest = pair.split("=", 1)
+        path, _, sub = rest.partition(":")
+        res = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True)
+        if res.returncode != 0:
+            continue
+        rows = list(csv.reader(io.StringIO(res.stdout)))
+        header, units, body = rows[0], rows[1], rows[2:]
+        col = {name: i for i, name in enumerate(header)}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd, wr, names = [], [], []
+        for r in body:
+            if sub and sub not in r[col["Kernel Name"]]:
+                continue
+            ur, uw = units[col["dram__bytes_read.sum"]], units[col["dram__bytes_write.sum"]]
+            rd.append(float(r[col["dram__bytes_read.sum"]].replace(",", "")) * scale.get(ur, 1.0))
+            wr.append(float(r[col["dram__bytes_write.sum"]].replace(",", "")) * scale.get(uw, 1.0))
+            names.append(r[col["Kernel Name"]][:48])
+        if rd:
+            out[key] = {"bytes_per_launch": (sum(rd) + sum(wr)) / len(rd), "launches": len(rd), "read": sum(rd) / len(rd),
+                        "write": sum(wr) / len(wr), "kernels": sorted(set(names)), "source": path.split("/")[-1]}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    for p in sys.argv[1:]:
-        summarise(p)
+    if len(sys.argv) > 1 and sys.argv[1] == "--traffic":
+        traffic(sys.argv[2:])
+    else:
+        for p in sys.argv[1:]:
+            summarise(p)
