@@ -60,6 +60,7 @@ struct Params {
     unsigned long long* trace;   // debugging: CTA (0,0,0) writes %globaltimer stamps of its phases here (or NULL)
     int c_planes;                // NP == 3 only: 1 -> C is three bf16 planes (hi, mid, lo) c_plane_stride elements apart
     long long c_plane_stride;
+    int trace_cta;               // debugging: linear (y * gridDim.x + x) id of the CTA that writes the trace stamps
     int tmem_cols;               // TMEM columns this CTA allocates (NP == 3: 2 BN while one chunk covers the k-range, else 4 BN)
 };
 
@@ -92,7 +93,7 @@ __device__ __forceinline__ void tma_load_op(const CUtensorMap* map, uint64_t* ba
 }
 
 __device__ __forceinline__ void trace_stamp(const Params& p, int slot) {
-    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    if (p.trace && (int)(blockIdx.y * gridDim.x + blockIdx.x) == p.trace_cta && blockIdx.z == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.trace[slot] = t;
@@ -216,14 +217,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int nsplit = gridDim.z;
+    // Single-pass launches walk the tiles column-tile-major: the CTAs of the LAST column tile get the highest linear ids.  tcgen05
+    // kernels run one CTA per SM, so a grid of more than 148 CTAs has a second wave; the weight gradients of an augmented layer
+    // (K = 128 k + 1: the last column tile holds only the bias column) then leave the cheap one-column tiles for it instead of full
+    // ones (156 tiles: second wave = 8 ragged tiles, which also start as soon as the first-wave ragged tiles have exited).
+    int m_idx = blockIdx.y, n_idx = blockIdx.x;
+    if (nsplit == 1) {
+        const int lin = blockIdx.y * gridDim.x + blockIdx.x;
+        n_idx = lin / (int)gridDim.y;
+        m_idx = lin - n_idx * (int)gridDim.y;
+    }
+    const int m0 = m_idx * BM, n0 = n_idx * BN;
     if (threadIdx.x == 0) trace_stamp(p, 0);                       // kernel entry
     const int total_kb = (p.K + BK - 1) / BK;
-    const int nsplit = gridDim.z;
     const int kb_per = (total_kb + nsplit - 1) / nsplit;
     const int kb_begin = blockIdx.z * kb_per;
     const int num_kb = min(total_kb, kb_begin + kb_per) - kb_begin;      // >= 1 by construction (host)
-    const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
@@ -289,7 +299,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc = make_idesc(BN, p.a_kmajor != 0, p.b_kmajor != 0);
+            // a ragged last column tile only pays for the MMA width it needs (multiples of 16)
+            const int n_eff = min(BN, ((p.N - n0) + 15) & ~15);
+            const uint32_t idesc = make_idesc(n_eff, p.a_kmajor != 0, p.b_kmajor != 0);
             const uint32_t a_adv = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);   // bytes per UMMA_K step
             const uint32_t b_adv = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
             int s = 0;
@@ -566,7 +578,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
     if (p.trace && threadIdx.x == 0) {          // debugging: slot 10 = exit of CTA (0,0,0), slot 11 = last CTA exit, slot 12 = first entry
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.trace[10] = t;
+        if ((int)(blockIdx.y * gridDim.x + blockIdx.x) == p.trace_cta && blockIdx.z == 0) p.trace[10] = t;
         atomicMax(&p.trace[11], t);
     }
 }
@@ -804,6 +816,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
 }
 
 
+int g_trace_cta = 0;
 unsigned long long* g_trace_buf = nullptr;   // set through codae_debug_set_trace (debugging hook, not part of the ABI)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -908,6 +921,8 @@ Plan make_plan(const codae_ctx* ctx, const Tc05Gemm& g) {
         int want = ctx->sm_count / tiles;
         if (want > total_kb / 2) want = total_kb / 2;
         if (want > kMaxSplit) want = kMaxSplit;
+        static const int dgrad_maxsplit = getenv("CODAE_DGRAD_MAXSPLIT") ? atoi(getenv("CODAE_DGRAD_MAXSPLIT")) : 0;
+        if (dgrad_maxsplit > 0 && g.a_kmajor && !g.b_kmajor && want > dgrad_maxsplit) want = dgrad_maxsplit;
         if (want > 1) {
             const int kb_per = (total_kb + want - 1) / want;
             nsplit = (total_kb + kb_per - 1) / kb_per;               // no empty split
@@ -968,6 +983,7 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     const int total_kb = (g.K + BK - 1) / BK;
     const int nsplit = pl.nsplit;
     p.trace = g_trace_buf;
+    p.trace_cta = g_trace_cta;
     p.staged = pl.staged ? 1 : 0;
     // bulk-store epilogue: plain f32 tiles of a single-pass launch (the weight gradients of the small-batch step)
     p.tma_store = (ctx->tma_store && pl.staged && nsplit == 1 && g.c_dtype == CODAE_F32 && !g.bias && g.act == CODAE_ACT_NONE &&
@@ -1084,6 +1100,10 @@ extern "C" int codae_debug_set_trace(void* device_buf) {
     g_trace_buf = reinterpret_cast<unsigned long long*>(device_buf);
     return 0;
 }
+extern "C" int codae_debug_set_trace_cta(int linear_cta) {
+    g_trace_cta = linear_cta;
+    return 0;
+}
 
 bool codae_tc05_supported(const codae_ctx* ctx, const Tc05Gemm& g) {
     if (!ctx || !ctx->encode_tiled) return false;
@@ -1110,8 +1130,23 @@ bool codae_tc05_supported(const codae_ctx* ctx, const Tc05Gemm& g) {
 static int pick_bn(const codae_ctx* ctx, const Tc05Gemm& g) {
     const long tiles_m = (g.M + BM - 1) / BM;
     const long t256 = tiles_m * ((g.N + 255) / 256), t128 = tiles_m * ((g.N + 127) / 128);
+    // tuning knobs (read once): CODAE_X3_BN / CODAE_DGRAD_BN = 64 | 128 force the tile width of the fp32-parity engine / of the
+    // input-gradient contraction (K-major A, MN-major B)
+    static const int x3_bn = getenv("CODAE_X3_BN") ? atoi(getenv("CODAE_X3_BN")) : 0;
+    static const int dgrad_bn = getenv("CODAE_DGRAD_BN") ? atoi(getenv("CODAE_DGRAD_BN")) : 0;
+    static const int wgrad_bn = getenv("CODAE_WGRAD_BN") ? atoi(getenv("CODAE_WGRAD_BN")) : 0;
+    const bool is_dgrad = g.a_kmajor && !g.b_kmajor, is_wgrad = !g.a_kmajor && !g.b_kmajor;
+    if (is_dgrad && (dgrad_bn == 64 || dgrad_bn == 128) && g.N >= dgrad_bn) return dgrad_bn;
+    if (is_wgrad && (wgrad_bn == 64 || wgrad_bn == 128 || (wgrad_bn == 256 && g.planes == 1)) && g.N >= wgrad_bn) return wgrad_bn;
+    if (g.planes == 3 && (x3_bn == 64 || x3_bn == 128) && g.N >= x3_bn) return x3_bn;
     if (g.planes == 1 && t256 >= ctx->sm_count && g.N >= 256) return 256;
     if (t128 >= ctx->sm_count && g.N >= 128) return 128;
+    // Small-batch input gradients: 128-wide tiles (12 clusters of 8 = 96 CTAs at 1536 wide) although the launch alone is slower
+    // than 24 x 6 CTAs of 64-wide tiles (86 vs 69 us for nine launches): tcgen05 kernels own their SM, and only this geometry
+    // lets the weight gradient of the same layer (side stream) run beside it.  Measured per step on a B200
+    // (tools/r02_ab_dgrad_bn.sh, r02_ab_bwd_split.sh): embedding.yaml bf16 0.3414 -> 0.3214 ms, fp32 0.5125 -> 0.4901,
+    // modanet 0.2704 -> 0.2558; 72-CTA and 64-wide 96-CTA variants were slower than the default (0.356 - 0.367).
+    if (is_dgrad && dgrad_bn == 0 && g.N >= 128 && tiles_m == 1) return 128;
     return 64;
 }
 

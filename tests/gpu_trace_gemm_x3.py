@@ -60,6 +60,11 @@ run("bf16 fwd", lambda: _C.linear_fwd(Xb[:, :K], Wb[:, :K], None, Yb[:, :N], M, 
 run("bf16 dgrad", lambda: _C.linear_dgrad(dYb[:, :N], Wb[:, :1536], Xb[:, :1536], dXb[:, :1536], M, N, 1536, _C.BF16))
 run("bf16 wgrad", lambda: _C.linear_wgrad(dYb[:, :N], Xb[:, :K], dW[:, :K], None, M, N, K, _C.BF16))
 
+for cta in (0, 143, 144, 147, 148, 155):
+    lib.codae_debug_set_trace_cta(cta)
+    run("x3 wgrad cta %d" % cta, lambda: _C.linear_wgrad(dY[:, :, :N], X[:, :, :K], dW[:, :K], None, M, N, K, _C.F32X3))
+lib.codae_debug_set_trace_cta(0)
+
 # graph-captured repetitions: GPU time per launch without host gaps
 for tag, fn in (("x3 fwd", lambda: _C.linear_fwd(X[:, :, :K], W[:, :, :K], None, Y[:, :, :N], M, N, K, _C.ACT_RELU, _C.F32X3)),
                 ("x3 dgrad", lambda: _C.linear_dgrad(dY[:, :, :N], W[:, :, :1536], X[:, :, :1536], dX[:, :, :1536], M, N, 1536, _C.F32X3)),
