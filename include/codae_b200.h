@@ -307,6 +307,15 @@ int codae_topk_merge(codae_ctx* ctx, const float* scores, const int64_t* idx, in
 int codae_score_rank(codae_ctx* ctx, const void* catalog, int cat_dtype, int64_t n_rows, int64_t ld, int E,
                      const float* query, int Q, float inv_scale, int metric, const int64_t* true_idx,
                      const int64_t* subset_idx, int64_t n_subset, int64_t* out_rank, void* stream);
+/* Rank mode for large query batches (Q >= 64 per category; every validation batch of train_dae_on_embedding.py:241-261 calls
+ * RankingLoss.get): the Q x n cosine numerators are ONE contraction on the fp32-parity tensor-core engine
+ * (codae_linear_fwd_x3 with X = queries, W = [subset rows ; the Q true rows] as CODAE_F32X3 planes, f32 output [Q, n + Q]);
+ * codae_row_sqnorm supplies |c|^2 / |q|^2 (out[r] = sum_d X[r, d]^2) and codae_rank_count the ranks:
+ *   out_rank[q] = #{ j < n : cos(q, true_q) > cos(q, c_j) },  cos = dot / max(sqrt(|c|^2 |q|^2), 1e-8)  (metering.py:67-75),
+ *   dot(q, c_j) = scores[q, j], dot(q, true_q) = scores[q, n + q]; cc [n + Q] f32, qq [Q] f32.  Cosine only. */
+int codae_row_sqnorm(codae_ctx* ctx, const float* X, int64_t ld, int64_t rows, int E, float* out, void* stream);
+int codae_rank_count(codae_ctx* ctx, const float* scores, int64_t ld, int Q, int64_t n, const float* cc, const float* qq,
+                     int64_t* out_rank, void* stream);
 
 /* Candidate SWAPS scored by full reconstruction error (the GEMM-bound reading of stage IV): candidate j replaces slot
  * `slot` of the (scaled) outfit, the DAE reconstructs the swapped outfit (codae_linear_fwd per layer, batched over the

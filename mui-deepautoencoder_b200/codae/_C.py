@@ -67,6 +67,8 @@ SIGNATURES = {
     "codae_score_topk": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i64, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _sz, _vp]),
     "codae_topk_merge": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "codae_score_rank": (_i, [_vp, _vp, _i, _i64, _i64, _i, _vp, _i, _f, _i, _vp, _vp, _i64, _vp, _vp]),
+    "codae_row_sqnorm": (_i, [_vp, _vp, _i64, _i64, _i, _vp, _vp]),
+    "codae_rank_count": (_i, [_vp, _vp, _i64, _i, _i64, _vp, _vp, _vp, _vp]),
     "codae_swap_build": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _f, _vp, _i, _i64, _vp]),
     "codae_swap_error_topk": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _f, _vp, _i64, _i64, _i, _vp, _vp, _vp,
                                    _sz, _vp]),
@@ -465,6 +467,20 @@ def score_rank(catalog, E, query, inv_scale, metric, true_idx, subset_idx, out_r
     check(lib().codae_score_rank(c, p(catalog), dt(catalog), catalog.shape[0], catalog.stride(0), E, p(query),
                                  query.shape[0], inv_scale, metric, p(true_idx), p(subset_idx),
                                  0 if subset_idx is None else subset_idx.numel(), p(out_rank), stream()), c)
+
+
+def row_sqnorm(X, E, out):
+    """out[r] = sum_d X[r, d]^2 (f32 rows of pitch X.stride(0))."""
+    _dev_check(X, out)
+    c = ctx(X.device)
+    check(lib().codae_row_sqnorm(c, p(X), X.stride(0), X.shape[0], E, p(out), stream()), c)
+
+
+def rank_count(scores, Q, n, cc, qq, out_rank):
+    """Ranks from a [Q, n + Q] matrix of dot products (columns n.. hold the true rows), cosine metric."""
+    _dev_check(scores, cc, qq, out_rank)
+    c = ctx(scores.device)
+    check(lib().codae_rank_count(c, p(scores), scores.stride(0), Q, n, p(cc), p(qq), p(out_rank), stream()), c)
 
 
 def swap_build(outfit, catalog, first_row, B, E, slot, io, inv_scale, out_x):

@@ -25,11 +25,14 @@ class RankingLoss:
     (metering.py:29-79).  The per-sample cosine_similarity + O(|val|) Python loop becomes one
     codae_score_rank sweep per masked category."""
 
+    GEMM_MIN_Q = 64      # queries of one category from which the dot products go through the tensor-core contraction
+
     def __init__(self, dataset, validation_indices, device):
         self.dataset = dataset
         self.device = device
         self.validation_indices = validation_indices
         self._val = None
+        self._gemm = {}      # category -> cached operand of the GEMM path (planes of the validation rows, their |c|^2)
 
     def ranks(self, prediction, fmask, indices):
         E = self.dataset.embedding_size
@@ -49,8 +52,51 @@ class RankingLoss:
             catalog = self.dataset.data_per_category[c]
             if not catalog.is_cuda:
                 raise RuntimeError("codae: dataset is not on a CUDA device (dataset.to(device)); no CPU fallback")
-            _C.score_rank(catalog, E, q, 1.0, _C.METRIC_COSINE, idx[rows].contiguous(), self._val, r)
+            if rows.numel() >= self.GEMM_MIN_Q and self._gemm_ok(catalog, E):
+                r = self._ranks_gemm(c, catalog, E, q, idx[rows].contiguous())
+            else:
+                _C.score_rank(catalog, E, q, 1.0, _C.METRIC_COSINE, idx[rows].contiguous(), self._val, r)
             out[rows] = r
+        return out
+
+    @staticmethod
+    def _gemm_ok(catalog, E):
+        return (catalog.dtype == torch.float32 and E % 8 == 0 and
+                _C.linear_engine(catalog.device, _C.F32X3, 128, 128, E) == _C.ENGINE_TCGEN05_F32X3)
+
+    def _ranks_gemm(self, c, catalog, E, q, true_idx, max_q=1024):
+        """Q >= 64 queries of category c: ONE [Q, E] x [E, n_val + Q] contraction on the fp32-parity tensor-core engine (operands
+        as bf16 triples, fp32 accumulation) + codae_rank_count.  The validation rows of the category are gathered and split into
+        planes once; the Q true rows are appended per call so that a true item inside the subset scores bit-identically on both
+        sides of the strict comparison of metering.py:73."""
+        dev = q.device
+        n = int(self._val.numel())
+        ent = self._gemm.get(c)
+        if ent is None:
+            rows = catalog[self._val].contiguous()                                  # [n, E] f32
+            planes = _C.new_x3((n + max_q, E), dev)
+            _C.split_x3(rows, planes[:, :n])
+            cc = torch.zeros(n + max_q, dtype=torch.float32, device=dev)
+            _C.row_sqnorm(rows, E, cc)
+            ent = (planes, cc, torch.zeros(max_q, dtype=torch.float32, device=dev))
+            self._gemm[c] = ent
+        planes, cc, qq = ent
+        out = torch.zeros(q.shape[0], dtype=torch.int64, device=dev)
+        for lo in range(0, q.shape[0], max_q):
+            qs = q[lo:lo + max_q]
+            Q = int(qs.shape[0])
+            true_rows = catalog[true_idx[lo:lo + Q]].contiguous()
+            _C.split_x3(true_rows, planes[:, n:n + Q])
+            _C.row_sqnorm(true_rows, E, cc[n:])
+            _C.row_sqnorm(qs, E, qq)
+            qp = _C.new_x3((Q, E), dev)
+            _C.split_x3(qs, qp)
+            ld = (n + Q + 3) // 4 * 4
+            scores = torch.empty((Q, ld), dtype=torch.float32, device=dev)
+            _C.linear_fwd(qp, planes[:, :n + Q], None, scores[:, :n + Q], Q, n + Q, E, _C.ACT_NONE, _C.F32X3)
+            r = torch.zeros(Q, dtype=torch.int64, device=dev)
+            _C.rank_count(scores, Q, n, cc, qq, r)
+            out[lo:lo + Q] = r
         return out
 
     def get(self, prediction, fmask, indices):

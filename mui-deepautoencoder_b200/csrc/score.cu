@@ -307,6 +307,49 @@ __global__ void __launch_bounds__(kThreads) score_rank_kernel(const void* __rest
         if (cnt[q]) atomicAdd(&out_rank[q], (unsigned long long)cnt[q]);
 }
 
+// ---- rank mode for large query batches: the Q x n dot products come from the fp32-parity tensor-core GEMM ---------------------
+// RankingLoss.get runs for every validation batch (train_dae_on_embedding.py:241-261; metering.py:46-79).  For Q >= 64 queries of
+// one category the dot products q . c_j are one [Q, E] x [E, n] contraction (codae_linear_fwd_x3: fp32 fidelity on tensor cores);
+// these two kernels supply the norms and turn the score matrix into ranks.
+//   row_sqnorm_kernel  out[r] = sum_d X[r, d]^2                  (warp per row, fixed shuffle tree)
+//   rank_count_kernel  out_rank[q] = #{ j < n : cos(q, true_q) > cos(q, c_j) } with cos = dot / max(sqrt(|c|^2 |q|^2), 1e-8),
+//                      dot(q, true_q) = scores[q, n + q] (the true rows are appended to the catalog operand so that a true item
+//                      that is itself in the subset gets bit-identical scores on both sides of the strict comparison)
+__global__ void __launch_bounds__(kThreads) row_sqnorm_kernel(const float* __restrict__ X, int64_t ld, int64_t rows, int E,
+                                                              float* __restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t r = (int64_t)blockIdx.x * kWarps + warp; r < rows; r += (int64_t)gridDim.x * kWarps) {
+        const float* row = X + r * ld;
+        float s = 0.f;
+        for (int c = lane; c < E; c += 32) { const float v = row[c]; s = fmaf(v, v, s); }
+        s = warp_sum(s);
+        if (lane == 0) out[r] = s;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) rank_count_kernel(const float* __restrict__ scores, int64_t ld, int Q, int64_t n,
+                                                              const float* __restrict__ cc, const float* __restrict__ qq,
+                                                              unsigned long long* __restrict__ out_rank) {
+    __shared__ unsigned int part[kWarps];
+    const int q = blockIdx.y;
+    const float* row = scores + (int64_t)q * ld;
+    const float nq = qq[q];
+    const float s_true = row[n + q] / fmaxf(sqrtf(cc[n + q] * nq), 1e-8f);
+    unsigned int cnt = 0;
+    for (int64_t j = (int64_t)blockIdx.x * kThreads + threadIdx.x; j < n; j += (int64_t)gridDim.x * kThreads) {
+        const float s = row[j] / fmaxf(sqrtf(cc[j] * nq), 1e-8f);
+        cnt += (s_true > s) ? 1u : 0u;
+    }
+    cnt = warp_sum(cnt);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = 0;
+        for (int w = 0; w < kWarps; ++w) t += part[w];
+        if (t) atomicAdd(&out_rank[q], (unsigned long long)t);      // integer counts: order-independent
+    }
+}
+
 // ---- candidate SWAPS scored by full reconstruction error --------------------------------------------------------
 // Second reading of "scores candidate item swaps by reconstruction error": put candidate j into slot c of the outfit, run
 // the DAE on the swapped outfit (the tensor-core GEMMs, batched over candidates) and score the swap by
@@ -535,6 +578,27 @@ int codae_score_rank(codae_ctx* ctx, const void* catalog, int cat_dtype, int64_t
     else return codae_fail(ctx, CODAE_EINVAL, "codae_score_rank: bad metric %d", metric);
 #undef LAUNCH
     return codae_check_launch(ctx, "score_rank_kernel");
+}
+
+int codae_row_sqnorm(codae_ctx* ctx, const float* X, int64_t ld, int64_t rows, int E, float* out, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && X && out && rows >= 0 && E >= 1 && ld >= E, "codae_row_sqnorm: bad argument");
+    if (rows == 0) return CODAE_OK;
+    row_sqnorm_kernel<<<sweep_grid(ctx, rows), kThreads, 0, as_stream(stream)>>>(X, ld, rows, E, out);
+    return codae_check_launch(ctx, "row_sqnorm_kernel");
+}
+
+int codae_rank_count(codae_ctx* ctx, const float* scores, int64_t ld, int Q, int64_t n, const float* cc, const float* qq,
+                     int64_t* out_rank, void* stream) {
+    CODAE_REQUIRE(ctx, ctx && scores && cc && qq && out_rank, "codae_rank_count: NULL argument");
+    CODAE_REQUIRE(ctx, Q >= 1 && Q <= 65535 && n >= 0 && ld >= n + Q, "codae_rank_count: bad shape Q=%d n=%lld ld=%lld", Q, (long long)n, (long long)ld);
+    cudaStream_t s = as_stream(stream);
+    cudaError_t e = cudaMemsetAsync(out_rank, 0, sizeof(int64_t) * Q, s);
+    if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+    int gx = (int)((n + kThreads * 8 - 1) / (kThreads * 8));
+    if (gx < 1) gx = 1;
+    if (gx > ctx->sm_count) gx = ctx->sm_count;
+    rank_count_kernel<<<dim3(gx, Q), kThreads, 0, s>>>(scores, ld, Q, n, cc, qq, reinterpret_cast<unsigned long long*>(out_rank));
+    return codae_check_launch(ctx, "rank_count_kernel");
 }
 
 }  // extern "C"

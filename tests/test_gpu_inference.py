@@ -201,3 +201,51 @@ def test_swap_scores_bf16_engine_and_chunk_invariance():
     assert np.allclose(s.numpy(), err[i].numpy(), rtol=1e-2)
     kth = float(O.topk(err, k)[0][-1])
     assert float(err[i].max()) <= kth * 1.01
+
+
+def test_ranking_loss_gemm_path_matches_row_sweep_and_fp64():
+    """Q >= 64 queries of one category: the dot products of RankingLoss come from ONE contraction on the fp32-parity tensor-core
+    engine (codae_linear_fwd_x3 + codae_rank_count) instead of one warp sweep per query (metering.py:46-79 runs for every
+    validation batch, train_dae_on_embedding.py:241-261).  Ranks are counts of strict fp32 comparisons: they must equal an fp64
+    ranking wherever no pair of cosines is within fp32 noise, and agree with the row-sweep kernel."""
+    from codae.dataset import ConcatenatedEmbeddingDataset
+    from codae.tool import RankingLoss
+    torch.manual_seed(21)
+    N, E, S, B = 6000, 128, 3, 384
+    cats = [torch.randn(N, E) for _ in range(S)]
+    ds = ConcatenatedEmbeddingDataset.from_tensors(cats)
+    ds.to(DEV)
+    val = list(range(1000, 5000))
+    idx = torch.randperm(4000)[:B] + 1000                       # true items inside the validation subset
+    idx[::7] = torch.randint(0, 1000, (len(idx[::7]),))         # ... and some outside it
+    cat_of = torch.arange(B) % S
+    cat_of[:6] = 0                                              # category 0: 132 queries (>= 128: GEMM path), the others 126 (row sweep)
+    pred = torch.randn(B, S * E)
+    for i in range(B):                                          # prediction near the true item so ranks are spread, not all ~n/2
+        c = int(cat_of[i])
+        pred[i, c * E:(c + 1) * E] = ds.data_per_category[c][idx[i]].cpu() * (0.3 * torch.rand(1)) + torch.randn(E)
+    fmask = torch.ones(B, S * E)
+    for i in range(B):
+        fmask[i, int(cat_of[i]) * E:(int(cat_of[i]) + 1) * E] = 0
+    pred_d, fmask_d = pred.to(DEV), fmask.to(DEV)
+    rl_gemm = RankingLoss(ds, val, device=DEV)
+    rl_gemm.GEMM_MIN_Q = 128
+    rl_sweep = RankingLoss(ds, val, device=DEV)
+    rl_sweep.GEMM_MIN_Q = 1 << 30
+    r_gemm = rl_gemm.ranks(pred_d, fmask_d, idx).cpu()
+    r_sweep = rl_sweep.ranks(pred_d, fmask_d, idx).cpu()
+    assert 0 in rl_gemm._gemm and 1 not in rl_gemm._gemm        # category 0 went through the contraction, the others did not
+    # fp64 ranking with a margin: pairs closer than 1e-6 may fall either way in fp32
+    lo, hi = torch.zeros(B, dtype=torch.int64), torch.zeros(B, dtype=torch.int64)
+    v = torch.tensor(val)
+    for i in range(B):
+        c = int(cat_of[i])
+        cat = ds.data_per_category[c].cpu().double()
+        qv = pred[i, c * E:(c + 1) * E].double()
+        cos = (cat @ qv) / (cat.norm(dim=1) * qv.norm()).clamp_min(1e-8)
+        st = cos[idx[i]]
+        lo[i] = int((st > cos[v] + 1e-6).sum())
+        hi[i] = int((st > cos[v] - 1e-6).sum())
+    assert bool(((r_gemm >= lo) & (r_gemm <= hi)).all()) and bool(((r_sweep >= lo) & (r_sweep <= hi)).all())
+    assert float((r_gemm == r_sweep).float().mean()) > 0.98 and int((r_gemm - r_sweep).abs().max()) <= 2
+    assert r_gemm.float().std() > 100                           # the ranks are spread out: the test is not vacuous
