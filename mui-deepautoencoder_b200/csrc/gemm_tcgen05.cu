@@ -38,7 +38,16 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int kMaxSplit = 8;     // portable cluster size limit
-constexpr int kChunkKb = 8;      // fp32-parity engine: k-blocks (of 64) accumulated in TMEM before the partial sum is folded into registers
+// fp32-parity engine: k-blocks (of 64) accumulated in TMEM before the partial sum is folded into registers (x3_chunk_kb():
+// tuning knob CODAE_X3_CHUNK_KB, read once)
+inline int x3_chunk_kb() {
+    static const int v = [] {
+        const char* e = getenv("CODAE_X3_CHUNK_KB");
+        const int x = e ? atoi(e) : 0;
+        return x >= 1 && x <= 64 ? x : 8;
+    }();
+    return v;
+}
 constexpr uint32_t kPersistentStageBytes = 4 * 2 * 4096;   // persistent kernel, bulk-store epilogue: 4 warps x 2 boxes of 32 rows x 128 B
 
 struct Params {
@@ -60,17 +69,18 @@ struct Params {
     unsigned long long* trace;   // debugging: CTA (0,0,0) writes %globaltimer stamps of its phases here (or NULL)
     int c_planes;                // NP == 3 only: 1 -> C is three bf16 planes (hi, mid, lo) c_plane_stride elements apart
     long long c_plane_stride;
+    int chunk_kb;                // NP == 3, CH: k-blocks per TMEM accumulation chunk
     int trace_cta;               // debugging: linear (y * gridDim.x + x) id of the CTA that writes the trace stamps
     int tmem_cols;               // TMEM columns this CTA allocates (NP == 3: 2 BN while one chunk covers the k-range, else 4 BN)
 };
 
 // NP = operand planes: 1 (bf16 engine) or 3 (fp32-parity engine, CODAE_F32X3: every operand is the bf16 triple hi + mid + lo of
 // an fp32 value; a stage holds [A_hi | A_mid | A_lo | B_hi | B_mid | B_lo]).  Six MMAs per k-step instead of one:
-//     hi.hi                         -> accumulator "big"   (TMEM columns [0, BN))
-//     hi.mid, mid.hi, mid.mid, hi.lo, lo.hi -> accumulator "small" (TMEM columns [BN, 2 BN)), everything <= 2^-8 of the big terms
-// and the epilogue adds the two.  Dropped terms (mid.lo, lo.mid, lo.lo) are <= 2^-24 of a product, the representation error of
-// the triple is 2^-24: the contraction has fp32-level accuracy (checked against the fp64 product in tests/test_host_logic.py
-// on the same arithmetic in numpy, and on the GPU against the oracle at 1e-5).
+//     hi.hi                                  -> one of NB accumulators "big" (round-robin over the k-steps, see x3_load_sum)
+//     hi.mid, mid.hi, mid.mid, hi.lo, lo.hi  -> accumulator "small", everything <= 2^-8 of the big terms
+// and the epilogue adds them.  Dropped terms (mid.lo, lo.mid, lo.lo) are <= 2^-24 of a product, the representation error of
+// the triple is 2^-24: measured against fp64 products of the same fp32 operands the contraction is as accurate as the FFMA engine
+// and torch's fp32 GEMM (1.6e-7 vs 6e-7 vs 1.3e-6 of max |result| at 128 x 1536 x 1536, tools/probes/x3_chunk_accuracy.py).
 template <int BN, int NP = 1>
 struct Cfg {
     static_assert(NP == 1 || (NP == 3 && BN <= 128), "three-plane stages of a 256-wide tile do not fit in shared memory");
@@ -78,8 +88,43 @@ struct Cfg {
     static constexpr uint32_t kStageBytes = NP * (kATileBytes + kBTileBytes);
     static constexpr int kStages = NP == 3 ? (BN == 128 ? 2 : 3) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-    static constexpr uint32_t kTmemCols = NP == 3 ? 4 * BN : BN;     // power of two >= 32; NP == 3: two sets of {big, small}
+    static constexpr uint32_t kTmemCols = NP == 3 ? 512 : BN;        // NP == 3: all columns -- one or two sets of NB + 1 accumulators
 };
+
+// fp32-parity engine: 32 columns of one TMEM accumulator set -> registers: ((big_0 + big_1) + ...) + small, round-to-nearest adds.
+// The "big" products (hi.hi) are dealt round-robin over nbig accumulators (k-step j -> accumulator j % nbig): TMEM accumulation
+// rounds TOWARD ZERO, a systematic error that grows with the number of MMA steps one accumulator takes and -- unlike
+// round-to-nearest noise -- adds up coherently from layer to layer (measured: forward error 3.7e-7 after layer 1 growing to
+// 1.2e-6 after layer 6 with one accumulator, where the FFMA engine stays at 4e-7).  nbig accumulators see 1/nbig of the steps each.
+// NB "big" accumulators per set (compile time): x3_nbig<BN, CH>() fills the 512 TMEM columns with one set (k-range within one
+// chunk) or two sets (chunked).
+template <int BN, bool CH>
+__host__ __device__ constexpr int x3_nbig() { return 512 / ((CH ? 2 : 1) * BN) - 1 > 4 ? 4 : 512 / ((CH ? 2 : 1) * BN) - 1; }
+template <int NB, bool kBatched>
+__device__ __forceinline__ void x3_load_sum(uint32_t taddr_set_chunk, int bn, uint32_t (&v)[32]) {
+    if constexpr (kBatched) {
+        // all NB + 1 loads in flight before the single tcgen05.wait::ld: one TMEM round trip per 32-column chunk
+        uint32_t u[NB][32];
+        tmem_ld32_nowait(taddr_set_chunk, v);
+#pragma unroll
+        for (int i = 1; i <= NB; ++i) tmem_ld32_nowait(taddr_set_chunk + (uint32_t)(i * bn), u[i - 1]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 1; i <= NB; ++i) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[i - 1][j]));
+        }
+    } else {
+        tmem_ld32(taddr_set_chunk, v);
+        uint32_t u[32];
+#pragma unroll
+        for (int i = 1; i <= NB; ++i) {                           // i == NB: the "small" accumulator
+            tmem_ld32(taddr_set_chunk + (uint32_t)(i * bn), u);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
+    }
+}
 
 // One operand tile per plane: plane pl lands plane_bytes after plane pl - 1.
 template <int NP>
@@ -203,13 +248,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                                                                 const __grid_constant__ CUtensorMap tma_c, const Params p) {
     using C = Cfg<BN, NP>;
     constexpr uint32_t kBOff = NP * kATileBytes;      // B planes follow the A planes of a stage
+    constexpr int NB = NP == 3 ? x3_nbig<BN, CH>() : 1;   // "big" accumulators per TMEM set (fp32-parity engine)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nstages = p.stages;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + nstages * C::kStageBytes);
     uint64_t* empty_bar = full_bar + nstages;
     uint64_t* tmem_full_bar = empty_bar + nstages;     // [2] (NP == 1 uses slot 0 only)
-    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] NP == 3: chunked accumulation, see kChunkKb
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2] NP == 3: chunked accumulation, see Params::chunk_kb
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
     constexpr int kStagePitch = BN + 4;               // floats per row of the staged fp32 tile
     __shared__ double sq_red[4];
@@ -318,10 +364,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                         umma_bf16(tmem_base, make_desc(a_addr + k * a_adv, p.a_kmajor != 0),
                                   make_desc(b_addr + k * b_adv, p.b_kmajor != 0), idesc, (kb | k) != 0);
                     } else {
-                        // chunked accumulation: k-blocks [ci kChunkKb, (ci + 1) kChunkKb) accumulate into TMEM set ci & 1 from
+                        // chunked accumulation: k-blocks [ci chunk_kb, (ci + 1) chunk_kb) accumulate into TMEM set ci & 1 from
                         // zero; the epilogue warps fold finished chunks into fp32 registers with round-to-nearest adds
-                        const int ci = CH ? kb / kChunkKb : 0, within = kb - ci * kChunkKb;
-                        const uint32_t d_big = tmem_base + (uint32_t)((ci & 1) * 2 * BN), d_small = d_big + BN;
+                        const int ci = CH ? kb / p.chunk_kb : 0, within = kb - ci * p.chunk_kb;
+                        const int step = within * (BK / UMMA_K) + k;                     // k-step inside the chunk
+                        const uint32_t set_base = tmem_base + (uint32_t)((ci & 1) * (NB + 1) * BN);
+                        const uint32_t d_big = set_base + (uint32_t)((step % NB) * BN), d_small = set_base + (uint32_t)(NB * BN);
                         if (CH && within == 0 && k == 0) {
                             mbar_wait(&tmem_empty_bar[ci & 1], (((uint32_t)ci >> 1) & 1) ^ 1);     // set drained (first use: free)
                             tc_fence_after();
@@ -331,9 +379,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                                        al = make_desc(a_addr + 2 * kATileBytes + k * a_adv, ak);
                         const uint64_t bh = make_desc(b_addr + k * b_adv, bk), bm = make_desc(b_addr + C::kBTileBytes + k * b_adv, bk),
                                        bl = make_desc(b_addr + 2 * C::kBTileBytes + k * b_adv, bk);
-                        const uint32_t first = (within | k) != 0;
-                        umma_bf16(d_big, ah, bh, idesc, first);                     // big
-                        umma_bf16(d_small, ah, bm, idesc, first);                   // small: five terms <= 2^-8 of the big one
+                        umma_bf16(d_big, ah, bh, idesc, step >= NB);              // big: the first use of an accumulator overwrites
+                        umma_bf16(d_small, ah, bm, idesc, step != 0);               // small: five terms <= 2^-8 of the big one
                         umma_bf16(d_small, am, bh, idesc, 1);
                         umma_bf16(d_small, am, bm, idesc, 1);
                         umma_bf16(d_small, ah, bl, idesc, 1);
@@ -342,10 +389,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
                 }
                 umma_commit(&empty_bar[s]);          // slot reusable once these MMAs have read it
                 if constexpr (NP == 3 && CH) {
-                    if ((kb + 1) % kChunkKb == 0 && kb + 1 < num_kb) umma_commit(&tmem_full_bar[(kb / kChunkKb) & 1]);   // chunk complete
+                    if ((kb + 1) % p.chunk_kb == 0 && kb + 1 < num_kb) umma_commit(&tmem_full_bar[(kb / p.chunk_kb) & 1]);   // chunk complete
                 }
             }
-            umma_commit(&tmem_full_bar[(NP == 3 && CH) ? ((num_kb - 1) / kChunkKb) & 1 : 0]);      // accumulator complete
+            umma_commit(&tmem_full_bar[(NP == 3 && CH) ? ((num_kb - 1) / p.chunk_kb) & 1 : 0]);      // accumulator complete
             trace_stamp(p, 4);                       // all MMAs issued
         }
     } else {
@@ -356,18 +403,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
         if constexpr (NP == 3 && CH) {
 #pragma unroll
             for (int j = 0; j < BN; ++j) racc[j] = 0.f;
-            const int nchunks = (num_kb + kChunkKb - 1) / kChunkKb;
+            const int nchunks = (num_kb + p.chunk_kb - 1) / p.chunk_kb;
             for (int ci = 0; ci + 1 < nchunks; ++ci) {
                 const int set = ci & 1;
                 mbar_wait(&tmem_full_bar[set], ((uint32_t)ci >> 1) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32], u[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 2 * BN + c * 32), v);
-                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * 2 * BN + BN + c * 32), u);
+                    uint32_t v[32];
+                    x3_load_sum<NB, false>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(set * (NB + 1) * BN + c * 32), BN, v);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(v[j]) + __uint_as_float(u[j]);
+                    for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(v[j]);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -375,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
             }
             const int last = nchunks - 1;
             mbar_wait(&tmem_full_bar[last & 1], ((uint32_t)last >> 1) & 1);
-            tmem_acc = tmem_base + (uint32_t)((last & 1) * 2 * BN);
+            tmem_acc = tmem_base + (uint32_t)((last & 1) * (NB + 1) * BN);
         } else {
             mbar_wait(tmem_full_bar, 0);
         }
@@ -423,14 +469,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_kernel(const __grid_con
             // last chunk: (big + small) + the running sum; fully unrolled, racc stays in registers
 #pragma unroll
             for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32], u[32];
-                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), v);
-                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN + c * 32), u);
+                uint32_t v[32];
+                x3_load_sum<NB, !CH>(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32), BN, v);
+                if constexpr (CH) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]) + __uint_as_float(u[j]);
-                    if constexpr (CH) x += racc[c * 32 + j];
-                    v[j] = __float_as_uint(x);
+                    for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + racc[c * 32 + j]);
                 }
                 emit(c, v);
             }
@@ -935,14 +978,14 @@ Plan make_plan(const codae_ctx* ctx, const Tc05Gemm& g) {
         while (nsplit > 1) {
             const int kb_per = (total_kb + nsplit - 1) / nsplit;
             const int st = kb_per < C3::kStages ? kb_per : C3::kStages;
-            const int fit = kb_per > kChunkKb ? x3_max_clusters<BN, true>(nsplit, smem_for(st)) : x3_max_clusters<BN, false>(nsplit, smem_for(st));
+            const int fit = kb_per > x3_chunk_kb() ? x3_max_clusters<BN, true>(nsplit, smem_for(st)) : x3_max_clusters<BN, false>(nsplit, smem_for(st));
             if (fit >= tiles) break;
             int want = nsplit - 1;
             const int kb2 = (total_kb + want - 1) / want;
             nsplit = (total_kb + kb2 - 1) / kb2;
         }
         const int kb_per = (total_kb + nsplit - 1) / nsplit;
-        pl.tmem_cols = kb_per > kChunkKb ? 4 * BN : 2 * BN;
+        pl.tmem_cols = 512;       // one set of NB + 1 accumulators, or two sets when the k-range is chunked (x3_nbig)
         const int st = kb_per < C3::kStages ? kb_per : C3::kStages;
         pl.stages = st;
     }
@@ -1071,7 +1114,8 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
-    const bool chunked = NP == 3 && kb_per_cta > kChunkKb;
+    const bool chunked = NP == 3 && kb_per_cta > x3_chunk_kb();
+    p.chunk_kb = x3_chunk_kb();
     static const bool debug_plan = getenv("CODAE_DEBUG_PLAN") != nullptr;
     if (debug_plan) {
         int occ = -1;
