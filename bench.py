@@ -301,6 +301,21 @@ def train_block(name, dtype, K, Wm, args, env, e2e=True):
                       "h2d_bytes_per_step": B * io * 4 + B * table.shape[1] * 2, "d2h_bytes_per_step": 32, "steps": Ke,
                       "api": "codae.tool.FusedStep.step(staged=(rows, mask_table_rows))"}
         del host_rows, host_tab, st_rows, st_tab
+        if B <= 1024 and world == 1:
+            # the scripts' own loop for a RESIDENT dataset (train_dae_on_embedding.py --graph): FusedStep.train_epoch -- permutation
+            # drawn on the device, 32 steps per CUDA-graph launch, one monitor read-back per epoch.  Wall clock around whole epochs.
+            rows = torch.arange(w["N"], dtype=torch.int64, device=dev)
+            gen = torch.Generator(device=dev)
+            gen.manual_seed(w["seed"])
+            fs.train_epoch(rows[:64 * B], B, generator=gen)             # captures the 32-step graph
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            n_steps = fs.train_epoch(rows, B, generator=gen)
+            mon = fs.read_monitors()                                   # the epoch's one device->host read
+            dt_epoch = time.perf_counter() - t0
+            out["epoch_mode"] = {"value": n_steps * B / dt_epoch, "unit": "samples/s", "steps": n_steps, "ms_per_step": 1e3 * dt_epoch / n_steps,
+                                 "api": "codae.tool.FusedStep.train_epoch (device sampler, 32 steps per graph launch)",
+                                 "h2d_bytes_per_step": 0, "d2h_bytes_per_epoch": 32, "rows_seen": mon["rows"]}
 
     # ---- per-kernel durations inside a real step (CUDA events on the launch stream) -> roofline ----------------------
     prof = profile_step(fs, batches[0], B, world, name)      # every rank: the steps inside contain the collective
@@ -489,7 +504,7 @@ def main():
                                ("modanet_merge_top_bottom_shoe.yaml bf16", "modanet", "bf16")):
             try:
                 blk, _ = train_block(name, dt_, 500, 30, args, env, e2e=True)
-                keep = ("value", "unit", "ms_per_step", "dtype", "engine", "config", "e2e", "roofline", "step_vs_floor", "kernels",
+                keep = ("value", "unit", "ms_per_step", "dtype", "engine", "config", "e2e", "epoch_mode", "roofline", "step_vs_floor", "kernels",
                         "gpu_launches", "steps", "warmup", "loss_last_step", "dp_mode")
                 sec[tag] = {k: blk[k] for k in keep if k in blk}
             except Exception as ex:      # the primary line is the contract: report, do not lose the run
@@ -641,7 +656,8 @@ def profile_step(fs, idx, B, world, name):
             ach, peak, unit = work / sec / 1e9, pk["hbm"], "GB/s"
         else:
             ach, peak, unit = work / sec / 1e12, tensor_peak, "TFLOP/s"
-        rooflines[n] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak, "traffic": None,
+        rooflines[n] = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                        "traffic": measured_traffic("%s_%s_%s" % (name, "bf16" if bf else ("fp32x3" if x3 else "fp32"), n)),
                         "kernel": n, "share_of_step": kernels[n]["share"], "peak_source": pk["src"],
                         "algorithmic_per_launch": work / kernels[n]["launches_per_step"]}
     # the dominant KERNEL: the three contractions are one kernel (tc05_gemm_kernel / simt_gemm_kernel)

@@ -92,6 +92,8 @@ class TinyLayer(ctypes.Structure):
 
 
 TINY_MAX_LAYERS = 8
+MIXED_MAX_VARIABLES = 64      # csrc/loss.cu: kMaxVar (variables per row, categories per classification variable)
+MIXED_MAX_CATEGORIES = 64
 
 _lib = None
 _lock = threading.RLock()   # re-entrant: ctx() loads the library under the same lock

@@ -19,7 +19,7 @@ class MixedVariableDataset(Dataset):
         for i, column in enumerate(pd_dataset):
             dtype = str(pd_dataset.dtypes.iloc[i])
             var = {"name": column, "lambda": 1}
-            if dtype in ("float64", "int64", "float32", "int32"):
+            if dtype in ("float64", "int64"):          # exactly the reference's rule (mixed_variable_dataset.py:34)
                 var["size"], var["type"] = 1, "regression"
             else:
                 var["size"], var["type"] = int(pd_dataset[column].nunique()), "classification"

@@ -198,6 +198,13 @@ class FlatMLP(torch.nn.Module):
         self.sync_weights()
         return super().state_dict(*args, **kwargs)
 
+    def load_state_dict(self, *args, **kwargs):
+        """Loads into the flat buffer (the Parameters are views of it) and rewrites the copy the tensor-core GEMMs read."""
+        out = super().load_state_dict(*args, **kwargs)
+        if self.flat is not None and (self.flat_bf16 is not None or self.flat_x3 is not None):
+            self.refresh_shadow()
+        return out
+
     def _require_cuda(self):
         self.sync_weights()
         if self.flat is None:

@@ -131,6 +131,11 @@ class Corrupter:
             subsets.extend(s)
         self.nb_run = sum(self.nb_corruption_per_k)
         self.subsets = subsets
+        # the device mask-id table is int16 and the kernels keep one 64-bit word of variables per mask
+        if self.nb_run > 32767:
+            raise Exception("Too many corruption subsets (%d): the device mask table holds ids up to 32767." % self.nb_run)
+        if self.nb_predictor > 64:
+            raise Exception("Too many variables (%d): the corruption kernels support at most 64." % self.nb_predictor)
 
         self.binary_masks = torch.ones((max(self.nb_run, 0), self.io_size))
         for r, sub in enumerate(subsets):

@@ -60,6 +60,7 @@ class FusedStep:
         self.dev = dev
         self.io = model.dims[0][0]
         self.eng = model.engine_dtype()
+        self._compute_dtype = model.compute_dtype      # buffers and the weight shadow are built for this engine: see _check_engine
         self.adt = model.act_dtype(self.eng)       # torch.float32 / torch.bfloat16 / "x3" (three bf16 planes per fp32 tensor)
         self.tc = self.eng != _C.F32               # a tensor-core engine (bf16, or fp32 parity on bf16 triples)
         n = model.flat.numel()
@@ -378,11 +379,17 @@ class FusedStep:
                 dist.all_reduce(self.gflat, op=dist.ReduceOp.SUM, group=self.pg)
         self.kernel_launches = self._enqueue_update()
 
+    def _check_engine(self):
+        if self.model.compute_dtype != self._compute_dtype:
+            raise RuntimeError("codae: model.set_compute_dtype(%r) after this FusedStep was built for %r; build a new FusedStep"
+                               % (self.model.compute_dtype, self._compute_dtype))
+
     # ---- public API ------------------------------------------------------------------------------------------
     def step(self, batch_idx, run=0, global_batch=None, staged=None):
         """One training step on observations `batch_idx` (int64 CUDA tensor [B]).
         staged=(rows [B, io] f32, table_rows [B, nb_run] i16): host-staged batch (end-to-end path): the kernels
         then read the staged rows instead of gathering from the resident dataset."""
+        self._check_engine()
         B = int(batch_idx.numel()) if staged is None else int(staged[0].shape[0])
         gb = B * self.world_size if global_batch is None else global_batch
         if B == 0:
@@ -485,6 +492,7 @@ class FusedStep:
         """Validation pass: corruption + forward + monitor sums only (train_dae_on_embedding.py:241-259),
         without building any autograd state.  Returns the reconstruction [B, io] (device, fp32).  Reads the weight buffer the
         GEMMs use, which is complete on every rank after every step (no master-weight gather needed)."""
+        self._check_engine()
         B = int(batch_idx.numel())
         b = self._buffers(B)
         b["idx"].copy_(batch_idx, non_blocking=True)

@@ -13,6 +13,10 @@ def get_rmse(x, y):
 
 def arch_tables(arch, device):
     """(var_pos, var_size, var_type) int32 device tensors of an `arch` list."""
+    if len(arch) > _C.MIXED_MAX_VARIABLES or any(int(v["size"]) > _C.MIXED_MAX_CATEGORIES for v in arch):
+        # the tabular loss / monitor kernels keep one variable's logits in registers (csrc/loss.cu: kMaxVar)
+        raise Exception("The tabular loss kernels support at most %d variables of at most %d categories each."
+                        % (_C.MIXED_MAX_VARIABLES, _C.MIXED_MAX_CATEGORIES))
     pos = torch.tensor([v["position"] for v in arch], dtype=torch.int32, device=device)
     size = torch.tensor([v["size"] for v in arch], dtype=torch.int32, device=device)
     typ = torch.tensor([_C.VAR_REGRESSION if v["type"] == "regression" else _C.VAR_CLASSIFICATION for v in arch],

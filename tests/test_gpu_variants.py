@@ -139,3 +139,44 @@ print("TINY OK")
 ''' % (HERE, HERE, HERE, name)
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
     assert r.returncode == 0 and "TINY OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_load_state_dict_refreshes_the_weight_shadow_and_engine_changes_are_refused(dtype):
+    """The tensor-core GEMMs read a copy of the weights (bf16, or the three planes of the fp32-parity engine): loading a
+    checkpoint must rewrite it, and switching the engine under a live FusedStep must fail loudly."""
+    from codae import _C
+    from codae.dataset import ConcatenatedEmbeddingDataset
+    from codae.model import EmbeddingDenoisingAutoencoder
+    from codae.tool import Corrupter, FusedStep
+    torch.manual_seed(2)
+    S, E, N, B = 3, 64, 256, 32
+    ds = ConcatenatedEmbeddingDataset.from_tensors([torch.randn(N, E).abs() for _ in range(S)])
+    donor = EmbeddingDenoisingAutoencoder(S * E, S * E, E, 2, 2, False)
+    sd = {k: v.clone() for k, v in donor.state_dict().items()}
+    out = []
+    for load_after in (False, True):
+        torch.manual_seed(3)
+        m = EmbeddingDenoisingAutoencoder(S * E, S * E, E, 2, 2, False)
+        if not load_after:
+            m.load_state_dict(sd)
+        m.set_compute_dtype(dtype).to(DEV)
+        if load_after:
+            ds.to(DEV)
+        cor = Corrupter(N, ds.arch, 1, DEV, seed=4)
+        fs = FusedStep(m, cor, ds.data.to(DEV), lr=1e-3, weight_decay=0.0, clip=True)
+        if load_after:
+            m.load_state_dict(sd)                        # after the FusedStep (and its shadow) exist
+        shadow = m.gemm_weights()
+        if dtype == "bf16":
+            assert torch.equal(shadow.view(torch.int16), m.flat.to(torch.bfloat16).view(torch.int16))
+        else:
+            want = torch.empty_like(shadow)
+            _C.split_x3(m.flat, want)
+            assert torch.equal(shadow.view(torch.int16), want.view(torch.int16))
+        fs.step(torch.arange(B, device=DEV))
+        out.append((fs.last_loss(B), m.flat.clone()))
+    assert out[0][0] == out[1][0] and torch.equal(out[0][1], out[1][1])
+    m.set_compute_dtype("fp32_simt")
+    with pytest.raises(RuntimeError, match="build a new FusedStep"):
+        fs.step(torch.arange(B, device=DEV))

@@ -176,3 +176,40 @@ def test_yaml_configs_keep_the_reference_schema():
     assert set(aba) == {"MODEL", "DATASET", "SEED", "EVALUATION", "PLOT"}
     poly = yaml.safe_load(open(os.path.join(cfg, "polyvore_multislot.yaml")))
     assert set(poly["MODEL"]) >= set(emb["MODEL"]) and len(poly["DATASET"]["USED_CATEGORY"]) == 8
+
+
+def test_corrupter_refuses_what_the_device_tables_cannot_hold():
+    """The device mask-id table is int16 and a mask is one 64-bit word of variables: sizes beyond that must fail loudly
+    (the reference has no such limits; silently wrapping ids would corrupt rows out of bounds)."""
+    arch = [dict(name=str(i), size=1, type="regression", position=i) for i in range(65)]
+    with pytest.raises(Exception, match="at most 64"):
+        Corrupter(4, arch, 1, torch.device("cpu"))
+    arch = [dict(name=str(i), size=1, type="regression", position=i) for i in range(60)]
+    with pytest.raises(Exception, match="32767"):
+        Corrupter(4, arch, 3, torch.device("cpu"))          # 60 + 1770 + 34220 subsets
+    Corrupter(4, arch, 2, torch.device("cpu"))              # 1830 subsets: fine
+
+
+def test_split3_arithmetic_matches_fp32_to_2_pow_minus_24():
+    """The three-plane format of the fp32-parity engine, in numpy: hi + mid + lo reproduces x to 2^-24 |x|, and the six products
+    the kernel keeps (hh | hm, mh, mm, hl, lh) give an fp32-accurate contraction where plain bf16 is 2e-3 off."""
+    rng = np.random.RandomState(0)
+
+    def bf16(a):
+        u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
+        u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16                  # round to nearest even
+        return u.astype(np.uint32).view(np.float32)
+
+    def split(a):
+        h = bf16(a)
+        m = bf16(a - h)
+        return h, m, bf16(a - h - m)
+    x = (rng.randn(4096) * 10.0 ** rng.randint(-6, 6, 4096)).astype(np.float32)
+    h, m, l = split(x)
+    assert np.all(np.abs(h.astype(np.float64) + m + l - x) <= np.abs(x) * 2.0 ** -24)
+    A, B = rng.randn(64, 512).astype(np.float32), (rng.randn(48, 512) / 22).astype(np.float32)
+    (ah, am, al), (bh, bm, bl) = split(A), split(B)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    x3 = ah @ bh.T + (ah @ bm.T + am @ bh.T + am @ bm.T + ah @ bl.T + al @ bh.T)
+    err = lambda y: np.abs(y - ref).max() / np.abs(ref).max()
+    assert err(x3) < 1e-6 and err(A @ B.T) < 1e-6 and err(ah @ bh.T) > 1e-4

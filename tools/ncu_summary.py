@@ -36,13 +36,15 @@ def summarise(path):
 
 
 def traffic(pairs):
-    """--traffic key=report.ncu-rep[:kernel-substring] ... -> JSON {key: {bytes_per_launch, launches, kernels, read, write, source}}:
+    """--traffic key=report.ncu-rep[:kernel-substring][#i,j] ... -> JSON {key: {bytes_per_launch, launches, kernels, read, write, source}}:
     mean dram__bytes_read.sum + dram__bytes_write.sum per captured launch (bench.py reads it as roofline.traffic)."""
     import json
     out = {}
     for pair in pairs:
         key, rest = pair.split("=", 1)
+        rest, _, picks = rest.partition("#")                  # optional "#0,2": launch indices (capture order) to average over
         path, _, sub = rest.partition(":")
+        picks = [int(x) for x in picks.split(",")] if picks else None
         res = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True)
         if res.returncode != 0:
             continue
@@ -51,8 +53,8 @@ def traffic(pairs):
         col = {name: i for i, name in enumerate(header)}
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         rd, wr, names = [], [], []
-        for r in body:
-            if sub and sub not in r[col["Kernel Name"]]:
+        for li, r in enumerate(body):
+            if (sub and sub not in r[col["Kernel Name"]]) or (picks is not None and li not in picks):
                 continue
             ur, uw = units[col["dram__bytes_read.sum"]], units[col["dram__bytes_write.sum"]]
             rd.append(float(r[col["dram__bytes_read.sum"]].replace(",", "")) * scale.get(ur, 1.0))
