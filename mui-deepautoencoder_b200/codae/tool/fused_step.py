@@ -424,11 +424,55 @@ class FusedStep:
             self._graphs[key] = gr
         gr.replay()
 
+    def train_steps(self, idx_rows, run=0, global_batch=None, graph_steps=32):
+        """n consecutive training steps, idx_rows: int64 CUDA tensor [n, B] (row j = the observations of step j).  Chunks of
+        `graph_steps` steps are ONE CUDA-graph launch each (no per-step Python call, no per-step index copy); the remainder runs
+        through step().  Same kernels on the same values as step(): bit-identical weights and monitors.
+        (Measured and rejected on a B200, profiles/r02_notes.md visit 8: running the optimizer update of step s beside the forward
+        pass of step s + 1 inside these graphs, each forward GEMM gated on per-layer completion flags of the update.)"""
+        self._check_engine()
+        n, Bl = int(idx_rows.shape[0]), int(idx_rows.shape[1])
+        gb = Bl * self.world_size if global_batch is None else global_batch
+        s = 0
+        if n and not self._calls.get(("epoch_warm", Bl)):
+            # the first step of a batch size runs eagerly (lazy attribute setup) -- it is a real step
+            self._calls[("epoch_warm", Bl)] = 1
+            saved, self.use_graph = self.use_graph, False
+            try:
+                self.step(idx_rows[0], run=run, global_batch=gb)
+            finally:
+                self.use_graph = saved
+            s = 1
+        K = max(1, int(graph_steps))
+        b = self._buffers(Bl)
+        table = self.corrupter.device_tables()[0]
+        while n - s >= K:
+            key = ("steps", Bl, run, gb, K)
+            ent = self._graphs.get(key)
+            if ent is None:
+                win = torch.zeros((K, Bl), dtype=torch.int64, device=self.dev)
+                win.copy_(idx_rows[s:s + K])
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    for j in range(K):
+                        self.kernel_launches = self._enqueue(Bl, b, run, gb, self.data, win[j], table)
+                ent = (gr, win)
+                self._graphs[key] = ent
+            gr, win = ent
+            win.copy_(idx_rows[s:s + K], non_blocking=True)
+            gr.replay()
+            self.step_count += K
+            s += K
+        for j in range(s, n):
+            self.step(idx_rows[j], run=run, global_batch=gb)
+        return n
+
     def train_epoch(self, train_idx, batch_size, generator=None, rank=0, run=0, graph_steps=32):
         """One epoch with the sampler on the device (train_dae_on_embedding.py:118-128: SubsetRandomSampler + DataLoader(batch_size),
         i.e. a fresh permutation of the training observations, consecutive batches, ragged last batch): the permutation is drawn
-        on the GPU, the per-step index rows live in one static window buffer and `graph_steps` consecutive steps are ONE CUDA
-        graph launch -- no per-step Python call, no per-step host->device index copy.
+        on the GPU and the full batches go through train_steps() -- `graph_steps` consecutive steps per CUDA-graph launch, no
+        per-step Python call, no per-step host->device index copy.
         train_idx: int64 CUDA tensor of observation ids; batch_size: GLOBAL batch (data parallel: every rank draws the same
         permutation from an identically seeded `generator` and takes rows rank::world_size of each batch, as the host sampler
         of script/_common.py does).  Returns the number of steps taken."""
@@ -440,40 +484,7 @@ class FusedStep:
         if n_full:
             Bl = batch_size // W
             local = perm[:n_full * batch_size].view(n_full, Bl, W)[:, :, rank].contiguous()      # g[rank::world] of every batch
-            s = 0
-            if not self._calls.get(("epoch_warm", Bl)):
-                # the first step of a batch size runs eagerly (lazy attribute setup) -- it is a real step of the epoch
-                self._calls[("epoch_warm", Bl)] = 1
-                saved, self.use_graph = self.use_graph, False
-                try:
-                    self.step(local[0], run=run, global_batch=batch_size)
-                finally:
-                    self.use_graph = saved
-                s = 1
-            K = max(1, int(graph_steps))
-            b = self._buffers(Bl)
-            table = self.corrupter.device_tables()[0]
-            while n_full - s >= K:
-                key = ("epoch", Bl, run, batch_size, K)
-                ent = self._graphs.get(key)
-                if ent is None:
-                    win = torch.zeros((K, Bl), dtype=torch.int64, device=dev)
-                    win.copy_(local[s:s + K])
-                    torch.cuda.synchronize()
-                    gr = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(gr):
-                        for j in range(K):
-                            self.kernel_launches = self._enqueue(Bl, b, run, batch_size, self.data, win[j], table)
-                    ent = (gr, win)
-                    self._graphs[key] = ent
-                gr, win = ent
-                win.copy_(local[s:s + K], non_blocking=True)
-                gr.replay()
-                self.step_count += K
-                s += K
-            for j in range(s, n_full):
-                self.step(local[j], run=run, global_batch=batch_size)
-            steps = n_full
+            steps = self.train_steps(local, run=run, global_batch=batch_size, graph_steps=graph_steps)
         # ragged tail (or a global batch the ranks cannot split evenly): the per-step path
         for lo in range(n_full * batch_size, n, batch_size):
             g = perm[lo:lo + batch_size]

@@ -457,3 +457,40 @@ def test_train_epoch_device_sampler_matches_step_loop(dtype):
     assert torch.equal(out["epoch"][3], out["loop"][3])
     for k in ("full", "partial", "rows"):
         assert out["epoch"][1][k] == out["loop"][1][k]
+
+
+@pytest.mark.parametrize("dtype,B", [("bf16", 128), ("fp32", 128), ("bf16", 2048)])
+def test_multi_step_graphs_are_bit_identical_to_the_step_loop(dtype, B):
+    """FusedStep.train_steps: chunks of graph_steps consecutive steps as ONE CUDA-graph launch each, at embedding.yaml's layer
+    width.  Same kernels, same values, same order per buffer => weights, moments, the weight copy the GEMMs read and the monitors
+    must equal the one-step-at-a-time loop exactly, replay after replay."""
+    from codae.dataset import ConcatenatedEmbeddingDataset
+    from codae.model import EmbeddingDenoisingAutoencoder
+    from codae.tool import Corrupter, FusedStep
+    S, E, N = 3, 512, 4096
+    torch.manual_seed(5)
+    cats = [torch.randn(N, E).abs() * (torch.rand(N, E) < 0.7) for _ in range(S)]
+    rows = torch.stack([torch.randperm(N)[:B] for _ in range(13)]).to(DEV)          # 13 steps: 1 eager + 3 graphs of 4
+    out = {}
+    for mode in ("graphs", "loop"):
+        torch.manual_seed(6)
+        ds = ConcatenatedEmbeddingDataset.from_tensors(cats)
+        model = EmbeddingDenoisingAutoencoder(S * E, S * E, E, 2, 2, False)           # 6 x Linear(1536, 1536)
+        model.set_compute_dtype(dtype)
+        model.to(DEV)
+        ds.to(DEV)
+        cor = Corrupter(N, ds.arch, 1, DEV, seed=9)
+        fs = FusedStep(model, cor, ds.data, lr=1e-4, weight_decay=1e-4, clip=True, use_graph=False)
+        if mode == "graphs":
+            assert fs.train_steps(rows, graph_steps=4) == 13
+            assert any(k[0] == "steps" for k in fs._graphs)
+        else:
+            for j in range(13):
+                fs.step(rows[j])
+        torch.cuda.synchronize()
+        out[mode] = (model.flat.clone(), fs.m.clone(), fs.v.clone(), fs.read_monitors(), model.gemm_weights().clone())
+    a, b = out["graphs"], out["loop"]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert torch.equal(a[4].view(torch.int16), b[4].view(torch.int16))
+    for k in ("full", "partial", "rows", "last_sum"):
+        assert a[3][k] == b[3][k], k
