@@ -1,5 +1,6 @@
-"""Probe: polyvore-shaped steps (10 x 4096^2, B = 8192) through FusedStep.train_steps -- multi-step CUDA graphs with (CODAE_PIPELINE=1)
-or without (=0) the optimizer update of step s running beside the forward pass of step s + 1."""
+"""Probe: polyvore-shaped steps (10 x 4096^2, B = 8192) through FusedStep.train_steps (multi-step CUDA graphs).  This was the harness
+of the pipelining experiment of visit 8 (optimizer update of step s beside the forward pass of step s + 1; CODAE_PIPELINE selected
+it): 7.31 ms/step without it, a trap in the bounded gate wait with it -- the variant is removed, the harness still times the graphs."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "mui-deepautoencoder_b200"))
