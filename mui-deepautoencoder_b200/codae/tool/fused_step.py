@@ -479,18 +479,31 @@ class FusedStep:
         dev, W = self.dev, self.world_size
         n = int(train_idx.numel())
         perm = train_idx[torch.randperm(n, device=dev, generator=generator)]
-        n_full = n // batch_size if batch_size % W == 0 else 0
+        local, tail = self.epoch_rows(perm, batch_size, W, rank)
         steps = 0
-        if n_full:
-            Bl = batch_size // W
-            local = perm[:n_full * batch_size].view(n_full, Bl, W)[:, :, rank].contiguous()      # g[rank::world] of every batch
+        if local is not None:
             steps = self.train_steps(local, run=run, global_batch=batch_size, graph_steps=graph_steps)
         # ragged tail (or a global batch the ranks cannot split evenly): the per-step path
-        for lo in range(n_full * batch_size, n, batch_size):
-            g = perm[lo:lo + batch_size]
-            self.step(g[rank::W], run=run, global_batch=int(g.numel()))
+        for rows, gb in tail:
+            self.step(rows, run=run, global_batch=gb)
             steps += 1
         return steps
+
+    @staticmethod
+    def epoch_rows(perm, batch_size, world_size=1, rank=0):
+        """Splits an epoch's permutation the way the host sampler does (script/_common.py: epoch_batches): consecutive global batches
+        of batch_size observations, rank r takes elements r::world_size of each.  Returns (local [n_full, batch_size // world_size]
+        or None, [(rows of this rank, global batch size)] for the batches that are ragged or not divisible by world_size)."""
+        n = int(perm.numel())
+        n_full = n // batch_size if batch_size % world_size == 0 else 0
+        local = None
+        if n_full:
+            local = perm[:n_full * batch_size].view(n_full, batch_size // world_size, world_size)[:, :, rank].contiguous()
+        tail = []
+        for lo in range(n_full * batch_size, n, batch_size):
+            g = perm[lo:lo + batch_size]
+            tail.append((g[rank::world_size], int(g.numel())))
+        return local, tail
 
     def flush(self):
         """Makes model.flat (the fp32 master weights) current on this rank.  Single GPU and the NCCL all-reduce schedule: no-op

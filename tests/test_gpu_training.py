@@ -494,3 +494,59 @@ def test_multi_step_graphs_are_bit_identical_to_the_step_loop(dtype, B):
     assert torch.equal(a[4].view(torch.int16), b[4].view(torch.int16))
     for k in ("full", "partial", "rows", "last_sum"):
         assert a[3][k] == b[3][k], k
+
+
+def test_polyvore_sized_step_vs_oracle():
+    """The configuration bench.py's headline line runs -- polyvore-shaped DAE, 10 x Linear(4096, 4096), B = 8192, k_max = 2, bf16
+    tensor-core engine (persistent TMEM-double-buffered GEMMs, bulk-store epilogues, sum(dW^2) from the weight-gradient launches,
+    CUDA-graph replay) -- against the oracle on the same seeded inputs: loss and reconstruction within 1e-2 (BASELINE.json's bf16
+    tolerance), post-Adam weights within the largest possible Adam step.  Two steps: eager, then captured + replayed."""
+    from oracle import codae_oracle as O
+    from oracle.philox import philox_mask_table
+    from codae.dataset import ConcatenatedEmbeddingDataset
+    from codae.model import EmbeddingDenoisingAutoencoder
+    from codae.tool import Corrupter, FusedStep
+    torch.manual_seed(13)
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    S, E, N, B, lr, wd = 8, 512, 3 * 8192, 8192, 1e-5, 1e-4
+    cats = [torch.randn(N, E).abs() * (torch.rand(N, E) < 0.7) for _ in range(S)]
+    ds = ConcatenatedEmbeddingDataset.from_tensors(cats)
+    model = EmbeddingDenoisingAutoencoder(S * E, S * E, E, 4, 4, False)
+    assert len(model.dims) == 10 and all(d == (4096, 4096) for d in model.dims)
+    W = [l.weight.detach().clone() for l in model.linears()]
+    b = [l.bias.detach().clone() for l in model.linears()]
+    data_cpu = ds.data.clone()
+    model.set_compute_dtype("bf16")
+    model.to(DEV)
+    ds.to(DEV)
+    cor = Corrupter(N, ds.arch, 2, DEV, seed=31)
+    nb_run = S + S * (S - 1) // 2
+    tbl = torch.from_numpy(philox_mask_table(31, N, nb_run).astype(np.int64))
+    assert torch.equal(tbl, cor.mask_to_use)
+    fs = FusedStep(model, cor, ds.data, lr=lr, weight_decay=wd, clip=True, use_graph=True)
+    assert fs.eng == 1 and fs.wgrad_sqnorm
+    dae = O.OracleDAE(W, b, model.relu, lr, wd, True)
+    bm, nm, _ = O.binary_masks(ds.arch, 2)
+    perm = torch.randperm(N)
+    for s in range(3):                     # eager, captured, replayed
+        idx = perm[s * B:(s + 1) * B]
+        fs.step(idx.to(DEV), run=0)
+        _, fmask = O.get_masks(bm, nm, tbl, idx.tolist(), 0, 2)
+        r = dae.step_embedding(data_cpu[idx], fmask)
+        assert abs(fs.last_loss(B) - r["loss"]) <= 1e-2 * abs(r["loss"]), (s, fs.last_loss(B), r["loss"])
+        y = fs._bufs[B]["acts"][-1][:, :S * E]
+        assert rel(y.cpu().numpy(), r["y"].numpy()) < 1e-2, s
+        got = flat_params(model)
+        want = np.concatenate([t.numpy().ravel() for t in dae.params()])
+        dw = np.abs(got - want)
+        assert (dw <= 1e-2 * np.abs(want).max()).mean() > 0.98 and dw.max() <= 2.2 * lr / (1 - 0.9) + 1e-2 * np.abs(want).max(), s
+        # per-step parity: restart the oracle from the device state (as test_full_size_step_vs_oracle does)
+        with torch.no_grad():
+            for l in range(len(model.dims)):
+                dae.W[l].copy_(model.weight_view(model.flat, l).cpu())
+                dae.b[l].copy_(model.bias_view(model.flat, l).cpu())
+            for j, (mt, vt) in enumerate(zip(dae.m, dae.v)):
+                l, is_bias = j // 2, j % 2
+                view = model.bias_view if is_bias else model.weight_view
+                mt.copy_(view(fs.m, l).cpu())
+                vt.copy_(view(fs.v, l).cpu())

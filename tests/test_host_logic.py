@@ -213,3 +213,24 @@ def test_split3_arithmetic_matches_fp32_to_2_pow_minus_24():
     x3 = ah @ bh.T + (ah @ bm.T + am @ bh.T + am @ bm.T + ah @ bl.T + al @ bh.T)
     err = lambda y: np.abs(y - ref).max() / np.abs(ref).max()
     assert err(x3) < 1e-6 and err(A @ B.T) < 1e-6 and err(ah @ bh.T) > 1e-4
+
+
+@pytest.mark.parametrize("n,B,W", [(45, 16, 2), (64, 16, 4), (45, 15, 2), (7, 16, 2), (128, 32, 1)])
+def test_device_sampler_splits_an_epoch_like_the_host_sampler(n, B, W):
+    """FusedStep.epoch_rows (the slicing behind train_epoch's device-side sampler) == script/_common.epoch_batches on the same
+    permutation: consecutive global batches, rank r takes elements r::W, ragged / indivisible batches through the per-step path."""
+    from codae.tool import FusedStep
+    sys.path.insert(0, os.path.join(PKG, "script"))
+    from _common import epoch_batches
+    perm = torch.randperm(n) + 100
+
+    class FixedPerm:                      # epoch_batches draws rng.permutation(len(indices)): hand it the identity
+        @staticmethod
+        def permutation(k):
+            return np.arange(k)
+    for r in range(W):
+        want = [(list(loc), gb) for loc, gb in epoch_batches(perm.tolist(), B, FixedPerm, r, W)]
+        local, tail = FusedStep.epoch_rows(perm, B, W, r)
+        got = [] if local is None else [(row.tolist(), B) for row in local]
+        got += [(rows.tolist(), gb) for rows, gb in tail]
+        assert got == want
