@@ -478,6 +478,10 @@ class FusedStep:
         of script/_common.py does).  Returns the number of steps taken."""
         dev, W = self.dev, self.world_size
         n = int(train_idx.numel())
+        if n:
+            lo, hi = int(train_idx.min()), int(train_idx.max())       # one read-back per epoch: the kernels gather rows unchecked
+            if lo < 0 or hi >= self.data.shape[0]:
+                raise Exception("Observation index out of range: [%d, %d] for a dataset of %d rows." % (lo, hi, self.data.shape[0]))
         perm = train_idx[torch.randperm(n, device=dev, generator=generator)]
         local, tail = self.epoch_rows(perm, batch_size, W, rank)
         steps = 0

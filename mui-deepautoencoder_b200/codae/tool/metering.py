@@ -103,10 +103,15 @@ class RankingLoss:
             out[lo:lo + Q] = r
         return out
 
-    def get(self, prediction, fmask, indices):
+    def get_tensor(self, prediction, fmask, indices):
+        """sum_i 1 - rank_i / (|val| - 1) as a 0-dim float64 DEVICE tensor: a validation loop can accumulate it without a host
+        synchronisation per batch (the reference adds a Python float per sample, metering.py:76)."""
         ranks = self.ranks(prediction, fmask, indices)
         n = len(self.validation_indices)
-        return float((1 - ranks.double() / (n - 1)).sum().item())
+        return (1 - ranks.double() / (n - 1)).sum()
+
+    def get(self, prediction, fmask, indices):
+        return float(self.get_tensor(prediction, fmask, indices).item())
 
 
 class _MixedMeanLoss(torch.autograd.Function):

@@ -109,7 +109,7 @@ if __name__ == "__main__":
         book["ptl"].append(ptl)
 
         trainer.reset_monitors()
-        rl = 0.0
+        rl = torch.zeros((), dtype=torch.float64, device=device)       # accumulated on the device: one read-back per epoch
         for local_idx, _ in epoch_batches(validation_indices, B, rng, rank, world):
             if len(local_idx) == 0:
                 continue
@@ -117,9 +117,9 @@ if __name__ == "__main__":
             out = trainer.evaluate(idx, run=0)
             if args.rank and args.nb_missing == 1:
                 _, fmask = corrupter.get_masks(idx, 0)
-                rl += ranking_loss.get(out, fmask, idx)
+                rl += ranking_loss.get_tensor(out, fmask, idx)
         mon = trainer.read_monitors()
-        acc = torch.tensor([mon["full"], mon["partial"], rl], dtype=torch.float64, device=device)
+        acc = torch.cat([torch.tensor([mon["full"], mon["partial"]], dtype=torch.float64, device=device), rl.view(1)])
         if world > 1:
             torch.distributed.all_reduce(acc)
         fvl = math.sqrt(acc[0].item() / (dataset.nb_predictor * nb_validation))

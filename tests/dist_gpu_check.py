@@ -115,6 +115,34 @@ for mode, dtype, graph, tol, z in CASES:
         m._flush_hook = None
         del fs, fs1
 
+# device sampler + multi-step CUDA graphs under data parallelism: every rank draws the same permutation and takes rows rank::world
+for dtype, tol in (("bf16", 1e-2), ("fp32", 1e-5)):
+    GB = 16 * world
+    n_train = GB * 7 + 5                     # 7 full global batches (1 eager + one graph of 4 + 2 single steps) + a ragged one; <= 1021 rows
+    assert 3 + n_train <= 1024
+    train_idx = torch.arange(3, 3 + n_train, dtype=torch.int64, device=dev)
+    ds, m, cor, fs = build(dtype, world, False, True, "peer")
+    gen = torch.Generator(device=dev); gen.manual_seed(123)
+    steps = fs.train_epoch(train_idx, GB, generator=gen, rank=rank, graph_steps=4)
+    fs.flush()
+    w_dp = flat(m)
+    gathered = [torch.empty_like(w_dp) for _ in range(world)]
+    dist.all_gather(gathered, w_dp)
+    replicas_equal = all(torch.equal(g, gathered[0]) for g in gathered)
+    ds1, m1, cor1, fs1 = build(dtype, 1, False)
+    gen1 = torch.Generator(device=dev); gen1.manual_seed(123)
+    steps1 = fs1.train_epoch(train_idx, GB, generator=gen1, graph_steps=4)
+    dw = (w_dp - flat(m1)).abs()
+    err = float(dw.max() / flat(m1).abs().max())
+    frac_off = float((dw > tol * flat(m1).abs().max()).float().mean())
+    good = replicas_equal and steps == steps1 == 8 and (err < tol or (frac_off < 0.10 and float(dw.max()) <= 10 * 2.2 * 1e-3))
+    ok &= good
+    if rank == 0:
+        print("DP train_epoch (device sampler, 4-step graphs) %s: steps=%d replicas_bitwise_equal=%s |w_dp - w_1|/|w| = %.2e (%.2f %% beyond tol) -> %s"
+              % (dtype, steps, replicas_equal, err, 100 * frac_off, "OK" if good else "FAIL"), flush=True)
+    m._flush_hook = None
+    del fs, fs1
+
 # sharded catalog
 torch.manual_seed(9)
 n, E, k = 200_003, 512, 10
