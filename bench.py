@@ -1,14 +1,16 @@
 """bench.py -- CODAE hot path on B200: train samples/s (headline) + candidate scores/s, with roofline and CPU baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload polyvore|embedding|modanet] [--dtype fp32|bf16]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload polyvore|embedding|modanet] [--dtype fp32|bf16|fp32_simt]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...   (one rank per GPU, NCCL)
   python bench.py --impl reference ...   the reference's own CPU implementation of the same step on the host cores (the
                                           unmodified reference classes from baseline/_ref; the oracle port if that is absent)
 
 Default workload: the polyvore-shaped multi-slot step (BASELINE.json configs[3]: 10 x Linear(4096, 4096), B = 8192 per GPU,
 bf16 tensor-core engine) -- the largest single-GPU training configuration and the one the tensor-pipe bar is written for.
-The shipped small-batch configs (embedding.yaml at fp32 AND bf16, the modanet yaml at bf16) and the 10 M-row scoring sweep
-are measured in the same run and reported as secondary blocks of the same JSON line (`secondary`, `scoring`).
+The shipped small-batch configs (embedding.yaml at fp32 -- the reference's precision, on the fp32-parity tensor-core engine --
+AND bf16, the modanet yaml at bf16) and the 10 M-row scoring sweep are measured in the same run and reported as secondary
+blocks of the same JSON line (`secondary`, `scoring`); each small-batch block also carries `epoch_mode`: the scripts' loop for
+a resident dataset (FusedStep.train_epoch: sampler on the device, 32 steps per CUDA-graph launch, wall clock around an epoch).
 
 A "step" is one pass of the training-step hot path over one batch of synthetic embeddings of the config's shape
 (corrupt -> encoder/decoder GEMMs -> loss -> backward GEMMs -> [all-reduce] -> clip -> Adam).  `value` is the
