@@ -95,14 +95,15 @@ int codae_mask_table_philox(codae_ctx* ctx, uint64_t seed, int64_t first_obs, in
  * (codae/tool/data_tool.py:96-103), Corrupter.get_masks (data_tool.py:239-262) and model.corrupt
  * (codae/model/embedding_denoising_autoencoder.py:226-239).
  *   data      [n_rows, ld_data] f32   resident dataset (ConcatenatedEmbeddingDataset.data)
- *   batch_idx [B] int64 or NULL       observation ids (NULL: observations 0..B-1)
+ *   batch_idx [B] int64 or NULL       observation ids (NULL: observations 0..B-1); an id outside [0, n_rows) traps the kernel
+ *                                     (launch failure) rather than gathering foreign memory -- the reference raises IndexError
  *   mask_table[n_rows, nb_run] int16  mask id of (observation, run)
  *   mask_bits [nb_run] u64            bit v set <=> variable v is zeroed by that mask (V <= 64)
  *   col_var   [io] u8                 variable index of every column
  *   out_cx    [B, ld_cx] f32|bf16     x * mask (a multiply: -0.0 / NaN propagate like the reference)
  *   out_x     [B, ld_x] f32 or NULL   gathered clean rows
  *   out_mask_id [B] int32 or NULL     mask id applied to every row                              */
-int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t ld_data, const int64_t* batch_idx, int B,
+int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t n_rows, int64_t ld_data, const int64_t* batch_idx, int B,
                       const int16_t* mask_table, int nb_run, int run, const uint64_t* mask_bits,
                       const uint8_t* col_var, int io, void* out_cx, int cx_dtype, int64_t ld_cx, float* out_x,
                       int64_t ld_x, int32_t* out_mask_id, void* stream);

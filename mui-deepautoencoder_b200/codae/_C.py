@@ -35,7 +35,7 @@ SIGNATURES = {
     "codae_weights_written": (_i, [_vp, _vp]),
     "codae_linear_engine": (_i, [_vp, _i, _i, _i, _i]),
     "codae_mask_table_philox": (_i, [_vp, _u64, _i64, _i64, _i, _vp, _vp]),
-    "codae_corrupt_fwd": (_i, [_vp, _vp, _i64, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i64, _vp, _i64, _vp, _vp]),
+    "codae_corrupt_fwd": (_i, [_vp, _vp, _i64, _i64, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _i, _i64, _vp, _i64, _vp, _vp]),
     "codae_dense_masks": (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
     "codae_mul_mask": (_i, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "codae_loss_workspace_bytes": (_sz, [_vp]),
@@ -235,7 +235,7 @@ def corrupt_fwd(data, batch_idx, B, mask_table, run, mask_bits, col_var, io, out
     _dev_check(data, batch_idx, mask_table, out_cx)
     _own_planes(out_cx, B)
     c = ctx(data.device)
-    check(lib().codae_corrupt_fwd(c, p(data), data.stride(0), p(batch_idx), B, p(mask_table), mask_table.shape[1], run,
+    check(lib().codae_corrupt_fwd(c, p(data), data.shape[0], data.stride(0), p(batch_idx), B, p(mask_table), mask_table.shape[1], run,
                                   p(mask_bits), p(col_var), io, p(out_cx), dt(out_cx), ld(out_cx), p(out_x),
                                   0 if out_x is None else out_x.stride(0), p(out_mask_id), stream()), c)
 

@@ -42,6 +42,12 @@ __global__ void mask_table_philox_kernel(uint64_t seed, int64_t first_obs, int64
 }
 
 __device__ __forceinline__ float keep_of(uint64_t bits, uint32_t var) { return ((bits >> var) & 1ull) ? 0.0f : 1.0f; }
+// The row gather is the one place of the step where a caller-supplied index addresses memory: an observation id outside
+// [0, n_rows) traps (reported as a launch failure) instead of reading somebody else's bytes -- the reference raises IndexError.
+__device__ __forceinline__ int64_t checked_obs(int64_t obs, int64_t n_rows) {
+    if ((uint64_t)obs >= (uint64_t)n_rows) __trap();
+    return obs;
+}
 
 // Vector path: io % 4 == 0, all pitches % 4 == 0, 16-byte aligned bases.
 // A group of G = 2^log2g threads (32..256) owns one row at a time: the row's (observation, mask id, mask bits) chain is
@@ -50,7 +56,7 @@ __device__ __forceinline__ float keep_of(uint64_t bits, uint32_t var) { return (
 constexpr int kRowUnroll = 4;
 // kOut: CODAE_F32 / CODAE_BF16 / CODAE_F32X3 (three bf16 planes B * ld_cx elements apart: the operand of the fp32-parity engine)
 template <int kOut>
-__global__ void __launch_bounds__(256) corrupt_fwd_vec_kernel(const float* __restrict__ data, int64_t ld_data,
+__global__ void __launch_bounds__(256) corrupt_fwd_vec_kernel(const float* __restrict__ data, int64_t n_rows, int64_t ld_data,
                                                               const int64_t* __restrict__ batch_idx, int B,
                                                               const int16_t* __restrict__ mask_table, int nb_run, int run,
                                                               const uint64_t* __restrict__ mask_bits,
@@ -68,7 +74,7 @@ __global__ void __launch_bounds__(256) corrupt_fwd_vec_kernel(const float* __res
     int mid = 0;
     uint64_t bits = 0;
     if (row < B) {
-        obs = batch_idx ? batch_idx[row] : (int64_t)row;
+        obs = checked_obs(batch_idx ? batch_idx[row] : (int64_t)row, n_rows);
         mid = mask_table[obs * nb_run + run];
         bits = mask_bits[mid];
     }
@@ -89,7 +95,7 @@ __global__ void __launch_bounds__(256) corrupt_fwd_vec_kernel(const float* __res
                 first_chunk = false;
                 const int nrow = row + row_stride;
                 if (nrow < B) {
-                    n_obs = batch_idx ? batch_idx[nrow] : (int64_t)nrow;
+                    n_obs = checked_obs(batch_idx ? batch_idx[nrow] : (int64_t)nrow, n_rows);
                     n_mid = mask_table[n_obs * nb_run + run];
                     n_bits = mask_bits[n_mid];
                 }
@@ -124,7 +130,7 @@ __global__ void __launch_bounds__(256) corrupt_fwd_vec_kernel(const float* __res
 
 // Scalar path for tabular widths (io = 11 for abalone) and unaligned pitches.
 template <bool kBf16Out>
-__global__ void __launch_bounds__(256) corrupt_fwd_scalar_kernel(const float* __restrict__ data, int64_t ld_data,
+__global__ void __launch_bounds__(256) corrupt_fwd_scalar_kernel(const float* __restrict__ data, int64_t n_rows, int64_t ld_data,
                                                                  const int64_t* __restrict__ batch_idx, int B,
                                                                  const int16_t* __restrict__ mask_table, int nb_run,
                                                                  int run, const uint64_t* __restrict__ mask_bits,
@@ -136,7 +142,7 @@ __global__ void __launch_bounds__(256) corrupt_fwd_scalar_kernel(const float* __
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
         const int row = (int)(e / io);
         const int c = (int)(e - (int64_t)row * io);
-        const int64_t obs = batch_idx ? batch_idx[row] : (int64_t)row;
+        const int64_t obs = checked_obs(batch_idx ? batch_idx[row] : (int64_t)row, n_rows);
         const int mid = mask_table[obs * nb_run + run];
         const float x = data[obs * ld_data + c];
         const float cx = x * keep_of(mask_bits[mid], col_var[c]);
@@ -199,12 +205,12 @@ int codae_mask_table_philox(codae_ctx* ctx, uint64_t seed, int64_t first_obs, in
     return codae_check_launch(ctx, "mask_table_philox_kernel");
 }
 
-int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t ld_data, const int64_t* batch_idx, int B,
+int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t n_rows, int64_t ld_data, const int64_t* batch_idx, int B,
                       const int16_t* mask_table, int nb_run, int run, const uint64_t* mask_bits, const uint8_t* col_var,
                       int io, void* out_cx, int cx_dtype, int64_t ld_cx, float* out_x, int64_t ld_x,
                       int32_t* out_mask_id, void* stream) {
     CODAE_REQUIRE(ctx, ctx && data && mask_table && mask_bits && col_var && out_cx, "codae_corrupt_fwd: NULL argument");
-    CODAE_REQUIRE(ctx, B >= 0 && io >= 1, "codae_corrupt_fwd: bad shape B=%d io=%d", B, io);
+    CODAE_REQUIRE(ctx, B >= 0 && io >= 1 && n_rows >= 1 && (batch_idx || B <= n_rows), "codae_corrupt_fwd: bad shape B=%d io=%d n_rows=%lld", B, io, (long long)n_rows);
     CODAE_REQUIRE(ctx, run >= 0 && run < nb_run, "codae_corrupt_fwd: run %d outside [0, %d)", run, nb_run);
     CODAE_REQUIRE(ctx, ld_data >= io && ld_cx >= io && (!out_x || ld_x >= io), "codae_corrupt_fwd: pitch < io");
     CODAE_REQUIRE(ctx, cx_dtype == CODAE_F32 || cx_dtype == CODAE_BF16 || cx_dtype == CODAE_F32X3, "codae_corrupt_fwd: bad cx_dtype %d", cx_dtype);
@@ -228,15 +234,15 @@ int codae_corrupt_fwd(codae_ctx* ctx, const float* data, int64_t ld_data, const 
         int g = (B + rows_per_cta - 1) / rows_per_cta;
         const int cap = ctx->sm_count * (bf ? occ_bf : (cx_dtype == CODAE_F32X3 ? occ_x3 : occ_f32));
         if (g > cap) g = cap;
-        if (bf) launch_pdl(ctx, corrupt_fwd_vec_kernel<CODAE_BF16>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
-        else if (cx_dtype == CODAE_F32X3) launch_pdl(ctx, corrupt_fwd_vec_kernel<CODAE_F32X3>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
-        else launch_pdl(ctx, corrupt_fwd_vec_kernel<CODAE_F32>, dim3(g), dim3(256), 0, s, data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        if (bf) launch_pdl(ctx, corrupt_fwd_vec_kernel<CODAE_BF16>, dim3(g), dim3(256), 0, s, data, n_rows, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        else if (cx_dtype == CODAE_F32X3) launch_pdl(ctx, corrupt_fwd_vec_kernel<CODAE_F32X3>, dim3(g), dim3(256), 0, s, data, n_rows, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        else launch_pdl(ctx, corrupt_fwd_vec_kernel<CODAE_F32>, dim3(g), dim3(256), 0, s, data, n_rows, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io / 4, log2g, out_cx, ld_cx, out_x, ld_x, out_mask_id);
     } else if (cx_dtype == CODAE_F32X3) {
         return codae_fail(ctx, CODAE_EINVAL, "codae_corrupt_fwd: CODAE_F32X3 output needs io and all pitches to be multiples of 4 and 16-byte aligned buffers");
     } else {
         const int g = grid_for(ctx, (int64_t)B * io, 256, 4);
-        if (bf) corrupt_fwd_scalar_kernel<true><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io, out_cx, ld_cx, out_x, ld_x, out_mask_id);
-        else corrupt_fwd_scalar_kernel<false><<<g, 256, 0, s>>>(data, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        if (bf) corrupt_fwd_scalar_kernel<true><<<g, 256, 0, s>>>(data, n_rows, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io, out_cx, ld_cx, out_x, ld_x, out_mask_id);
+        else corrupt_fwd_scalar_kernel<false><<<g, 256, 0, s>>>(data, n_rows, ld_data, batch_idx, B, mask_table, nb_run, run, mask_bits, col_var, io, out_cx, ld_cx, out_x, ld_x, out_mask_id);
     }
     return codae_check_launch(ctx, "corrupt_fwd_kernel");
 }
