@@ -182,34 +182,24 @@ def test_load_state_dict_refreshes_the_weight_shadow_and_engine_changes_are_refu
         fs.step(torch.arange(B, device=DEV))
 
 
-def test_out_of_range_observation_id_fails_loudly():
-    """The row gather of codae_corrupt_fwd is where a caller-supplied index addresses memory: an id outside [0, n_rows) must stop
-    the kernel (a launch failure surfaced at the next synchronisation) instead of gathering foreign bytes; train_epoch checks its
-    ids up front and raises before anything is launched.  Run in a child process: a trapped kernel ends that process's context."""
-    code = r"""
-import sys, torch
-sys.path.insert(0, %r); sys.path.insert(0, %r)
-from codae.dataset import ConcatenatedEmbeddingDataset
-from codae.model import EmbeddingDenoisingAutoencoder
-from codae.tool import Corrupter, FusedStep
-dev = torch.device("cuda", 0)
-ds = ConcatenatedEmbeddingDataset.from_tensors([torch.randn(256, 64).abs() for _ in range(3)])
-m = EmbeddingDenoisingAutoencoder(192, 192, 64, 2, 2, False); m.to(dev); ds.to(dev)
-fs = FusedStep(m, Corrupter(256, ds.arch, 1, dev, seed=1), ds.data, lr=1e-3, weight_decay=0.0)
-try:
-    fs.train_epoch(torch.arange(200, 300, device=dev), 32)
-    print("EPOCH-NOT-REFUSED")
-except Exception as e:
-    print("EPOCH-REFUSED:", e)
-fs.step(torch.arange(32, device=dev)); torch.cuda.synchronize(); print("GOOD-STEP-OK")
-try:
-    fs.step(torch.arange(240, 272, device=dev)); torch.cuda.synchronize()
-    print("BAD-STEP-NOT-CAUGHT")
-except Exception as e:
-    print("BAD-STEP-CAUGHT:", type(e).__name__)
-""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
-       os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mui-deepautoencoder_b200"))
-    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
-    out = r.stdout
-    assert "EPOCH-REFUSED: Observation index out of range" in out, out + r.stderr[-2000:]
-    assert "GOOD-STEP-OK" in out and "BAD-STEP-CAUGHT" in out and "BAD-STEP-NOT-CAUGHT" not in out, out + r.stderr[-2000:]
+def test_out_of_range_observation_ids_are_refused_before_launch():
+    """The row gather of codae_corrupt_fwd is where a caller-supplied index addresses memory.  train_epoch checks its ids up front
+    and raises before anything is launched (the reference raises IndexError); inside the kernel an id outside [0, n_rows) traps
+    instead of gathering foreign bytes -- that path is deliberately NOT exercised here (a trapped kernel ends the process's CUDA
+    context and shows up in the host's fault log)."""
+    from codae.dataset import ConcatenatedEmbeddingDataset
+    from codae.model import EmbeddingDenoisingAutoencoder
+    from codae.tool import Corrupter, FusedStep
+    ds = ConcatenatedEmbeddingDataset.from_tensors([torch.randn(256, 64).abs() for _ in range(3)])
+    m = EmbeddingDenoisingAutoencoder(192, 192, 64, 2, 2, False)
+    m.to(DEV)
+    ds.to(DEV)
+    fs = FusedStep(m, Corrupter(256, ds.arch, 1, DEV, seed=1), ds.data, lr=1e-3, weight_decay=0.0)
+    before = m.flat.clone()
+    with pytest.raises(Exception, match="Observation index out of range"):
+        fs.train_epoch(torch.arange(200, 300, device=DEV), 32)
+    with pytest.raises(Exception, match="Observation index out of range"):
+        fs.train_epoch(torch.tensor([5, -1, 7], device=DEV), 2)
+    torch.cuda.synchronize()
+    assert torch.equal(before, m.flat)                       # nothing ran
+    assert fs.train_epoch(torch.arange(0, 256, device=DEV), 32) == 8
