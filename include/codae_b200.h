@@ -280,6 +280,14 @@ typedef struct codae_dp_peers {
     const float* grads[CODAE_DP_MAX_WORLD];
     void* w_out[CODAE_DP_MAX_WORLD];
     void* signals[CODAE_DP_MAX_WORLD];
+    /* NVSwitch multicast (NVLS) addresses of the SAME gradient / weight buffers, or NULL.  When both are given the kernel
+     * reduces its shard with one multimem.ld_reduce per 16 bytes (the switch adds the ranks' values: each rank receives its
+     * shard once, not world - 1 times) and broadcasts the new weights with one multicast store per 16 bytes.  The sum is
+     * formed inside the switch instead of in rank order; every rank still reduces only its own shard, so replicas stay
+     * bitwise equal.  Used from 8 ranks on (measured: the multimem path moves fewer bytes but at a lower rate -- slower than the
+     * peer loops at 2 and 4 GPUs, faster at 8); CODAE_DP_NVLS=0|1 overrides.  torch symmetric memory: handle.multicast_ptr. */
+    const float* grads_mc;
+    void* w_mc;
 } codae_dp_peers;
 size_t codae_dp_workspace_bytes(const codae_ctx* ctx);
 int64_t codae_dp_shard_elems(int64_t n, int world);

@@ -82,7 +82,7 @@ class DpPeers(ctypes.Structure):
     """struct codae_dp_peers (include/codae_b200.h): every rank's gradient buffer, weight buffer and signal pad as device
     pointers valid in this process."""
     _fields_ = [("world", _c.c_int32), ("rank", _c.c_int32), ("grads", _vp * DP_MAX_WORLD), ("w_out", _vp * DP_MAX_WORLD),
-                ("signals", _vp * DP_MAX_WORLD)]
+                ("signals", _vp * DP_MAX_WORLD), ("grads_mc", _vp), ("w_mc", _vp)]
 
 
 class TinyLayer(ctypes.Structure):
@@ -356,9 +356,11 @@ def dp_workspace(device):
     return torch.zeros(int(lib().codae_dp_workspace_bytes(c)), dtype=torch.uint8, device=device)
 
 
-def dp_peers(world, rank, grad_ptrs, w_ptrs, signal_ptrs):
+def dp_peers(world, rank, grad_ptrs, w_ptrs, signal_ptrs, grads_mc=0, w_mc=0):
+    """grads_mc / w_mc: NVSwitch multicast addresses of the gradient / weight buffers (0: peer loads and stores)."""
     pe = DpPeers()
     pe.world, pe.rank = world, rank
+    pe.grads_mc, pe.w_mc = (int(grads_mc) or None), (int(w_mc) or None)
     for q in range(world):
         pe.grads[q], pe.w_out[q], pe.signals[q] = int(grad_ptrs[q]), int(w_ptrs[q]), int(signal_ptrs[q])
     return pe

@@ -67,6 +67,7 @@ class FusedStep:
         if self.tc:
             model.refresh_shadow()
         self.dp_mode = None
+        self.dp_nvls = False          # peer mode: reduce / broadcast through NVSwitch multicast addresses
         self._master_stale = False
         self._peers = None
         if world_size > 1:
@@ -175,7 +176,14 @@ class FusedStep:
         self._shard = (min(n, rank * S), min(n, (rank + 1) * S), S)
         self.m = torch.zeros(S, dtype=torch.float32, device=dev)            # moments exist for this rank's shard only
         self.v = torch.zeros(S, dtype=torch.float32, device=dev)
-        self._peers = _C.dp_peers(self.world_size, rank, *ptrs)
+        # NVSwitch multicast (NVLS) addresses of the gradient and weight buffers when the fabric offers them: in-switch reduction
+        mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in handles[:2]]
+        have = torch.tensor([1 if all(mc) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(have, op=dist.ReduceOp.MIN, group=group)            # every rank takes the same path
+        if int(have.item()) == 0:
+            mc = [0, 0]
+        self.dp_nvls = bool(all(mc))
+        self._peers = _C.dp_peers(self.world_size, rank, *ptrs, grads_mc=mc[0], w_mc=mc[1])
         self._symm = (g, w, sig, handles)                                    # keep the mappings alive
         self.dp_ws = _C.dp_workspace(dev)
         self._dp_group = group

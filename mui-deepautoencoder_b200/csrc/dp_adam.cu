@@ -16,6 +16,11 @@
 // Bytes over NVLink per rank and step: (G-1)/G * 4P in + (G-1)/G * 2P out (bf16) instead of 2 (G-1)/G * 4P each way for a ring
 // all-reduce; HBM traffic of the optimizer drops from 30 P to about (4 G + 26) P / G.
 // Cross-GPU waits are bounded (CODAE_DP_TIMEOUT_S, default 30 s): a rank that never arrives traps instead of hanging the GPU.
+//
+// NVLS (peers->grads_mc / w_mc = NVSwitch multicast addresses of the same buffers, e.g. torch symmetric memory's multicast_ptr):
+// phase 1 is ONE multimem.ld_reduce per 16 bytes -- the switch adds the G ranks' values and returns the sum, so a rank receives
+// its shard once instead of G - 1 times -- and phase 2 ONE multimem store per 16 bytes that the switch fans out to every rank.
+// Bytes on this rank's links: 4P/G in + 2P/G (bf16) out instead of (G-1)/G * 4P in + (G-1)/G * 2P out.
 #include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
@@ -43,6 +48,8 @@ struct DpArgs {
     const float* grads[kMaxWorld];
     void* w_out[kMaxWorld];
     unsigned long long* signals[kMaxWorld];
+    const float* grads_mc;       // NVLS multicast address of the gradient buffers (or NULL: peer loads)
+    void* w_mc;                  // NVLS multicast address of the weight buffers (or NULL: peer stores)
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -55,6 +62,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+// NVSwitch in-fabric reduction / fan-out over a multicast address (sm_90+: LDGMC / multicast STG)
+__device__ __forceinline__ float4 multimem_ld_reduce_f4(const float* mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(mc) : "memory");
+    return r;
+}
+__device__ __forceinline__ void multimem_st_f4(float* mc, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st_bf16x8(void* mc, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -112,14 +132,19 @@ __global__ void __launch_bounds__(kThreads) dp_reduce_adam_gather_kernel(float* 
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt4; e += stride) {
             const long long i = lo + 4 * e;
-            float4 part[kMaxWorld];
+            float4 acc;
+            if (a.grads_mc) {
+                acc = multimem_ld_reduce_f4(a.grads_mc + i);          // the switch returns the sum over all ranks
+            } else {
+                float4 part[kMaxWorld];
 #pragma unroll
-            for (int q = 0; q < kMaxWorld; ++q)
-                if (q < world) part[q] = ld_peer_f4(a.grads[q] + i);
-            float4 acc = part[0];
+                for (int q = 0; q < kMaxWorld; ++q)
+                    if (q < world) part[q] = ld_peer_f4(a.grads[q] + i);
+                acc = part[0];
 #pragma unroll
-            for (int q = 1; q < kMaxWorld; ++q)
-                if (q < world) { acc.x += part[q].x; acc.y += part[q].y; acc.z += part[q].z; acc.w += part[q].w; }
+                for (int q = 1; q < kMaxWorld; ++q)
+                    if (q < world) { acc.x += part[q].x; acc.y += part[q].y; acc.z += part[q].z; acc.w += part[q].w; }
+            }
             *reinterpret_cast<float4*>(gmine + i) = acc;
             s0 = fmaf(acc.x, acc.x, s0); s1 = fmaf(acc.y, acc.y, s1); s2 = fmaf(acc.z, acc.z, s2); s3 = fmaf(acc.w, acc.w, s3);
         }
@@ -175,11 +200,18 @@ __global__ void __launch_bounds__(kThreads) dp_reduce_adam_gather_kernel(float* 
             uint4 w;
             w.x = pack_bf16x2(p0.x, p0.y); w.y = pack_bf16x2(p0.z, p0.w);
             w.z = pack_bf16x2(p1.x, p1.y); w.w = pack_bf16x2(p1.z, p1.w);
+            if (a.w_mc) {
+                multimem_st_bf16x8(reinterpret_cast<__nv_bfloat16*>(a.w_mc) + i, w);      // one store, every rank (this one included)
+            } else {
 #pragma unroll
-            for (int q = 0; q < kMaxWorld; ++q)
-                if (q < world) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.w_out[q]) + i) = w;
+                for (int q = 0; q < kMaxWorld; ++q)
+                    if (q < world) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(a.w_out[q]) + i) = w;
+            }
+        } else if (a.w_mc) {
+            // f32 engine: the weight buffer IS the master buffer (w_out[rank] == p): the multicast store updates it here as well
+            multimem_st_f4(reinterpret_cast<float*>(a.w_mc) + i, p0);
+            multimem_st_f4(reinterpret_cast<float*>(a.w_mc) + i + 4, p1);
         } else {
-            // f32 engine: the weight buffer IS the master buffer (w_out[rank] == p)
 #pragma unroll
             for (int q = 0; q < kMaxWorld; ++q)
                 if (q < world) {
@@ -264,6 +296,19 @@ int codae_dp_adam_step(codae_ctx* ctx, const codae_dp_peers* peers, float* p, fl
         a.w_out[q] = in ? peers->w_out[q] : nullptr;
         a.signals[q] = in ? reinterpret_cast<unsigned long long*>(peers->signals[q]) : nullptr;
     }
+    // NVLS when both multicast addresses are given AND the group is large enough for the byte saving to beat the lower throughput of
+    // the multimem path.  Measured on B200s (tools/r02_nvls_ab.sh, r02_nvls_ab8.sh; ms/step, multimem vs peer loops):
+    //   embedding.yaml bf16  2 GPUs 0.464 / 0.394   4 GPUs 0.448 / 0.426   8 GPUs 0.439 / 0.470
+    //   embedding.yaml fp32  2 GPUs 0.830 / 0.647   4 GPUs 0.815 / 0.802   8 GPUs 0.784 / 0.918
+    //   polyvore bf16        2 GPUs 7.99  / 7.70    4 GPUs 7.82  / 7.68    8 GPUs 7.82  / 7.89
+    // CODAE_DP_NVLS = 0 | 1 forces the choice (read once).
+    static const int nvls_env = getenv("CODAE_DP_NVLS") ? atoi(getenv("CODAE_DP_NVLS")) : -1;
+    const bool nvls_on = nvls_env < 0 ? peers->world >= 8 : nvls_env != 0;
+    const bool nvls = nvls_on && peers->grads_mc && peers->w_mc;
+    CODAE_REQUIRE(ctx, !nvls || ((reinterpret_cast<uintptr_t>(peers->grads_mc) | reinterpret_cast<uintptr_t>(peers->w_mc)) & 15) == 0,
+                  "codae_dp_adam_step: multicast addresses must be 16-byte aligned");
+    a.grads_mc = nvls ? peers->grads_mc : nullptr;
+    a.w_mc = nvls ? peers->w_mc : nullptr;
     static int max_blocks_per_sm = 0;
     if (!max_blocks_per_sm) {
         cudaError_t oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks_per_sm, dp_reduce_adam_gather_kernel, kThreads, 0);

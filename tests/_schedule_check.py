@@ -276,7 +276,7 @@ sys.modules["torch.distributed._symmetric_memory"] = _symm
 dist._symmetric_memory = _symm
 _C.dp_shard_elems = lambda n, world: ((n + world - 1) // world + 7) // 8 * 8
 _C.dp_workspace = lambda device: torch.zeros(64, dtype=torch.uint8)
-_C.dp_peers = lambda world, rank, g, w, s: (world, rank, g, w, s)
+_C.dp_peers = lambda world, rank, g, w, s, **kw: (world, rank, g, w, s)
 
 from codae.dataset import ConcatenatedEmbeddingDataset  # noqa: E402
 from codae.model import EmbeddingDenoisingAutoencoder  # noqa: E402

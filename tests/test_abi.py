@@ -107,16 +107,17 @@ def test_dp_peers_struct_layout_matches_header(tmp_path):
     from codae import _C
     src = tmp_path / "layout.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "codae_b200.h"\nint main(void) {\n'
-                   '  printf("%zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(codae_dp_peers), offsetof(codae_dp_peers, world), '
+                   '  printf("%zu %zu %zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(codae_dp_peers), offsetof(codae_dp_peers, world), '
                    'offsetof(codae_dp_peers, rank), offsetof(codae_dp_peers, grads), offsetof(codae_dp_peers, w_out), '
-                   'offsetof(codae_dp_peers, signals), CODAE_DP_MAX_WORLD, CODAE_DP_SIGNAL_BYTES);\n  return 0;\n}\n')
+                   'offsetof(codae_dp_peers, signals), offsetof(codae_dp_peers, grads_mc), offsetof(codae_dp_peers, w_mc), '
+                   'CODAE_DP_MAX_WORLD, CODAE_DP_SIGNAL_BYTES);\n  return 0;\n}\n')
     exe = tmp_path / "layout"
     r = subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True).stdout.split()]
     P = _C.DpPeers
     assert got == [ctypes.sizeof(P), P.world.offset, P.rank.offset, P.grads.offset, P.w_out.offset, P.signals.offset,
-                   _C.DP_MAX_WORLD, _C.DP_SIGNAL_BYTES], got
+                   P.grads_mc.offset, P.w_mc.offset, _C.DP_MAX_WORLD, _C.DP_SIGNAL_BYTES], got
 
 
 def test_dp_shard_arithmetic():
