@@ -278,8 +278,10 @@ class FusedStep:
             _C.tiny_mlp_bwd(self._tiny_layers, model.flat, self.gflat, acts, gbuf, B); n += 1
             return n + self._enqueue_update(b.get("sq_partials"))
         # Backward.  The input-gradient chain dgrad(L-1) -> ... -> dgrad(1) is the critical path; every weight gradient
-        # only needs dL/d(out_l) and the stored activation, so wgrad(l) runs on a second stream next to dgrad(l)
-        # (at B=128 each of these kernels is a ~8 us latency chain that leaves most of the GPU idle).
+        # only needs dL/d(out_l) and the stored activation, so wgrad(l) runs on a second stream next to dgrad(l).
+        # A tcgen05 kernel owns its SM (one CTA per SM whatever its resources), so the two only overlap when their grids fit the
+        # 148 SMs together: the library launches small-batch input gradients as 12 clusters of 8 = 96 CTAs for that reason
+        # (csrc/gemm_tcgen05.cu: pick_bn; embedding.yaml bf16 0.341 -> 0.321 ms/step).
         overlap_comm = self.world_size > 1 and self.overlap_allreduce and self.dp_mode == "nccl"
         if overlap_comm:
             import torch.distributed as dist
