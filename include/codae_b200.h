@@ -70,9 +70,15 @@ int codae_ctx_sm_count(const codae_ctx* ctx);
  *                     bit; measured 98.8 -> 64.2 us for the ten weight gradients of the embedding.yaml step.
  *   CODAE_OPT_TMA_STORE_PERSISTENT  (default on: 7.155 -> 6.970 ms/step at 10 x 4096^2, B = 8192) the same for the persistent kernel
  *                     of the large contractions: every epilogue warp stages 32 rows x 128 bytes per store in one of two
- *                     boxes of its own and issues the bulk store itself (f32 and bf16 outputs, all fused epilogues). */
+ *                     boxes of its own and issues the bulk store itself (f32 and bf16 outputs, all fused epilogues).
+ *   CODAE_OPT_CTA_PAIR  (default on) 256-wide persistent contractions run as CTA PAIRS: a cluster of two CTAs on one TPC works
+ *                     on a 256 x 256 tile with tcgen05.mma.cta_group::2 (M = 256) -- each CTA stages its own 128 rows of A and
+ *                     only HALF of B (32 KB instead of 48 KB of shared-memory traffic per k-block, six ring slots instead of
+ *                     four), the leader issues the MMAs, each CTA drains its own half of the accumulator.  Same k order per
+ *                     output element, bit-identical results; measured on a B200 at M = 8192, 4096 x 4096: fwd 1443 -> 1645,
+ *                     dgrad 1364 -> 1569, wgrad 1215 -> 1406 TFLOP/s; polyvore-shaped step 7.55 -> 6.60-6.75 ms. */
 enum codae_option { CODAE_OPT_SPLITK = 0, CODAE_OPT_PDL = 1, CODAE_OPT_PERSISTENT = 2, CODAE_OPT_WEIGHT_PREFETCH = 3,
-                    CODAE_OPT_TMA_STORE = 4, CODAE_OPT_TMA_STORE_PERSISTENT = 5 };
+                    CODAE_OPT_TMA_STORE = 4, CODAE_OPT_TMA_STORE_PERSISTENT = 5, CODAE_OPT_CTA_PAIR = 6 };
 int codae_ctx_set_option(codae_ctx* ctx, int option, int value);
 /* Tells the library that `stream` has just been made to wait (event / stream wait) for work on ANOTHER stream that writes
  * layer weights -- e.g. an optimizer launch on a side stream.  The next launch on `stream` is then issued with a full stream

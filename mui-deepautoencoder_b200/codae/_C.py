@@ -140,7 +140,7 @@ def ctx(device=None):
     return c
 
 
-OPT_SPLITK, OPT_PDL, OPT_PERSISTENT, OPT_WEIGHT_PREFETCH, OPT_TMA_STORE, OPT_TMA_STORE_PERSISTENT = 0, 1, 2, 3, 4, 5
+OPT_SPLITK, OPT_PDL, OPT_PERSISTENT, OPT_WEIGHT_PREFETCH, OPT_TMA_STORE, OPT_TMA_STORE_PERSISTENT, OPT_CTA_PAIR = 0, 1, 2, 3, 4, 5, 6
 
 
 def set_option(device, option, value):

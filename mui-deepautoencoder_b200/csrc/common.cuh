@@ -23,6 +23,7 @@ struct codae_ctx {
     int weight_prefetch; // 1: fwd / dgrad GEMMs issue the TMA loads of their WEIGHT tiles before griddepcontrol.wait
     int tma_store;       // 1: single-pass f32 output tiles leave through TMA bulk stores (default on)
     int tma_store_persistent;  // 1: the persistent kernel's epilogue warps store through per-warp TMA boxes (default on)
+    int cta_pair;        // 1: 256-wide persistent contractions run as CTA pairs (cta_group::2 MMAs on 256 x 256 tiles)
     int weights_dirty;   // a weight-writing kernel (Adam, clip+Adam, bf16 cast) was the last codae launch on dirty_stream
     cudaStream_t dirty_stream;
     std::mutex mu;

@@ -87,6 +87,11 @@ int codae_ctx_create(int device, codae_ctx** out) {
         const char* e = getenv("CODAE_TMA_STORE_PERSISTENT");
         c->tma_store_persistent = e ? (atoi(e) != 0) : 1;   // default on: 7.155 -> 6.970 ms/step at 10 x 4096^2, B = 8192
     }
+    {   // default on: the three contractions of a 4096-wide layer at B = 8192 ran 0.190 / 0.202 / 0.226 ms (fwd / dgrad / wgrad)
+        // single-CTA and 0.167 / 0.175 / 0.196 ms as pairs, bit-identical; polyvore-shaped step 7.55 -> 6.60-6.75 ms
+        const char* e = getenv("CODAE_CTA_PAIR");
+        c->cta_pair = e ? (atoi(e) != 0) : 1;
+    }
     c->weights_dirty = 0;
     c->dirty_stream = nullptr;
     void* fn = nullptr;
@@ -115,6 +120,7 @@ int codae_ctx_set_option(codae_ctx* ctx, int option, int value) {
     else if (option == CODAE_OPT_WEIGHT_PREFETCH) ctx->weight_prefetch = value ? 1 : 0;
     else if (option == CODAE_OPT_TMA_STORE) ctx->tma_store = value ? 1 : 0;
     else if (option == CODAE_OPT_TMA_STORE_PERSISTENT) ctx->tma_store_persistent = value ? 1 : 0;
+    else if (option == CODAE_OPT_CTA_PAIR) ctx->cta_pair = value ? 1 : 0;
     else return codae_fail(ctx, CODAE_EINVAL, "codae_ctx_set_option: unknown option %d", option);
     return CODAE_OK;
 }
@@ -134,6 +140,7 @@ int codae_ctx_get_option(const codae_ctx* ctx, int option) {
         case CODAE_OPT_WEIGHT_PREFETCH: return ctx->weight_prefetch;
         case CODAE_OPT_TMA_STORE: return ctx->tma_store;
         case CODAE_OPT_TMA_STORE_PERSISTENT: return ctx->tma_store_persistent;
+        case CODAE_OPT_CTA_PAIR: return ctx->cta_pair;
         default: return CODAE_EINVAL;
     }
 }

@@ -642,12 +642,31 @@ __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int
     n_idx = r / gm;
 }
 
-template <int BN>
+//
+// kPair (BN = 256, launched as clusters of 2 along x): a CTA PAIR works on one 256 x 256 tile with cta_group::2 MMAs.  CTA r of
+// the pair stages its own 128 rows of A and its own HALF (128 columns) of B -- 32 KB per k-block instead of 48 KB, six ring
+// slots instead of four --, the leader (cluster rank 0) issues one 256 x 256 x 16 MMA per k-step that reads both CTAs' shared
+// memory and leaves rows 0..127 of the accumulator in the leader's TMEM and rows 128..255 in the peer's; every CTA drains its
+// own 128 x 256 half exactly like the single-CTA kernel.  Barriers: the full barriers live in the leader and count both CTAs'
+// TMA bytes (the peer's loads name the leader's barrier, cp.async.bulk.tensor.cta_group::2); empty and accumulator-full
+// barriers are per CTA and signalled by multicast tcgen05.commit; the leader's accumulator-empty barriers take the arrivals of
+// all eight epilogue warps of the pair.  Same k order per output element as the single-CTA kernel.
+template <int BN, bool kPair = false>
+struct PCfg {
+    static_assert(!kPair || BN == 256, "CTA pairs work on 256 x 256 tiles");
+    static constexpr uint32_t kBTileBytes = (kPair ? BN / 2 : BN) * BK * 2;      // this CTA's share of B
+    static constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
+    static constexpr int kStages = kPair ? 6 : Cfg<BN>::kStages;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const __grid_constant__ CUtensorMap tma_a,
                                                                            const __grid_constant__ CUtensorMap tma_b,
                                                                            const __grid_constant__ CUtensorMap tma_c,
                                                                            const Params p) {
-    using C = Cfg<BN>;
+    using C = PCfg<BN, kPair>;
+    constexpr int kRowsPerTile = kPair ? 2 * BM : BM;         // rows of the tile a CTA (pair) works on
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     constexpr int kS = C::kStages;
@@ -662,22 +681,30 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+    const int tiles_m = (p.M + kRowsPerTile - 1) / kRowsPerTile, tiles_n = (p.N + BN - 1) / BN;
     const int total_tiles = tiles_m * tiles_n;
     const int num_kb = (p.K + BK - 1) / BK;
+    // work items: a CTA (kPair: a pair) walks tiles worker, worker + num_workers, ...
+    const int rank = kPair ? (int)cluster_ctarank() : 0;
+    const int worker = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int num_workers = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_a)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_b)) : "memory");
         if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tma_c)) : "memory");
         for (int s = 0; s < kS; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], 4); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full_bar[a], 1); mbar_init(&tmem_empty_bar[a], kPair ? 8 : 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    if (warp == 1) {
+        if constexpr (kPair) tmem_alloc_pair(tmem_slot, 2 * BN);
+        else tmem_alloc(tmem_slot, 2 * BN);
+    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync();      // the peer's barriers are initialised before anything is signalled across the pair
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
@@ -687,49 +714,77 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            for (int t = worker; t < total_tiles; t += num_workers) {
                 int m_idx, n_idx;
                 tile_coords(t, tiles_m, tiles_n, p.group_m, m_idx, n_idx);
-                const int m0 = m_idx * BM, n0 = n_idx * BN;
-                for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == kS ? 0 : s + 1), ph ^= (s == 0)) {
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* a_dst = smem + s * C::kStageBytes;
-                    uint8_t* b_dst = a_dst + kATileBytes;
-                    mbar_expect_tx(&full_bar[s], C::kStageBytes);
-                    const int k0 = kb * BK;
-                    if (p.a_kmajor) {
-                        tma_load_2d(&tma_a, &full_bar[s], a_dst, k0, m0);
-                    } else {
-                        tma_load_2d(&tma_a, &full_bar[s], a_dst, m0, k0);
-                        tma_load_2d(&tma_a, &full_bar[s], a_dst + 8192, m0 + 64, k0);
+                const int m0 = m_idx * kRowsPerTile + rank * BM, n0 = n_idx * BN;
+                if constexpr (kPair) {
+                    // this CTA's half of B: columns [n0 + rank n_half, + n_half) of the n_eff columns the pair's MMA covers
+                    const int n_half = min(BN, ((p.N - n0) + 31) & ~31) >> 1;
+                    const int nb0 = n0 + rank * n_half;
+                    for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == kS ? 0 : s + 1), ph ^= (s == 0)) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);                       // own slot drained (multicast commit of the leader)
+                        uint8_t* a_dst = smem + s * C::kStageBytes;
+                        uint8_t* b_dst = a_dst + kATileBytes;
+                        if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * C::kStageBytes);   // the leader's barrier counts both CTAs' bytes
+                        const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);
+                        const int k0 = kb * BK;
+                        if (p.a_kmajor) {
+                            tma_load_2d_pair(&tma_a, bar, a_dst, k0, m0);
+                        } else {
+                            tma_load_2d_pair(&tma_a, bar, a_dst, m0, k0);
+                            tma_load_2d_pair(&tma_a, bar, a_dst + 8192, m0 + 64, k0);
+                        }
+                        if (p.b_kmajor) {
+                            tma_load_2d_pair(&tma_b, bar, b_dst, k0, nb0);                  // box {64 k, 128 n}
+                        } else {
+                            tma_load_2d_pair(&tma_b, bar, b_dst, nb0, k0);                  // box {64 n, 64 k} x 2
+                            tma_load_2d_pair(&tma_b, bar, b_dst + 8192, nb0 + 64, k0);
+                        }
                     }
-                    if (p.b_kmajor) {
-                        tma_load_2d(&tma_b, &full_bar[s], b_dst, k0, n0);
-                    } else {
+                } else {
+                    for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == kS ? 0 : s + 1), ph ^= (s == 0)) {
+                        mbar_wait(&empty_bar[s], ph ^ 1);
+                        uint8_t* a_dst = smem + s * C::kStageBytes;
+                        uint8_t* b_dst = a_dst + kATileBytes;
+                        mbar_expect_tx(&full_bar[s], C::kStageBytes);
+                        const int k0 = kb * BK;
+                        if (p.a_kmajor) {
+                            tma_load_2d(&tma_a, &full_bar[s], a_dst, k0, m0);
+                        } else {
+                            tma_load_2d(&tma_a, &full_bar[s], a_dst, m0, k0);
+                            tma_load_2d(&tma_a, &full_bar[s], a_dst + 8192, m0 + 64, k0);
+                        }
+                        if (p.b_kmajor) {
+                            tma_load_2d(&tma_b, &full_bar[s], b_dst, k0, n0);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tma_b, &full_bar[s], b_dst + j * 8192, n0 + 64 * j, k0);
+                            for (int j = 0; j < BN / 64; ++j) tma_load_2d(&tma_b, &full_bar[s], b_dst + j * 8192, n0 + 64 * j, k0);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: tile i accumulates into TMEM buffer i & 1 =====
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {                 // kPair: the leader issues the pair's MMAs
             const uint32_t a_adv = p.a_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
             const uint32_t b_adv = p.b_kmajor ? (UMMA_K * 2) : (UMMA_K * 128);
             int s = 0;
             uint32_t ph = 0;
             int it = 0;
-            for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+            for (int t = worker; t < total_tiles; t += num_workers, ++it) {
                 int m_idx, n_idx;
                 tile_coords(t, tiles_m, tiles_n, p.group_m, m_idx, n_idx);
                 // a ragged last column tile (the bias column of the augmented weight gradient: 1 of 256 columns) only
-                // pays for the MMA width it needs (multiples of 16)
-                const int n_eff = min(BN, ((p.N - n_idx * BN) + 15) & ~15);
-                const uint32_t idesc = make_idesc(n_eff, p.a_kmajor != 0, p.b_kmajor != 0);
+                // pays for the MMA width it needs (multiples of 16; a pair: multiples of 32, half from each CTA)
+                const int n_eff = kPair ? min(BN, ((p.N - n_idx * BN) + 31) & ~31) : min(BN, ((p.N - n_idx * BN) + 15) & ~15);
+                const uint32_t idesc = make_idesc(n_eff, p.a_kmajor != 0, p.b_kmajor != 0, kRowsPerTile);
                 const int acc = it & 1;
                 const uint32_t acc_ph = (it >> 1) & 1;
-                mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);          // epilogue has drained this buffer (first use: free)
+                // epilogue has drained this buffer (first use: free); kPair: the warps of both CTAs
+                if constexpr (kPair) mbar_wait_cluster(&tmem_empty_bar[acc], acc_ph ^ 1);
+                else mbar_wait(&tmem_empty_bar[acc], acc_ph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
                 for (int kb = 0; kb < num_kb; ++kb, s = (s + 1 == kS ? 0 : s + 1), ph ^= (s == 0)) {
@@ -739,12 +794,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
                     const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
-                        umma_bf16(d_tmem, make_desc(a_addr + k * a_adv, p.a_kmajor != 0),
-                                  make_desc(b_addr + k * b_adv, p.b_kmajor != 0), idesc, (kb | k) != 0);
+                        const uint64_t ad = make_desc(a_addr + k * a_adv, p.a_kmajor != 0), bd = make_desc(b_addr + k * b_adv, p.b_kmajor != 0);
+                        if constexpr (kPair) umma_bf16_pair(d_tmem, ad, bd, idesc, (kb | k) != 0);
+                        else umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[s]);
+                    if constexpr (kPair) umma_commit_pair(&empty_bar[s]);
+                    else umma_commit(&empty_bar[s]);
                 }
-                umma_commit(&tmem_full_bar[acc]);
+                if constexpr (kPair) umma_commit_pair(&tmem_full_bar[acc]);
+                else umma_commit(&tmem_full_bar[acc]);
             }
         }
     } else {
@@ -761,12 +819,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
         const int n4 = p.N & ~tail_mask;
         uint8_t* wbuf = stage_base + q * 8192;
         int unit = 0;
-        for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+        for (int t = worker; t < total_tiles; t += num_workers, ++it) {
             const int acc = it & 1;
             const uint32_t acc_ph = (it >> 1) & 1;
             int m_idx, n_idx;
             tile_coords(t, tiles_m, tiles_n, p.group_m, m_idx, n_idx);
-            const int m0 = m_idx * BM, n0 = n_idx * BN;
+            const int m0 = m_idx * kRowsPerTile + rank * BM, n0 = n_idx * BN;
             mbar_wait(&tmem_full_bar[acc], acc_ph);
             tc_fence_after();
             const int row = m0 + q * 32 + lane;
@@ -780,7 +838,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
                     // every column of this buffer is in registers: hand it back to the MMA warp before the last stores
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                    if (lane == 0) {
+                        if constexpr (kPair) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty_bar[acc]), 0));   // the leader's barrier
+                        else mbar_arrive(&tmem_empty_bar[acc]);
+                    }
                 }
                 const int col0 = n0 + c * 32;
                 if (!tma_st) {
@@ -851,10 +912,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc05_gemm_persistent_kernel(const
         if (p.sq_partial) sq_partial_store(p.sq_partial + blockIdx.x, sq_acc, sq_red);
     }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (kPair) cluster_sync();      // neither CTA leaves (or frees TMEM) while the other may still signal or write into it
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        if constexpr (kPair) tmem_dealloc_pair(tmem_base, 2 * BN);
+        else tmem_dealloc(tmem_base, 2 * BN);
     }
 }
 
@@ -887,6 +950,7 @@ struct Plan {
     int nsplit;        // cluster split-K factor (grid z)
     bool staged;       // epilogue through the shared-memory tile
     bool persistent;   // one CTA per SM walking tiles
+    bool pair = false; // persistent kernel as CTA pairs (cta_group::2, 256 x 256 tiles)
     int gx, gy;        // output tiles along N and M
     int ctas;          // CTAs the launch will have (= sum-of-squares slots it writes)
     int stages = 0;    // NP == 3: pipeline depth chosen by x3_geometry (0: the launch code's default)
@@ -994,7 +1058,8 @@ Plan make_plan(const codae_ctx* ctx, const Tc05Gemm& g) {
     // (measured: the direct epilogue is faster for the 4096-wide weight gradients, 247 vs 261 us)
     pl.staged = nsplit > 1 || (g.c_dtype == CODAE_F32 && tiles <= 2 * ctx->sm_count);
     pl.persistent = NP == 1 && nsplit == 1 && !pl.staged && ctx->persistent && tiles > 2 * ctx->sm_count;
-    pl.ctas = pl.persistent ? ctx->sm_count : tiles * nsplit;
+    pl.pair = pl.persistent && BN == 256 && ctx->cta_pair && ctx->sm_count >= 2;
+    pl.ctas = pl.persistent ? (pl.pair ? (ctx->sm_count & ~1) : ctx->sm_count) : tiles * nsplit;
     return pl;
 }
 
@@ -1042,8 +1107,13 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
     if constexpr (NP == 1) if (pl.persistent) {
         static bool pattr_set = false;
         if (!pattr_set) {
-            cudaError_t e = cudaFuncSetAttribute(tc05_gemm_persistent_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaError_t e = cudaFuncSetAttribute(tc05_gemm_persistent_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  (int)(C::kSmemBytes + kPersistentStageBytes));
+            if constexpr (BN == 256) {
+                if (e == cudaSuccess)
+                    e = cudaFuncSetAttribute(tc05_gemm_persistent_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(PCfg<BN, true>::kSmemBytes + kPersistentStageBytes));
+            }
             if (e != cudaSuccess) return codae_fail(ctx, CODAE_ECUDA, "cudaFuncSetAttribute(smem=%u): %s", C::kSmemBytes + kPersistentStageBytes, cudaGetErrorString(e));
             pattr_set = true;
         }
@@ -1063,7 +1133,45 @@ int launch(codae_ctx* ctx, const Tc05Gemm& g, cudaStream_t s) {
         }
         p.group_m = env_group_m;
         p.stages = C::kStages;
-        cudaError_t le = launch_pdl(ctx, tc05_gemm_persistent_kernel<BN>, dim3(ctx->sm_count), dim3(kThreads),
+        static const bool debug_persistent = getenv("CODAE_DEBUG_PLAN") != nullptr;
+        if (debug_persistent)
+            fprintf(stderr, "codae plan: M=%d N=%d K=%d BN=%d persistent pair %d tma_store %d ctas %d\n", g.M, g.N, g.K, BN, (int)pl.pair,
+                    p.tma_store, pl.ctas);
+        if constexpr (BN == 256) if (pl.pair) {
+            // CTA pairs: 256-row tiles (raster groups of group_m / 2 of them), this CTA's B box is 128 columns wide
+            using PC = PCfg<BN, true>;
+            p.group_m = env_group_m > 1 ? env_group_m / 2 : 1;
+            p.stages = PC::kStages;
+            if (g.b_kmajor) {
+                rc = make_map(ctx, &mb, g.B, g.N, g.K, g.ldb, BK, BN / 2);
+                if (rc) return rc;
+            }
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(pl.ctas);
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = PC::kSmemBytes + (p.tma_store ? kPersistentStageBytes : 0);
+            cfg.stream = s;
+            cudaLaunchAttribute attr[2];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            int na = 1;
+            if (codae_pdl_allowed(ctx, s)) {
+                attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[na].val.programmaticStreamSerializationAllowed = 1;
+                ++na;
+            }
+            cfg.attrs = attr;
+            cfg.numAttrs = na;
+            cudaError_t le = cudaLaunchKernelEx(&cfg, tc05_gemm_persistent_kernel<BN, true>, ma, mb, mc, p);
+            if (le != cudaSuccess) {
+                cudaGetLastError();
+                return codae_fail(ctx, CODAE_ECUDA, "tc05_gemm_persistent_kernel<%d, pair> launch: %s", BN, cudaGetErrorString(le));
+            }
+            return codae_check_launch(ctx, "tc05_gemm_persistent_kernel<pair>");
+        }
+        cudaError_t le = launch_pdl(ctx, tc05_gemm_persistent_kernel<BN, false>, dim3(ctx->sm_count), dim3(kThreads),
                                     C::kSmemBytes + (p.tma_store ? kPersistentStageBytes : 0), s, ma, mb, mc, p);
         if (le != cudaSuccess) {
             cudaGetLastError();

@@ -102,6 +102,17 @@ print("RAGGED OK")
     assert r.returncode == 0 and "RAGGED OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
 
 
+def test_cta_pair_persistent_kernel_is_bit_identical():
+    """CODAE_OPT_CTA_PAIR (default on): the persistent kernel as CTA pairs (tcgen05.mma.cta_group::2 on 256 x 256 tiles, the
+    peer's TMA loads counted on the leader's barriers, multicast commits) against the single-CTA persistent kernel -- forward
+    (ReLU bf16 / plain f32), masked input gradient and weight gradient + its sum of squares, ragged row tiles, a peer CTA whose
+    rows are all out of range, ragged column tiles (bias-gradient column, n_eff = 32 / 64 / 96): same bits, guard rows and
+    padding columns untouched; the weight gradients also against fp64 products (tools/probes/cta_pair_check.py)."""
+    r = subprocess.run([sys.executable, os.path.join(HERE, "..", "tools", "probes", "cta_pair_check.py")], capture_output=True,
+                       text=True, timeout=240)
+    assert r.returncode == 0 and "PAIR OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
 @pytest.mark.parametrize("name", ["abalone_k1", "abalone_k3"])
 def test_tiny_mlp_abalone_matches_reference(name):
     """FusedStep(tiny_mlp=True): the abalone model's forward and backward passes as one launch each (codae_tiny_mlp_fwd / _bwd)
