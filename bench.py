@@ -683,6 +683,13 @@ def profile_step(fs, idx, B, world, name):
                         "tensor pipe; latency-bound in practice, see DESIGN.md section 7" if small else
                         ("useful fp32 flops vs 1/6 of the sustained cuBLAS bf16 peak (six bf16 MMAs per fp32 product)" if x3 else
                          "dense bf16 contraction vs the sustained cuBLAS bf16 peak")}
+        if bf and bound == "tensor":
+            # the same rate against cuBLAS's BURST figure (best single 8192^3 launch; the launches of a step run back to back, so the
+            # sustained figure is the denominator of `frac`) and against the nominal dense bf16 peak of the part
+            roof["frac_of_burst_peak"] = ach / pk["tensor"]
+            roof["frac_of_nominal_2250"] = ach / 2250.0
+            if os.environ.get("CODAE_CTA_PAIR", "1") != "0" and "persistent" in roof["kernel"]:
+                roof["kernel"] = "tc05_gemm_persistent_kernel<256, CTA pair> (fwd + dgrad + wgrad launches; cta_group::2, 256 x 256 tiles)"
         if x3 and bound == "hbm":
             # the same time against the fp32 information content (4 B per weight / activation element instead of the triple's 6)
             roof["frac_at_fp32_bytes"] = roof["frac"] * 4.0 / 6.0
