@@ -32,6 +32,17 @@ def test_header_vs_ctypes_table():
         assert len(_C.SIGNATURES[name][1]) == n, name
 
 
+def test_option_enum_matches_python_constants():
+    """enum codae_option in the header vs the OPT_* constants the Python side passes to codae_ctx_set_option."""
+    from codae import _C
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    body = re.search(r"enum\s+codae_option\s*\{(.*?)\}", src, flags=re.S).group(1)
+    enum = {m.group(1): int(m.group(2)) for m in re.finditer(r"CODAE_(OPT_\w+)\s*=\s*(\d+)", body)}
+    assert len(enum) >= 7 and sorted(enum.values()) == list(range(len(enum)))
+    for name, value in enum.items():
+        assert getattr(_C, name) == value, name
+
+
 def test_library_exports_every_symbol():
     from codae import _C
     lib = _C.lib()
