@@ -26,7 +26,8 @@
 //
 // Large problems (more than 2 output tiles per SM) use tc05_gemm_persistent_kernel further down: one CTA per SM walks
 // tiles in L2-friendly groups, the accumulator is double-buffered in TMEM so that the epilogue of tile i overlaps the
-// MMAs of tile i+1, and the shared-memory ring keeps running across tile boundaries.
+// MMAs of tile i+1, and the shared-memory ring keeps running across tile boundaries.  Its 256-wide form runs as CTA PAIRS
+// (tcgen05.mma.cta_group::2 on 256 x 256 tiles, see the comment above PCfg).
 #include <cuda.h>
 #include <stdlib.h>
 
